@@ -1,0 +1,255 @@
+/* tbi_sm100.h -- C ABI of libtbi_sm100.so: the B200 (sm_100a) kernels under the TBI_ResNest hot path.
+ *
+ * The reference (silverlight6/Ultrasound_Modeling) has no FFI layer: its model code calls
+ * tf.keras.layers.* directly and TensorFlow picks cuDNN/XLA kernels.  This ABI sits where those
+ * library kernels sat.  Each entry point names the reference call site(s) it replaces.
+ *
+ * Conventions:
+ *   - activations NHWC, contiguous; a tensor may be addressed as a channel slice of a wider
+ *     pixel record (cstride = elements per pixel record, coff = first channel), which is how
+ *     tf.concat (TBI_ResNest.py:110-122,139) is never materialised;
+ *   - the caller owns every buffer, including workspaces; the library never allocates, frees or
+ *     synchronises; every call enqueues on the cudaStream_t it is handed (passed as void*);
+ *   - every call returns 0 or a negative TBI_ERR_*; tbi_last_error() gives the thread-local text;
+ *     an unsupported shape is an error, never a fallback;
+ *   - dtype is the STORAGE type of activations and packed weights (TBI_F32 | TBI_BF16);
+ *     accumulation is always fp32; parameter gradients and optimizer state are always fp32.
+ */
+#ifndef TBI_SM100_H
+#define TBI_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TBI_VERSION 100
+
+enum { TBI_OK = 0, TBI_ERR_BAD_SHAPE = -1, TBI_ERR_BAD_ALIGN = -2, TBI_ERR_UNSUPPORTED = -3, TBI_ERR_CUDA = -4 };
+enum { TBI_F32 = 0, TBI_BF16 = 1 };
+enum { TBI_ACT_NONE = 0, TBI_ACT_ELU = 1, TBI_ACT_LRELU = 2 /* slope 0.3 */, TBI_ACT_RELU = 3 };
+/* which implementation executes a tap-GEMM: AUTO picks tcgen05 when the shape qualifies */
+enum { TBI_IMPL_AUTO = 0, TBI_IMPL_SIMT = 1, TBI_IMPL_TCGEN05 = 2 };
+
+#define TBI_MAX_TAPS 16
+
+/* A (possibly strided) channel-slice view of an NHWC tensor. */
+typedef struct {
+    void*   ptr;       /* base of the tensor (element 0 of pixel 0)                    */
+    int32_t h, w;      /* spatial dims                                                 */
+    int32_t c;         /* channels in this view                                        */
+    int32_t cstride;   /* elements per pixel record (>= coff + c)                      */
+    int32_t coff;      /* first channel of the view inside the record                  */
+} tbi_view;
+
+/* Fused epilogue of a tap-GEMM, applied to the fp32 accumulator v of output element (pixel, co):
+ *   v += bias[co]                        (bias != NULL; BN-affine is folded into weights+bias)
+ *   v *= keep[pixel,co]                  (drop_keep != NULL; uint8 MULTIPLIER: 0 = dropped, 2 = kept (1/(1-rate)),
+ *                                         1 = dropout disabled; tf.nn.dropout(x,0.5), TBI_ResNest.py:216)
+ *   v  = act(v)
+ *   v += residual[pixel,co]              (residual.ptr != NULL; may alias out -> accumulate)
+ *   v *= act'(dact_ref[pixel,co]) [* dact_keep]     (dact != NONE; derivative from the stored
+ *                                         forward OUTPUT; fuses the previous layer's activation
+ *                                         backward into this dgrad)
+ * Output channels >= split_c go to out2 instead (dgrad of a virtual concat); out2 takes only the
+ * residual2 add (accumulation of a skip-connection gradient), no dact.
+ */
+typedef struct {
+    const float*   bias;
+    const uint8_t* drop_keep;     /* indexed like out (dense, c == cstride)                   */
+    int32_t        act;
+    tbi_view       residual;      /* ptr NULL = none                                          */
+    int32_t        dact;          /* TBI_ACT_* whose derivative to apply, from dact_ref       */
+    tbi_view       dact_ref;
+    const uint8_t* dact_keep;     /* dropout keep-mask that followed dact_ref's layer, or NULL */
+    tbi_view       out;           /* h,w = dims of the output tensor                          */
+    int32_t        out_f32;       /* 1: out is float32 whatever dtype is (head logits)        */
+    int32_t        out_stride;    /* 1, or 2 for a transposed-conv phase                      */
+    int32_t        out_off_y, out_off_x;
+    int32_t        split_c;       /* 0 = no split                                             */
+    tbi_view       out2;
+    tbi_view       residual2;
+} tbi_epilogue;
+
+/* One tap-GEMM:  acc[pixel p=(n,gy,gx)][co] = sum_tap sum_ci  in[n, gy*in_stride+dy[tap], gx*in_stride+dx[tap], ci]
+ *                                                          * w[co][tap*cin_g + ci]
+ * (out-of-range input pixels read as 0).  The input is the virtual concat of src[0] and src[1]
+ * along channels.  groups > 1: input channel block g feeds output channel block g (single source).
+ * Packed weights are K-major: [cout_total][ntaps*cin_g] in `dtype`.
+ * Every convolution of the path is a list of these (tbi_conv2d_* / tbi_conv2d_transpose_s2_* build them).
+ */
+typedef struct {
+    int32_t  dtype;
+    int32_t  impl;             /* TBI_IMPL_*                                                  */
+    int32_t  n, gh, gw;        /* pixel grid (GEMM M = n*gh*gw)                               */
+    int32_t  groups;
+    int32_t  cin_g, cout_g;    /* per-group K channels (sum over sources) and output channels */
+    tbi_view src[2];           /* src[1].ptr NULL = single source                             */
+    int32_t  in_stride;        /* 1, or 2 (dgrad of a stride-2 transposed conv)               */
+    int32_t  ntaps;
+    int32_t  dy[TBI_MAX_TAPS], dx[TBI_MAX_TAPS];
+    const void* w;
+    tbi_epilogue epi;
+} tbi_tapgemm;
+
+/* Weight-gradient tap-GEMM (fp32 accumulate, atomically ADDED into dw, which the caller zeroes):
+ *   dw[tap*tap_stride + ci*ci_stride + co*co_stride] +=
+ *        sum_p a[n, gy*a_stride+a_dy[tap], gx*a_stride+a_dx[tap], ci] * b[n, gy*b_stride+b_dy[tap], gx*b_stride+b_dx[tap], co]
+ * a = forward input (virtual concat of a_src[0..1]), b = gradient w.r.t. the pre-activation output.
+ * groups as above (ci in [0,cin_g) of group g pairs with co in group g; ci index in dw is group-local,
+ * co index is global).  dw strides let the result land directly in Keras HWIO / HWOI layout.
+ */
+typedef struct {
+    int32_t  dtype;
+    int32_t  impl;
+    int32_t  n, gh, gw;
+    int32_t  groups, cin_g, cout_g;
+    tbi_view a_src[2];
+    tbi_view b_src;
+    int32_t  a_stride, b_stride;
+    int32_t  ntaps;
+    int32_t  a_dy[TBI_MAX_TAPS], a_dx[TBI_MAX_TAPS], b_dy[TBI_MAX_TAPS], b_dx[TBI_MAX_TAPS];
+    float*   dw;
+    int64_t  tap_stride, ci_stride, co_stride;
+    float*   dbias;            /* optional: dbias[co] += sum_p b[p,co]  (computed once, tap 0)    */
+    void*    workspace;        /* tcgen05 split-K partials; tbi_workspace_bytes() tells how much  */
+    int64_t  workspace_bytes;
+} tbi_tapwgrad;
+
+int         tbi_version(void);
+const char* tbi_last_error(void);
+/* 1 if the running device is sm_100 and the tcgen05 kernels can launch; 0 otherwise */
+int         tbi_device_ok(void);
+
+/* ---- convolutions ------------------------------------------------------------------------
+ * tbi_tapgemm_run / tbi_tapwgrad_run are the single execution entry points; the named conv
+ * entry points below fill the descriptors for the shapes the reference uses and call them.
+ * replaces: tf.keras.layers.Conv2D fwd + its GradientTape input/filter gradients
+ *           (TBI_ResNest.py:83-91,140,143,162-168; ResNest.py:14-24,77-85,122-131; Decoder.py:11-25,103)
+ */
+int tbi_tapgemm_run(const tbi_tapgemm* d, void* stream);
+int tbi_tapwgrad_run(const tbi_tapwgrad* d, void* stream);
+int64_t tbi_workspace_bytes(const tbi_tapwgrad* d);
+
+/* Conv2D k in {1,3}, stride 1, SAME, dilation in {1,2,4,8}, groups >= 1, <= 2 sources.
+ * w_packed: see tbi_pack_conv_weights (mode FWD for fwd, DGRAD for dgrad).                      */
+int tbi_conv2d_fwd(int dtype, int impl, int n, int h, int w, int ksize, int dilation, int groups,
+                   const tbi_view* src0, const tbi_view* src1, int cout_total,
+                   const void* w_packed, const tbi_epilogue* epi, void* stream);
+/* dgrad: dz (cout_total channels) -> dx (cin_total channels) through epi->out / out2.            */
+int tbi_conv2d_dgrad(int dtype, int impl, int n, int h, int w, int ksize, int dilation, int groups,
+                     const tbi_view* dz, int cin_total, const void* w_packed_dgrad,
+                     const tbi_epilogue* epi, void* stream);
+/* wgrad into Keras (grouped) HWIO [k,k,cin_g,cout_total] fp32, ADDED; dbias optional.           */
+int tbi_conv2d_wgrad(int dtype, int impl, int n, int h, int w, int ksize, int dilation, int groups,
+                     const tbi_view* x0, const tbi_view* x1, const tbi_view* dz,
+                     float* dw_hwio, float* dbias, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Conv2DTranspose k in {3,4}, stride 2, TF 'same' (TBI_ResNest.py:124,210; Decoder.py:57-59,120).
+ * fwd runs one tap-GEMM per output parity phase (4 phases); input dims h,w -> output 2h,2w.
+ * w_packed: tbi_pack_convt_weights (FWD: [phase][cout][taps*cin]; DGRAD: [cin][k*k*cout]).       */
+int tbi_conv2d_transpose_s2_fwd(int dtype, int impl, int n, int h, int w, int ksize,
+                                const tbi_view* src0, const tbi_view* src1, int cout,
+                                const void* w_packed, const tbi_epilogue* epi, void* stream);
+int tbi_conv2d_transpose_s2_dgrad(int dtype, int impl, int n, int h, int w, int ksize,
+                                  const tbi_view* dz /* 2h x 2w, cout ch */, int cin_total,
+                                  const void* w_packed_dgrad, const tbi_epilogue* epi, void* stream);
+/* wgrad into Keras HWOI [k,k,cout,cin] fp32, ADDED.                                             */
+int tbi_conv2d_transpose_s2_wgrad(int dtype, int impl, int n, int h, int w, int ksize,
+                                  const tbi_view* x0, const tbi_view* x1, const tbi_view* dz,
+                                  float* dw_hwoi, float* dbias, void* workspace, int64_t workspace_bytes,
+                                  void* stream);
+
+/* ---- weight packing (master fp32 Keras layout -> K-major compute copies, BN scale folded) ----
+ * scale: per-output-channel multiplier (gamma/sqrt(var+eps)) or NULL.
+ * mode 0 = FWD  : out[co][tap][ci_g]            = W[tap][ci_g][co] * scale[co]
+ * mode 1 = DGRAD: out[g*cin_g+ci][tap'][co_g]   = W[flip(tap')][ci][g*cout_g+co_g] * scale[co]
+ * W is (grouped) HWIO [k,k,cin_g,cout_total].                                                   */
+int tbi_pack_conv_weights(int dtype, int mode, int ksize, int groups, int cin_g, int cout_total,
+                          const float* w_hwio, const float* scale, void* out, void* stream);
+/* W is HWOI [k,k,cout,cin].
+ * mode 0 = FWD  : out[phase=(a,b)][co][t][ci] with t over the taps of that phase (order = tbi_convt_phase_taps)
+ * mode 1 = DGRAD: out[ci][ky*k+kx][co]         = W[ky][kx][co][ci] * scale[co]                   */
+int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout,
+                           const float* w_hwoi, const float* scale, void* out, void* stream);
+/* taps of output-parity phase (a,b): returns count; ky/kx = kernel index, dy/dx = input offset.  */
+int tbi_convt_phase_taps(int ksize, int a, int b, int* ky, int* kx, int* dy, int* dx);
+
+/* Folded BN-inference affine of a conv layer, and the matching parameter gradients.
+ * fold:  scale[c] = gamma/sqrt(var+eps);  fbias[c] = (bias-mean)*scale+beta   (gamma NULL: scale=1, fbias=bias)
+ * grads (after wgrad produced dw_raw = A^T dz and dbias_raw = colsum(dz), both w.r.t. pre-activation z):
+ *   dgamma = (sum_k W[k,c]*dw_raw[k,c] + (bias-mean)*dbias_raw) / sqrt(var+eps);  dbeta = dbias_raw
+ *   dw = dw_raw*scale (in place);  dbias = dbias_raw*scale (in place)
+ * layout: co_stride/k_count describe dw/W as k_count rows per channel: element (k,c) at
+ *   k_outer*outer_stride + c*co_stride + k_inner  with k = k_outer*inner + k_inner  (HWIO: inner=1, co_stride=1,
+ *   outer_stride=cout;  HWOI: inner=cin, co_stride=cin, outer_stride=cout*cin).
+ * replaces: BatchNormalization fwd/bwd in inference mode (TBI_ResNest.py:90,144,164,169,190,213). */
+int tbi_bn_fold(int c, const float* gamma, const float* beta, const float* mean, const float* var,
+                const float* bias, float eps, float* scale, float* fbias, void* stream);
+int tbi_bn_param_grad(int c, int64_t k_outer, int64_t inner, int64_t outer_stride, int64_t co_stride,
+                      const float* w, float* dw, const float* bias, float* dbias,
+                      const float* gamma, const float* mean, const float* var, float eps,
+                      float* dgamma, float* dbeta, void* stream);
+
+/* ---- bandwidth-bound fused kernels ------------------------------------------------------------ */
+/* AveragePooling2D(2,2) (TBI_ResNest.py:92-107; ResNest.py:25-28).  bwd: dx = dy/4 broadcast,
+ * optionally accumulated into dx (accumulate=1) and/or multiplied by act'(dact_ref) (stem ELU).  */
+int tbi_avgpool2x2_fwd(int dtype, int n, int h, int w, const tbi_view* x, const tbi_view* y, void* stream);
+int tbi_avgpool2x2_bwd(int dtype, int n, int h, int w, const tbi_view* dy, const tbi_view* dx,
+                       int accumulate, int dact, const tbi_view* dact_ref, void* stream);
+
+/* Radix split-attention tail (TBI_ResNest.py:175-207; ResNest.py:153-199).
+ * u: [n,h,w, K*R*c] channel order (k,r,c); v: [n,h,w,K*c].  Parameters per cardinal k:
+ *   w1 [K][c][c/2], b1 [K][c/2], BN (gamma,beta,mean,var) [K][c/2], w2 [K][R][c/2][c], b2 [K][R][c].
+ * softmax over the CHANNEL axis when R>1, sigmoid when R==1 (reference quirk, kept).
+ * gap [n][K][c], h1 [n][K][c/2], att [n][K][R][c] are fp32 buffers the caller keeps for bwd.
+ * fwd = gap pass + fc + recombine pass;  bwd = da pass + fc-bwd + dU pass (dU already multiplied
+ * by act'(u): it is the gradient w.r.t. the pre-activation of the conv that produced u).         */
+typedef struct {
+    int32_t dtype, n, h, w, kpaths, radix, c;
+    int32_t act;                       /* activation of dense1 and of the producer of u (ELU | LRELU) */
+    float   bn_eps;
+    const float *w1, *b1, *gamma, *beta, *mean, *var, *w2, *b2;
+    float *gap, *h1, *att;
+} tbi_splitatt;
+int tbi_split_attention_fwd(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, void* stream);
+/* scratch: fp32 [n][K][R][c] (da) + [n][K][c] (dgap).  Parameter grads are ADDED.                */
+int tbi_split_attention_bwd(const tbi_splitatt* p, const tbi_view* u, const tbi_view* dv, const tbi_view* du,
+                            float* dw1, float* db1, float* dgamma, float* dbeta, float* dw2, float* db2,
+                            float* scratch, void* stream);
+/* the two bandwidth passes alone (microbench config 2 times exactly these) */
+int tbi_splitatt_gap(const tbi_splitatt* p, const tbi_view* u, void* stream);
+int tbi_splitatt_combine(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, void* stream);
+
+/* Softmax over classes + my_loss_cat (TBI_ResNest.py:125,234-248) + argmax accuracy (:48-51).
+ * logits fp32 [n,h,w,nc]; y fp32 one-hot/soft [n,h,w,nc]; probs fp32 out; loss_map fp32 [h,w];
+ * correct: int32 counter (ADDED; caller zeroes); dlogits (may be NULL; stored as dlogits_dtype)
+ * = d sum(loss_map) / d logits.                                                                  */
+int tbi_softmax_loss_fwd_bwd(int dlogits_dtype, int n, int h, int w, int nc, const float* logits, const float* y,
+                             float* probs, float* loss_map, int32_t* correct, void* dlogits, void* stream);
+
+/* dz = dy * act'(y_ref) [* keep]     (standalone activation backward where it cannot be fused)   */
+int tbi_act_bwd(int dtype, int64_t npix, int act, const tbi_view* dy, const tbi_view* y_ref,
+                const uint8_t* keep, const tbi_view* dz, void* stream);
+/* dst += src  (identity shortcut gradient, TBI_ResNest.py:148 when Cin == Cout)                   */
+int tbi_accumulate(int dtype, int64_t npix, const tbi_view* src, const tbi_view* dst, void* stream);
+/* out[c] += sum_p x[p,c]  (bias gradient)                                                        */
+int tbi_colsum(int dtype, int64_t npix, const tbi_view* x, float* out, void* stream);
+/* keep-multiplier (0|2) generation for the always-on dropout (counter-based hash RNG); the stream position is
+ * (*step_ptr)*count + i so that a CUDA-graph replay draws a fresh mask each step (step_ptr may be NULL) */
+int tbi_dropout_mask(uint8_t* keep, int64_t count, uint64_t seed, const int32_t* step_ptr, void* stream);
+/* x fp32/fp64 host-layout NHWC -> storage dtype (device to device)                               */
+int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void* src, void* dst, void* stream);
+
+/* Keras Adam (TBI_ResNest.py:28,46): lr_t = lr*sqrt(1-b2^t)/(1-b1^t); p -= lr_t*m/(sqrt(v)+eps).
+ * step_count: device int32 holding t-1; the kernel reads it; tbi_adam_advance increments it.
+ * grad_scale multiplies gradients first (1/world for data-parallel averaging).                   */
+int tbi_adam_multi(int64_t count, float* p, const float* g, float* m, float* v, const int32_t* step_count,
+                   float lr, float b1, float b2, float eps, float grad_scale, void* stream);
+int tbi_adam_advance(int32_t* step_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TBI_SM100_H */

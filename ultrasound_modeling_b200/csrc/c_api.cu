@@ -1,0 +1,194 @@
+// extern "C" surface of libtbi_sm100.so (declared in include/tbi_sm100.h): error plumbing, the
+// convolution entry points (which expand into tap-GEMM descriptors) and implementation dispatch.
+#include "tbi_common.cuh"
+#include <string.h>
+#include <mutex>
+
+static thread_local char g_err[512] = "";
+
+int tbi_set_error(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+    return code;
+}
+
+int tbi_sm_count() {
+    static int n = 0;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0; cudaDeviceProp p{};
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&p, dev) == cudaSuccess) n = p.multiProcessorCount;
+        if (n <= 0) n = 148;
+    });
+    return n;
+}
+
+extern "C" int tbi_version(void) { return TBI_VERSION; }
+extern "C" const char* tbi_last_error(void) { return g_err; }
+extern "C" int tbi_device_ok(void) {
+    int dev = 0; cudaDeviceProp p{};
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return p.major == 10 ? 1 : 0;
+}
+
+extern "C" int tbi_tapgemm_run(const tbi_tapgemm* d, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->impl == TBI_IMPL_SIMT) return tbi_tapgemm_simt(d, s);
+    const char* why = "";
+    const bool ok = tbi_tapgemm_tc_supported(d, &why);
+    if (d->impl == TBI_IMPL_TCGEN05) {
+        if (!ok) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapgemm: tcgen05 path does not take this shape: %s", why);
+        return tbi_tapgemm_tc(d, s);
+    }
+    return ok ? tbi_tapgemm_tc(d, s) : tbi_tapgemm_simt(d, s);
+}
+
+extern "C" int tbi_tapwgrad_run(const tbi_tapwgrad* d, void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d->impl == TBI_IMPL_SIMT) return tbi_tapwgrad_simt(d, s);
+    const char* why = "";
+    const bool ok = tbi_tapwgrad_tc_supported(d, &why);
+    if (d->impl == TBI_IMPL_TCGEN05) {
+        if (!ok) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapwgrad: tcgen05 path does not take this shape: %s", why);
+        return tbi_tapwgrad_tc(d, s);
+    }
+    return ok ? tbi_tapwgrad_tc(d, s) : tbi_tapwgrad_simt(d, s);
+}
+
+extern "C" int64_t tbi_workspace_bytes(const tbi_tapwgrad* d) {
+    const char* why = "";
+    if (d->impl == TBI_IMPL_SIMT || !tbi_tapwgrad_tc_supported(d, &why)) return 0;
+    return tbi_tapwgrad_tc_workspace(d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conv2D (stride 1, SAME)
+// ---------------------------------------------------------------------------------------------
+static int fill_conv_taps(int ksize, int dilation, int* dy, int* dx) {
+    int n = 0;
+    for (int r = 0; r < ksize; ++r)
+        for (int c = 0; c < ksize; ++c) { dy[n] = (r - ksize / 2) * dilation; dx[n] = (c - ksize / 2) * dilation; ++n; }
+    return n;
+}
+
+static int check_conv_args(int ksize, int dilation) {
+    TBI_CHECK(ksize == 1 || ksize == 3, TBI_ERR_UNSUPPORTED, "conv2d: ksize %d (1 or 3)", ksize);
+    TBI_CHECK(dilation == 1 || dilation == 2 || dilation == 4 || dilation == 8, TBI_ERR_UNSUPPORTED, "conv2d: dilation %d", dilation);
+    return TBI_OK;
+}
+
+extern "C" int tbi_conv2d_fwd(int dtype, int impl, int n, int h, int w, int ksize, int dilation, int groups,
+                              const tbi_view* src0, const tbi_view* src1, int cout_total, const void* w_packed,
+                              const tbi_epilogue* epi, void* stream) {
+    int rc = check_conv_args(ksize, dilation); if (rc) return rc;
+    TBI_CHECK(groups >= 1 && cout_total % groups == 0, TBI_ERR_BAD_SHAPE, "conv2d_fwd: cout %d %% groups %d", cout_total, groups);
+    tbi_tapgemm d; memset(&d, 0, sizeof(d));
+    d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = groups;
+    d.src[0] = *src0; if (src1 && src1->ptr) d.src[1] = *src1;
+    const int cin = src0->c + ((src1 && src1->ptr) ? src1->c : 0);
+    TBI_CHECK(cin % groups == 0, TBI_ERR_BAD_SHAPE, "conv2d_fwd: cin %d %% groups %d", cin, groups);
+    d.cin_g = cin / groups; d.cout_g = cout_total / groups;
+    d.in_stride = 1; d.ntaps = fill_conv_taps(ksize, dilation, d.dy, d.dx);
+    d.w = w_packed; d.epi = *epi;
+    if (d.epi.out_stride == 0) d.epi.out_stride = 1;
+    return tbi_tapgemm_run(&d, stream);
+}
+
+extern "C" int tbi_conv2d_dgrad(int dtype, int impl, int n, int h, int w, int ksize, int dilation, int groups,
+                                const tbi_view* dz, int cin_total, const void* w_packed_dgrad, const tbi_epilogue* epi,
+                                void* stream) {
+    int rc = check_conv_args(ksize, dilation); if (rc) return rc;
+    TBI_CHECK(groups >= 1 && dz->c % groups == 0 && cin_total % groups == 0, TBI_ERR_BAD_SHAPE, "conv2d_dgrad: groups");
+    tbi_tapgemm d; memset(&d, 0, sizeof(d));
+    d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = groups;
+    d.src[0] = *dz;
+    d.cin_g = dz->c / groups;            // K side = forward output channels
+    d.cout_g = cin_total / groups;       // produced = forward input channels
+    d.in_stride = 1; d.ntaps = fill_conv_taps(ksize, dilation, d.dy, d.dx);
+    d.w = w_packed_dgrad; d.epi = *epi;
+    if (d.epi.out_stride == 0) d.epi.out_stride = 1;
+    return tbi_tapgemm_run(&d, stream);
+}
+
+extern "C" int tbi_conv2d_wgrad(int dtype, int impl, int n, int h, int w, int ksize, int dilation, int groups,
+                                const tbi_view* x0, const tbi_view* x1, const tbi_view* dz, float* dw_hwio, float* dbias,
+                                void* workspace, int64_t workspace_bytes, void* stream) {
+    int rc = check_conv_args(ksize, dilation); if (rc) return rc;
+    tbi_tapwgrad d; memset(&d, 0, sizeof(d));
+    d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = groups;
+    d.a_src[0] = *x0; if (x1 && x1->ptr) d.a_src[1] = *x1;
+    d.b_src = *dz;
+    const int cin = x0->c + ((x1 && x1->ptr) ? x1->c : 0);
+    TBI_CHECK(groups >= 1 && cin % groups == 0 && dz->c % groups == 0, TBI_ERR_BAD_SHAPE, "conv2d_wgrad: groups");
+    d.cin_g = cin / groups; d.cout_g = dz->c / groups;
+    d.a_stride = 1; d.b_stride = 1;
+    d.ntaps = fill_conv_taps(ksize, dilation, d.a_dy, d.a_dx);
+    d.dw = dw_hwio;
+    d.tap_stride = (int64_t)d.cin_g * dz->c; d.ci_stride = dz->c; d.co_stride = 1;
+    d.dbias = dbias; d.workspace = workspace; d.workspace_bytes = workspace_bytes;
+    return tbi_tapwgrad_run(&d, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Conv2DTranspose (stride 2, TF 'same'):  oy = 2*iy - pad + ky,  pad = 1 (k=4) or 0 (k=3, cropped)
+// ---------------------------------------------------------------------------------------------
+extern "C" int tbi_conv2d_transpose_s2_fwd(int dtype, int impl, int n, int h, int w, int ksize, const tbi_view* src0,
+                                           const tbi_view* src1, int cout, const void* w_packed, const tbi_epilogue* epi,
+                                           void* stream) {
+    TBI_CHECK(ksize == 3 || ksize == 4, TBI_ERR_UNSUPPORTED, "convT: ksize %d", ksize);
+    const int cin = src0->c + ((src1 && src1->ptr) ? src1->c : 0);
+    size_t woff = 0;
+    for (int ph = 0; ph < 4; ++ph) {
+        tbi_tapgemm d; memset(&d, 0, sizeof(d));
+        int ky[TBI_MAX_TAPS], kx[TBI_MAX_TAPS];
+        d.ntaps = tbi_convt_phase_taps(ksize, ph >> 1, ph & 1, ky, kx, d.dy, d.dx);
+        d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = 1;
+        d.src[0] = *src0; if (src1 && src1->ptr) d.src[1] = *src1;
+        d.cin_g = cin; d.cout_g = cout; d.in_stride = 1;
+        d.w = (const char*)w_packed + woff * tbi_dtype_size(dtype);
+        woff += (size_t)d.ntaps * cin * cout;
+        d.epi = *epi;
+        d.epi.out_stride = 2; d.epi.out_off_y = ph >> 1; d.epi.out_off_x = ph & 1;
+        int rc = tbi_tapgemm_run(&d, stream); if (rc) return rc;
+    }
+    return TBI_OK;
+}
+
+extern "C" int tbi_conv2d_transpose_s2_dgrad(int dtype, int impl, int n, int h, int w, int ksize, const tbi_view* dz,
+                                             int cin_total, const void* w_packed_dgrad, const tbi_epilogue* epi, void* stream) {
+    TBI_CHECK(ksize == 3 || ksize == 4, TBI_ERR_UNSUPPORTED, "convT: ksize %d", ksize);
+    TBI_CHECK(dz->h == 2 * h && dz->w == 2 * w, TBI_ERR_BAD_SHAPE, "convT dgrad: dz dims %dx%d != 2x(%dx%d)", dz->h, dz->w, h, w);
+    const int pad = ksize == 4 ? 1 : 0;
+    tbi_tapgemm d; memset(&d, 0, sizeof(d));
+    d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = 1;
+    d.src[0] = *dz; d.cin_g = dz->c; d.cout_g = cin_total; d.in_stride = 2;
+    d.ntaps = 0;
+    for (int ky = 0; ky < ksize; ++ky)
+        for (int kx = 0; kx < ksize; ++kx) { d.dy[d.ntaps] = ky - pad; d.dx[d.ntaps] = kx - pad; ++d.ntaps; }
+    d.w = w_packed_dgrad; d.epi = *epi;
+    if (d.epi.out_stride == 0) d.epi.out_stride = 1;
+    return tbi_tapgemm_run(&d, stream);
+}
+
+extern "C" int tbi_conv2d_transpose_s2_wgrad(int dtype, int impl, int n, int h, int w, int ksize, const tbi_view* x0,
+                                             const tbi_view* x1, const tbi_view* dz, float* dw_hwoi, float* dbias,
+                                             void* workspace, int64_t workspace_bytes, void* stream) {
+    TBI_CHECK(ksize == 3 || ksize == 4, TBI_ERR_UNSUPPORTED, "convT: ksize %d", ksize);
+    TBI_CHECK(dz->h == 2 * h && dz->w == 2 * w, TBI_ERR_BAD_SHAPE, "convT wgrad: dz dims");
+    const int pad = ksize == 4 ? 1 : 0;
+    tbi_tapwgrad d; memset(&d, 0, sizeof(d));
+    d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = 1;
+    d.a_src[0] = *x0; if (x1 && x1->ptr) d.a_src[1] = *x1;
+    d.b_src = *dz;
+    const int cin = x0->c + ((x1 && x1->ptr) ? x1->c : 0);
+    d.cin_g = cin; d.cout_g = dz->c; d.a_stride = 1; d.b_stride = 2;
+    d.ntaps = 0;
+    for (int ky = 0; ky < ksize; ++ky)
+        for (int kx = 0; kx < ksize; ++kx) { d.b_dy[d.ntaps] = ky - pad; d.b_dx[d.ntaps] = kx - pad; ++d.ntaps; }
+    d.dw = dw_hwoi;
+    d.tap_stride = (int64_t)cin * dz->c; d.ci_stride = 1; d.co_stride = cin;
+    d.dbias = nullptr;                   // a tap of a stride-2 gather does not visit every dz pixel: use colsum
+    d.workspace = workspace; d.workspace_bytes = workspace_bytes;
+    int rc = tbi_tapwgrad_run(&d, stream); if (rc) return rc;
+    if (dbias) return tbi_colsum(dtype, (int64_t)n * dz->h * dz->w, dz, dbias, stream);
+    return TBI_OK;
+}

@@ -1,0 +1,585 @@
+"""Host-side executor of the TBI_ResNest graph (reference: TBI_ResNest.py:80-220, loss :234-248,
+step :35-55) on top of the C ABI in include/tbi_sm100.h.
+
+PyTorch is used for device memory, streams, CUDA graphs and torch.distributed only; every
+arithmetic op of the path is a kernel of libtbi_sm100.so.  There is no torch/CPU fallback: if the
+library or an sm_100 device is missing, construction raises.
+
+Design (DESIGN.md has the long form):
+  * all trainable parameters live in ONE flat fp32 buffer (creation order == Keras trainable order),
+    gradients and Adam moments in parallel flat buffers -> one Adam launch, contiguous NCCL buckets;
+  * the K*R cardinal branches of a stage are executed as ONE 1x1 conv (Cout = K*R*cv11) and ONE
+    grouped 3x3 conv (groups = K*R); the master tensors are stored fused and sliced back into the
+    Keras-named tensors only in state_dict()/load_state_dict();
+  * BatchNorm (inference-affine) is folded into the packed compute weights + a
+    per-channel bias each step; gamma/beta gradients are recovered from the raw weight gradient
+    (tbi_bn_param_grad), so no pre-activation tensor is ever stored;
+  * tf.concat is never materialised: consumers take two source views, dgrads split their output;
+  * forward/backward are static "programs" (lists of prebuilt ctypes calls) -> CUDA-graph friendly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, BF16, F32, IMPL_AUTO, Epilogue, SplitAtt, TapWgrad, View, check)
+
+BN_EPS = 1e-3
+STAGES = (("conv2_1", 64), ("conv2_2", 128), ("conv3_1", 256), ("conv3_2", 512), ("conv4_1", 512))
+UPSAMPLES = ((512, True), (512, True), (512, True), (256, False), (128, False))
+SKIP_C = (32, 64, 128, 256, 512, 512)          # channels of conv1_pool .. conv6_pool
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def view(t: torch.Tensor, c: Optional[int] = None, coff: int = 0) -> View:
+    """tbi_view of an NHWC tensor (or a channel slice [coff, coff+c) of it)."""
+    assert t.dim() == 4 and t.is_contiguous()
+    n, h, w, ct = t.shape
+    return View(t.data_ptr(), h, w, ct if c is None else c, ct, coff)
+
+
+NULL_VIEW = View(None, 0, 0, 0, 0, 0)
+
+
+def cardinal_channels(stage_out: int, radix: int, kpaths: int) -> Tuple[int, int]:
+    oc = stage_out // 2                                    # TBI_ResNest.py:134
+    return int(oc / radix / kpaths), int(oc / kpaths)       # TBI_ResNest.py:157-158
+
+
+class _Spec:
+    """one tensor in a flat buffer"""
+    __slots__ = ("name", "shape", "offset", "numel")
+
+    def __init__(self, name, shape):
+        self.name, self.shape = name, tuple(shape)
+        self.numel = int(np.prod(shape))
+        self.offset = -1
+
+
+class FlatStore:
+    """A flat fp32 device buffer carved into named tensors (each 16-byte aligned)."""
+
+    def __init__(self):
+        self.specs: "OrderedDict[str, _Spec]" = OrderedDict()
+        self.total = 0
+
+    def add(self, name, shape) -> str:
+        assert name not in self.specs, name
+        s = _Spec(name, shape)
+        s.offset = self.total
+        self.total += (s.numel + 3) // 4 * 4
+        self.specs[name] = s
+        return name
+
+    def alloc(self, device) -> torch.Tensor:
+        return torch.zeros(max(self.total, 4), dtype=torch.float32, device=device)
+
+    def get(self, buf: torch.Tensor, name: str) -> torch.Tensor:
+        s = self.specs[name]
+        return buf[s.offset:s.offset + s.numel].view(s.shape)
+
+
+class ConvLayer:
+    """A Conv2D / Conv2DTranspose (+ optional inference BN + activation), possibly several Keras
+    layers fused along Cout."""
+
+    def __init__(self, name, kind, k, cin, cout, groups=1, bn=False, act=ACT_NONE, keras=None, keras_bn=None):
+        self.name, self.kind, self.k = name, kind, k
+        self.cin, self.cout, self.groups, self.bn, self.act = cin, cout, groups, bn, act
+        self.cin_g = cin // groups
+        self.keras = keras or []        # [(keras_layer_name, co_start, co_stop)]
+        self.keras_bn = keras_bn or []  # [(keras_bn_name, co_start, co_stop)]
+        self.wshape = (k, k, self.cin_g, cout) if kind == "conv" else (k, k, cout, cin)
+
+
+class Engine:
+    def __init__(self, height, width, channel, num_class, ksize, radix, kpaths, dtype="bf16", device="cuda",
+                 impl=IMPL_AUTO, seed=0, layout_only=False):
+        """layout_only=True builds just the parameter inventory / Keras name map (host logic, no device):
+        used by CPU tests; such an engine cannot execute anything."""
+        if not layout_only:
+            if not torch.cuda.is_available():
+                raise _lib.TbiError("ultrasound_modeling_b200 needs a CUDA device (sm_100); there is no CPU path")
+            self.L = _lib.lib()
+            if not self.L.tbi_device_ok():
+                raise _lib.TbiError("libtbi_sm100.so: device is not sm_100 (B200)")
+        assert height % 64 == 0 and width % 64 == 0, "TBI_ResNest needs H, W multiples of 64 (6 poolings)"
+        assert ksize in (1, 3)
+        self.H, self.W, self.Cin, self.num_class = height, width, channel, num_class
+        self.ksize, self.radix, self.kpaths = ksize, radix, kpaths
+        self.device = torch.device(device)
+        self.dt = BF16 if dtype in ("bf16", torch.bfloat16) else F32
+        self.tdtype = torch.bfloat16 if self.dt == BF16 else torch.float32
+        self.impl = impl
+        self.N = 0
+        self._define_layers()
+        if not layout_only:
+            self._alloc_params(seed)
+
+    # ------------------------------------------------------------------ parameters
+    def _define_layers(self):
+        R, K, ks = self.radix, self.kpaths, self.ksize
+        self.P = FlatStore()       # trainable
+        self.S = FlatStore()       # moving statistics (not trainable)
+        self.convs: "OrderedDict[str, ConvLayer]" = OrderedDict()
+        self.atts: List[dict] = []
+
+        def add(layer: ConvLayer):
+            self.convs[layer.name] = layer
+            self.P.add(layer.name + "/w", layer.wshape)
+            self.P.add(layer.name + "/b", (layer.cout,))
+            if layer.bn:
+                self.P.add(layer.name + "/gamma", (layer.cout,))
+                self.P.add(layer.name + "/beta", (layer.cout,))
+                self.S.add(layer.name + "/mean", (layer.cout,))
+                self.S.add(layer.name + "/var", (layer.cout,))
+            return layer
+
+        add(ConvLayer("Conv1", "conv", 3, self.Cin, 16, act=ACT_ELU, keras=[("Conv1", 0, 16)]))
+        add(ConvLayer("conv2_1_1", "conv", 3, 16, 32, act=ACT_ELU, keras=[("conv2_1_1", 0, 32)]))
+        add(ConvLayer("conv2_1_2", "conv", 3, 32, 32, bn=True, act=ACT_ELU, keras=[("conv2_1_2", 0, 32)],
+                      keras_bn=[("conv2_1_2bn", 0, 32)]))
+        cin = 32
+        self.stage_info = []
+        for si, (stage, out) in enumerate(STAGES):
+            cv11, cvkk = cardinal_channels(out, R, K)
+            assert cv11 >= 1 and cvkk >= 2, "radix*kpaths too large for this stage width"
+            G = K * R
+            k1, k1bn, k2, k2bn = [], [], [], []
+            for k in range(K):
+                for r in range(R):
+                    g = k * R + r
+                    nc = f"{stage}_car_k{k}"
+                    k1.append((f"{nc}1_r{r}", g * cv11, (g + 1) * cv11)); k1bn.append((f"{nc}1_{r}bn", g * cv11, (g + 1) * cv11))
+                    k2.append((f"{nc}2_r{r}", g * cvkk, (g + 1) * cvkk)); k2bn.append((f"{nc}2_{r}bn", g * cvkk, (g + 1) * cvkk))
+            c1 = add(ConvLayer(f"{stage}/c1", "conv", 1, cin, G * cv11, bn=True, act=ACT_ELU, keras=k1, keras_bn=k1bn))
+            c2 = add(ConvLayer(f"{stage}/c2", "conv", ks, G * cv11, G * cvkk, groups=G, bn=True, act=ACT_ELU, keras=k2, keras_bn=k2bn))
+            c = cvkk
+            att = dict(stage=stage, c=c, name=f"{stage}/att")
+            self.P.add(att["name"] + "/w1", (K, c, c // 2)); self.P.add(att["name"] + "/b1", (K, c // 2))
+            self.P.add(att["name"] + "/gamma", (K, c // 2)); self.P.add(att["name"] + "/beta", (K, c // 2))
+            self.S.add(att["name"] + "/mean", (K, c // 2)); self.S.add(att["name"] + "/var", (K, c // 2))
+            self.P.add(att["name"] + "/w2", (K, R, c // 2, c)); self.P.add(att["name"] + "/b2", (K, R, c))
+            self.atts.append(att)
+            auto = "conv2d" if si == 0 else f"conv2d_{si}"
+            cc2 = add(ConvLayer(f"{stage}/cc2", "conv", ks, K * cvkk, out, keras=[(auto, 0, out)]))
+            sc = None
+            if cin != out:
+                sc = add(ConvLayer(f"{stage}/sc", "conv", 1, cin, out, bn=True, act=ACT_ELU, keras=[(f"{stage}_cc", 0, out)],
+                                   keras_bn=[(f"{stage}_scbn", 0, out)]))
+            self.stage_info.append(dict(stage=stage, cin=cin, out=out, cv11=cv11, cvkk=cvkk, G=G, c1=c1, c2=c2, att=att, cc2=cc2, sc=sc))
+            cin = out
+        cin = SKIP_C[5]
+        self.ups = []
+        for i, (out, drop) in enumerate(UPSAMPLES):
+            bnname = "batch_normalization" if i == 0 else f"batch_normalization_{i}"
+            up = add(ConvLayer(f"upsample_{i}", "convt", 4, cin, out, bn=True, act=ACT_RELU,
+                               keras=[(f"upsample_{i}_t_conv", 0, out)], keras_bn=[(bnname, 0, out)]))
+            self.ups.append(dict(layer=up, drop=drop, cin=cin, out=out))
+            cin = out + SKIP_C[4 - i]
+        self.head = add(ConvLayer("f_tran", "convt", 4, cin, self.num_class, keras=[("f_tran", 0, self.num_class)]))
+
+    def _alloc_params(self, seed):
+        dev = self.device
+        self.params = self.P.alloc(dev)
+        self.grads = self.P.alloc(dev)
+        self.adam_m = self.P.alloc(dev)
+        self.adam_v = self.P.alloc(dev)
+        self.stats = self.S.alloc(dev)
+        self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        # Keras defaults: glorot_uniform kernels, zero bias, BN gamma=1 beta=0 mean=0 var=1
+        g = torch.Generator().manual_seed(seed)
+        host = torch.zeros(self.params.numel(), dtype=torch.float32)
+        hstat = torch.zeros(self.stats.numel(), dtype=torch.float32)
+
+        def hv(store, buf, name):
+            s = store.specs[name]
+            return buf[s.offset:s.offset + s.numel].view(s.shape)
+
+        for L in self.convs.values():
+            w = hv(self.P, host, L.name + "/w")
+            rf = L.k * L.k
+            # per Keras layer fans (a fused tensor is several Keras layers side by side along Cout)
+            for (_, a, b) in L.keras:
+                if L.kind == "conv":
+                    fan = rf * L.cin_g + rf * (b - a)
+                    lim = math.sqrt(6.0 / fan)
+                    w[..., a:b] = (torch.rand(w[..., a:b].shape, generator=g) * 2 - 1) * lim
+                else:
+                    fan = rf * L.cin + rf * L.cout
+                    lim = math.sqrt(6.0 / fan)
+                    w.copy_((torch.rand(w.shape, generator=g) * 2 - 1) * lim)
+            if L.bn:
+                hv(self.P, host, L.name + "/gamma").fill_(1.0)
+                hv(self.S, hstat, L.name + "/var").fill_(1.0)
+        for att in self.atts:
+            c = att["c"]
+            w1 = hv(self.P, host, att["name"] + "/w1"); w2 = hv(self.P, host, att["name"] + "/w2")
+            w1.copy_((torch.rand(w1.shape, generator=g) * 2 - 1) * math.sqrt(6.0 / (c + c // 2)))
+            w2.copy_((torch.rand(w2.shape, generator=g) * 2 - 1) * math.sqrt(6.0 / (c + c // 2)))
+            hv(self.P, host, att["name"] + "/gamma").fill_(1.0)
+            hv(self.S, hstat, att["name"] + "/var").fill_(1.0)
+        self.params.copy_(host)
+        self.stats.copy_(hstat)
+
+    def p(self, name): return self.P.get(self.params, name)
+    def g(self, name): return self.P.get(self.grads, name)
+    def s(self, name): return self.S.get(self.stats, name)
+
+    # ------------------------------------------------------------------ Keras-named state dict
+    def _keras_items(self):
+        """yield (keras_name, store, flat_name, index) where index slices the fused tensor"""
+        R, K = self.radix, self.kpaths
+        for L in self.convs.values():
+            for (kn, a, b) in L.keras:
+                if L.kind == "conv":
+                    yield kn + "/kernel", "P", L.name + "/w", (Ellipsis, slice(a, b))
+                else:
+                    yield kn + "/kernel", "P", L.name + "/w", (Ellipsis,)
+                yield kn + "/bias", "P", L.name + "/b", (slice(a, b),)
+            for (kn, a, b) in L.keras_bn:
+                yield kn + "/gamma", "P", L.name + "/gamma", (slice(a, b),)
+                yield kn + "/beta", "P", L.name + "/beta", (slice(a, b),)
+                yield kn + "/moving_mean", "S", L.name + "/mean", (slice(a, b),)
+                yield kn + "/moving_variance", "S", L.name + "/var", (slice(a, b),)
+        for att in self.atts:
+            st, nm = att["stage"], att["name"]
+            for k in range(K):
+                an = f"{st}_car_k{k}_att"
+                yield f"{an}1/kernel", "P", nm + "/w1", (k, None, None)          # -> [1,1,c,c/2]
+                yield f"{an}1/bias", "P", nm + "/b1", (k,)
+                yield f"{an}_bn/gamma", "P", nm + "/gamma", (k,)
+                yield f"{an}_bn/beta", "P", nm + "/beta", (k,)
+                yield f"{an}_bn/moving_mean", "S", nm + "/mean", (k,)
+                yield f"{an}_bn/moving_variance", "S", nm + "/var", (k,)
+                for r in range(R):
+                    yield f"{an}2_r{r}/kernel", "P", nm + "/w2", (k, r, None, None)
+                    yield f"{an}2_r{r}/bias", "P", nm + "/b2", (k, r)
+
+    def _named(self, pbuf, sbuf):
+        out = OrderedDict()
+        for kn, store, flat, idx in self._keras_items():
+            t = self.P.get(pbuf, flat) if store == "P" else self.S.get(sbuf, flat)
+            out[kn] = t[idx]
+        return out
+
+    def state_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        """Keras-named, Keras-layout (HWIO / HWOI) copies of every variable."""
+        return OrderedDict((k, v.detach().clone()) for k, v in self._named(self.params, self.stats).items())
+
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        named = self._named(self.params, self.stats)
+        missing = [k for k in named if k not in sd]
+        if missing:
+            raise KeyError(f"load_state_dict: missing {missing[:4]}... ({len(missing)})")
+        for k, dst in named.items():
+            src = torch.as_tensor(sd[k]).to(device=self.device, dtype=torch.float32)
+            dst.copy_(src.reshape(dst.shape))
+
+    def grad_dict(self) -> "OrderedDict[str, torch.Tensor]":
+        """Keras-named gradients of the last backward (trainable variables only)."""
+        named = self._named(self.grads, self.stats)
+        return OrderedDict((k, v.detach().clone()) for k, v in named.items()
+                           if not (k.endswith("/moving_mean") or k.endswith("/moving_variance")))
+
+    # ------------------------------------------------------------------ buffers + programs
+    def build(self, n: int):
+        """allocate activations for batch n and assemble the static call programs"""
+        if n == self.N:
+            return
+        self.N = n
+        dev, td = self.device, self.tdtype
+        H, W = self.H, self.W
+        E = lambda *shape: torch.empty(shape, dtype=td, device=dev)
+        self.x_in = torch.zeros(n, H, W, self.Cin, dtype=torch.float32, device=dev)
+        self.y_in = torch.zeros(n, H, W, self.num_class, dtype=torch.float32, device=dev)
+        self.x0 = E(n, H, W, self.Cin)
+        self.t = [E(n, H, W, 16), E(n, H, W, 32), E(n, H, W, 32)]
+        self.dstem = [E(n, H, W, 16), E(n, H, W, 32), E(n, H, W, 32)]
+        self.pool = [E(n, H >> (i + 1), W >> (i + 1), SKIP_C[i]) for i in range(6)]
+        self.dpool = [E(n, H >> (i + 1), W >> (i + 1), SKIP_C[i]) for i in range(6)]
+        self.stage_buf = []
+        for si, info in enumerate(self.stage_info):
+            h, w = H >> (si + 1), W >> (si + 1)
+            G, cv11, cvkk, out, K, R = info["G"], info["cv11"], info["cvkk"], info["out"], self.kpaths, self.radix
+            b = dict(T1=E(n, h, w, G * cv11), U=E(n, h, w, G * cvkk), V=E(n, h, w, K * cvkk), Y=E(n, h, w, out),
+                     dZ1=E(n, h, w, G * cv11), dZ2=E(n, h, w, G * cvkk), dV=E(n, h, w, K * cvkk), dY=E(n, h, w, out),
+                     gap=torch.empty(n, K, cvkk, dtype=torch.float32, device=dev),
+                     h1=torch.empty(n, K, cvkk // 2, dtype=torch.float32, device=dev),
+                     att=torch.empty(n, K, R, cvkk, dtype=torch.float32, device=dev))
+            if info["sc"] is not None:
+                b["SC"] = E(n, h, w, out); b["dZsc"] = E(n, h, w, out)
+            self.stage_buf.append(b)
+        att_scratch = max(n * self.kpaths * (self.radix * i["cvkk"] + 2 * i["cvkk"]) for i in self.stage_info)
+        self.att_scratch = torch.empty(att_scratch, dtype=torch.float32, device=dev)
+        self.up = []; self.dup = []; self.keep = []
+        for i, u in enumerate(self.ups):
+            h, w = H >> (5 - i), W >> (5 - i)
+            self.up.append(E(n, h, w, u["out"])); self.dup.append(E(n, h, w, u["out"]))
+            self.keep.append(torch.ones(n, h, w, u["out"], dtype=torch.uint8, device=dev) if u["drop"] else None)
+        self.logits = torch.empty(n, H, W, self.num_class, dtype=torch.float32, device=dev)
+        self.probs = torch.empty(n, H, W, self.num_class, dtype=torch.float32, device=dev)
+        self.dlogits = E(n, H, W, self.num_class)
+        self.loss_map = torch.empty(H, W, dtype=torch.float32, device=dev)
+        self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
+        # packed compute weights + folded BN
+        esz = 2 if self.dt == BF16 else 4
+        self.packed = {}
+        for L in self.convs.values():
+            nel = L.k * L.k * L.cin_g * L.cout
+            self.packed[L.name] = dict(wf=torch.empty(nel, dtype=td, device=dev), wb=torch.empty(nel, dtype=td, device=dev),
+                                       scale=torch.empty(L.cout, dtype=torch.float32, device=dev),
+                                       fbias=torch.empty(L.cout, dtype=torch.float32, device=dev))
+        self._assemble()
+
+    # -- program assembly helpers: each appends (fn, args) ; stream is appended at call time
+    def _assemble(self):
+        L = self.L
+        dt, impl, n = self.dt, self.impl, self.N
+        self.prog_prepare, self.prog_fwd, self.prog_loss, self.prog_bwd = [], [], [], []
+        self._keepalive = []
+        ws_bytes = 0
+        wgrads = []
+        # (number of prog_bwd calls issued, lowest flat offset above which every gradient is final):
+        # lets the data-parallel wrapper all-reduce finished buckets while backward continues
+        self.bwd_marks: List[Tuple[int, int]] = []
+        done = set()
+        order = list(self.P.specs.values())
+
+        def mark(prefix):
+            for s_ in order:
+                if s_.name.startswith(prefix + "/"):
+                    done.add(s_.name)
+            wm = self.P.total
+            for s_ in reversed(order):
+                if s_.name not in done:
+                    break
+                wm = s_.offset
+            self.bwd_marks.append((len(self.prog_bwd), wm))
+
+        def keep(*objs):
+            self._keepalive.extend(objs)
+            return objs[0] if len(objs) == 1 else objs
+
+        def bref(v):
+            return C.byref(keep(v))
+
+        def epi(**kw):
+            e = Epilogue()
+            for k, v in kw.items():
+                setattr(e, k, v)
+            if e.out_stride == 0:
+                e.out_stride = 1
+            return e
+
+        def prepare(Lr: ConvLayer):
+            pk = self.packed[Lr.name]
+            if Lr.bn:
+                self.prog_prepare.append((L.tbi_bn_fold, (Lr.cout, _ptr(self.p(Lr.name + "/gamma")), _ptr(self.p(Lr.name + "/beta")),
+                                                          _ptr(self.s(Lr.name + "/mean")), _ptr(self.s(Lr.name + "/var")),
+                                                          _ptr(self.p(Lr.name + "/b")), BN_EPS, _ptr(pk["scale"]), _ptr(pk["fbias"]))))
+            else:
+                self.prog_prepare.append((L.tbi_bn_fold, (Lr.cout, None, None, None, None, _ptr(self.p(Lr.name + "/b")), BN_EPS,
+                                                          _ptr(pk["scale"]), _ptr(pk["fbias"]))))
+            sc = _ptr(pk["scale"]) if Lr.bn else None
+            wp = _ptr(self.p(Lr.name + "/w"))
+            if Lr.kind == "conv":
+                self.prog_prepare.append((L.tbi_pack_conv_weights, (dt, 0, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, sc, _ptr(pk["wf"]))))
+                self.prog_prepare.append((L.tbi_pack_conv_weights, (dt, 1, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, sc, _ptr(pk["wb"]))))
+            else:
+                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 0, Lr.k, Lr.cin, Lr.cout, wp, sc, _ptr(pk["wf"]))))
+                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 1, Lr.k, Lr.cin, Lr.cout, wp, sc, _ptr(pk["wb"]))))
+
+        for Lr in self.convs.values():
+            prepare(Lr)
+
+        def conv_fwd(Lr, h, w, src0, src1, e):
+            pk = self.packed[Lr.name]
+            e.bias = _ptr(pk["fbias"]); e.act = Lr.act
+            if Lr.kind == "conv":
+                self.prog_fwd.append((L.tbi_conv2d_fwd, (dt, impl, n, h, w, Lr.k, 1, Lr.groups, bref(src0), bref(src1) if src1 is not None else None,
+                                                         Lr.cout, _ptr(pk["wf"]), bref(e))))
+            else:
+                self.prog_fwd.append((L.tbi_conv2d_transpose_s2_fwd, (dt, impl, n, h, w, Lr.k, bref(src0), bref(src1) if src1 is not None else None,
+                                                                      Lr.cout, _ptr(pk["wf"]), bref(e))))
+
+        def conv_bwd(Lr, h, w, x0, x1, dz, e_dgrad):
+            """wgrad (+dbias) [+ BN param grads]; then dgrad through e_dgrad (None: no input gradient)."""
+            nonlocal ws_bytes
+            pk = self.packed[Lr.name]
+            dw, db = _ptr(self.g(Lr.name + "/w")), _ptr(self.g(Lr.name + "/b"))
+            if Lr.kind == "conv":
+                wargs = [dt, impl, n, h, w, Lr.k, 1, Lr.groups, bref(x0), bref(x1) if x1 is not None else None, bref(dz), dw, db, None, 0]
+                self.prog_bwd.append((L.tbi_conv2d_wgrad, wargs))
+            else:
+                wargs = [dt, impl, n, h, w, Lr.k, bref(x0), bref(x1) if x1 is not None else None, bref(dz), dw, db, None, 0]
+                self.prog_bwd.append((L.tbi_conv2d_transpose_s2_wgrad, wargs))
+            wgrads.append((Lr, wargs, n, h, w, x0, x1, dz))
+            if Lr.bn:
+                if Lr.kind == "conv":
+                    lay = (Lr.k * Lr.k * Lr.cin_g, 1, Lr.cout, 1)
+                else:
+                    lay = (Lr.k * Lr.k, Lr.cin, Lr.cout * Lr.cin, Lr.cin)
+                self.prog_bwd.append((L.tbi_bn_param_grad, (Lr.cout, *lay, _ptr(self.p(Lr.name + "/w")), dw, _ptr(self.p(Lr.name + "/b")), db,
+                                                            _ptr(self.p(Lr.name + "/gamma")), _ptr(self.s(Lr.name + "/mean")),
+                                                            _ptr(self.s(Lr.name + "/var")), BN_EPS, _ptr(self.g(Lr.name + "/gamma")),
+                                                            _ptr(self.g(Lr.name + "/beta")))))
+            mark(Lr.name)
+            if e_dgrad is not None:
+                if Lr.kind == "conv":
+                    self.prog_bwd.append((L.tbi_conv2d_dgrad, (dt, impl, n, h, w, Lr.k, 1, Lr.groups, bref(dz), Lr.cin, _ptr(pk["wb"]), bref(e_dgrad))))
+                else:
+                    self.prog_bwd.append((L.tbi_conv2d_transpose_s2_dgrad, (dt, impl, n, h, w, Lr.k, bref(dz), Lr.cin, _ptr(pk["wb"]), bref(e_dgrad))))
+
+        H, W = self.H, self.W
+        cv = self.convs
+        # ---------------- forward ----------------
+        self.prog_fwd.append((L.tbi_cast, (1, dt, self.x_in.numel(), _ptr(self.x_in), _ptr(self.x0))))
+        conv_fwd(cv["Conv1"], H, W, view(self.x0), None, epi(out=view(self.t[0])))
+        conv_fwd(cv["conv2_1_1"], H, W, view(self.t[0]), None, epi(out=view(self.t[1])))
+        conv_fwd(cv["conv2_1_2"], H, W, view(self.t[1]), None, epi(out=view(self.t[2])))
+        self.prog_fwd.append((L.tbi_avgpool2x2_fwd, (dt, n, H, W, bref(view(self.t[2])), bref(view(self.pool[0])))))
+        self.att_desc = []
+        for si, info in enumerate(self.stage_info):
+            h, w = H >> (si + 1), W >> (si + 1)
+            b = self.stage_buf[si]
+            pin = self.pool[si]
+            conv_fwd(info["c1"], h, w, view(pin), None, epi(out=view(b["T1"])))
+            conv_fwd(info["c2"], h, w, view(b["T1"]), None, epi(out=view(b["U"])))
+            nm = info["att"]["name"]
+            sa = keep(SplitAtt(dt, n, h, w, self.kpaths, self.radix, info["cvkk"], ACT_ELU, BN_EPS,
+                               _ptr(self.p(nm + "/w1")), _ptr(self.p(nm + "/b1")), _ptr(self.p(nm + "/gamma")), _ptr(self.p(nm + "/beta")),
+                               _ptr(self.s(nm + "/mean")), _ptr(self.s(nm + "/var")), _ptr(self.p(nm + "/w2")), _ptr(self.p(nm + "/b2")),
+                               _ptr(b["gap"]), _ptr(b["h1"]), _ptr(b["att"])))
+            self.att_desc.append(sa)
+            self.prog_fwd.append((L.tbi_split_attention_fwd, (C.byref(sa), bref(view(b["U"])), bref(view(b["V"])))))
+            if info["sc"] is not None:
+                conv_fwd(info["sc"], h, w, view(pin), None, epi(out=view(b["SC"])))
+                res = view(b["SC"])
+            else:
+                res = view(pin)
+            conv_fwd(info["cc2"], h, w, view(b["V"]), None, epi(out=view(b["Y"]), residual=res))
+            self.prog_fwd.append((L.tbi_avgpool2x2_fwd, (dt, n, h, w, bref(view(b["Y"])), bref(view(self.pool[si + 1])))))
+        for i, u in enumerate(self.ups):
+            h, w = H >> (6 - i), W >> (6 - i)          # input dims
+            src0 = view(self.pool[5]) if i == 0 else view(self.up[i - 1])
+            src1 = None if i == 0 else view(self.pool[5 - i])
+            conv_fwd(u["layer"], h, w, src0, src1, epi(out=view(self.up[i]), drop_keep=_ptr(self.keep[i])))
+        conv_fwd(self.head, H // 2, W // 2, view(self.up[4]), view(self.pool[0]), epi(out=view(self.logits), out_f32=1))
+        # ---------------- loss ----------------
+        self.prog_loss.append((L.tbi_softmax_loss_fwd_bwd, (dt, n, H, W, self.num_class, _ptr(self.logits), _ptr(self.y_in), _ptr(self.probs),
+                                                            _ptr(self.loss_map), _ptr(self.correct), _ptr(self.dlogits))))
+        # ---------------- backward ----------------
+        # head: d(up4) gets ReLU' of up4 (no dropout on upsample_4); d(pool[0]) plain write
+        conv_bwd(self.head, H // 2, W // 2, view(self.up[4]), view(self.pool[0]), view(self.dlogits),
+                 epi(out=view(self.dup[4]), dact=ACT_RELU, dact_ref=view(self.up[4]), split_c=self.ups[4]["out"], out2=view(self.dpool[0])))
+        for i in range(4, -1, -1):
+            u = self.ups[i]
+            h, w = H >> (6 - i), W >> (6 - i)
+            if i == 0:
+                e = epi(out=view(self.dpool[5]))
+                conv_bwd(u["layer"], h, w, view(self.pool[5]), None, view(self.dup[0]), e)
+            else:
+                e = epi(out=view(self.dup[i - 1]), dact=ACT_RELU, dact_ref=view(self.up[i - 1]), dact_keep=_ptr(self.keep[i - 1]),
+                        split_c=self.ups[i - 1]["out"], out2=view(self.dpool[5 - i]))
+                conv_bwd(u["layer"], h, w, view(self.up[i - 1]), view(self.pool[5 - i]), view(self.dup[i]), e)
+        for si in range(4, -1, -1):
+            info, b = self.stage_info[si], self.stage_buf[si]
+            h, w = H >> (si + 1), W >> (si + 1)
+            pin, dpin = self.pool[si], self.dpool[si]
+            self.prog_bwd.append((L.tbi_avgpool2x2_bwd, (dt, n, h, w, bref(view(self.dpool[si + 1])), bref(view(b["dY"])), 0, ACT_NONE, None)))
+            conv_bwd(info["cc2"], h, w, view(b["V"]), None, view(b["dY"]), epi(out=view(b["dV"])))
+            if info["sc"] is not None:
+                self.prog_bwd.append((L.tbi_act_bwd, (dt, n * h * w, ACT_ELU, bref(view(b["dY"])), bref(view(b["SC"])), None, bref(view(b["dZsc"])))))
+                conv_bwd(info["sc"], h, w, view(pin), None, view(b["dZsc"]), epi(out=view(dpin), residual=view(dpin)))
+            else:
+                self.prog_bwd.append((L.tbi_accumulate, (dt, n * h * w, bref(view(b["dY"])), bref(view(dpin)))))
+            nm = info["att"]["name"]
+            self.prog_bwd.append((L.tbi_split_attention_bwd, (C.byref(self.att_desc[si]), bref(view(b["U"])), bref(view(b["dV"])), bref(view(b["dZ2"])),
+                                                              _ptr(self.g(nm + "/w1")), _ptr(self.g(nm + "/b1")), _ptr(self.g(nm + "/gamma")),
+                                                              _ptr(self.g(nm + "/beta")), _ptr(self.g(nm + "/w2")), _ptr(self.g(nm + "/b2")),
+                                                              _ptr(self.att_scratch))))
+            mark(nm)
+            conv_bwd(info["c2"], h, w, view(b["T1"]), None, view(b["dZ2"]),
+                     epi(out=view(b["dZ1"]), dact=ACT_ELU, dact_ref=view(b["T1"])))
+            conv_bwd(info["c1"], h, w, view(pin), None, view(b["dZ1"]), epi(out=view(dpin), residual=view(dpin)))
+        self.prog_bwd.append((L.tbi_avgpool2x2_bwd, (dt, n, H, W, bref(view(self.dpool[0])), bref(view(self.dstem[2])), 0, ACT_ELU, bref(view(self.t[2])))))
+        conv_bwd(cv["conv2_1_2"], H, W, view(self.t[1]), None, view(self.dstem[2]), epi(out=view(self.dstem[1]), dact=ACT_ELU, dact_ref=view(self.t[1])))
+        conv_bwd(cv["conv2_1_1"], H, W, view(self.t[0]), None, view(self.dstem[1]), epi(out=view(self.dstem[0]), dact=ACT_ELU, dact_ref=view(self.t[0])))
+        conv_bwd(cv["Conv1"], H, W, view(self.x0), None, view(self.dstem[0]), None)
+        # tcgen05 wgrad workspace (split-K partials), sized for the largest layer
+        for (Lr, wargs, *_rest) in wgrads:
+            pass
+        self.ws = None
+        self._wgrads = wgrads
+
+    # ------------------------------------------------------------------ execution
+    def _run(self, prog, stream):
+        for fn, args in prog:
+            rc = fn(*args, stream)
+            if rc != 0:
+                check(rc, fn.__name__)
+
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def prepare(self):
+        self._run(self.prog_prepare, self.stream())
+
+    def draw_dropout(self, seed: int = 0x5EED):
+        st = self.stream()
+        for i, k in enumerate(self.keep):
+            if k is not None:
+                check(self.L.tbi_dropout_mask(k.data_ptr(), k.numel(), seed + 7919 * i, self.step_count.data_ptr(), st), "dropout_mask")
+
+    def set_dropout(self, masks: Optional[Sequence[Optional[torch.Tensor]]]):
+        """explicit 0/1 keep-masks (parity runs); None -> dropout disabled.  The device buffers hold the
+        MULTIPLIER the epilogue applies: 0 dropped, 2 kept, 1 disabled."""
+        for i, k in enumerate(self.keep):
+            if k is None:
+                continue
+            if masks is None or masks[i] is None:
+                k.fill_(1)
+            else:
+                k.copy_(torch.as_tensor(masks[i]).to(device=self.device, dtype=torch.uint8) * 2)
+
+    def forward(self):
+        self._run(self.prog_fwd, self.stream())
+
+    def loss(self):
+        self.correct.zero_()
+        self._run(self.prog_loss, self.stream())
+
+    def backward(self):
+        self.grads.zero_()
+        self._run(self.prog_bwd, self.stream())
+
+    def adam(self, lr: float, grad_scale: float = 1.0):
+        st = self.stream()
+        check(self.L.tbi_adam_multi(self.P.total, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                                    self.adam_v.data_ptr(), self.step_count.data_ptr(), lr, 0.9, 0.999, 1e-7, grad_scale, st), "adam")
+        check(self.L.tbi_adam_advance(self.step_count.data_ptr(), st), "adam_advance")
+
+    def launches_per_step(self, train: bool = True) -> int:
+        """kernel launches of one step (conv entry points expand: convT fwd = 4 phase launches, convT wgrad = wgrad + colsum,
+        split-attention fwd = 3 (+memset), bwd = 4 (+memset))."""
+        def count(prog):
+            c = 0
+            for fn, _ in prog:
+                nm = fn.__name__
+                c += {"tbi_conv2d_transpose_s2_fwd": 4, "tbi_conv2d_transpose_s2_wgrad": 2, "tbi_split_attention_fwd": 3,
+                      "tbi_split_attention_bwd": 4}.get(nm, 1)
+            return c
+        n = count(self.prog_prepare) + count(self.prog_fwd) + count(self.prog_loss)
+        if train:
+            n += count(self.prog_bwd) + 2 + sum(1 for k in self.keep if k is not None)
+        return n

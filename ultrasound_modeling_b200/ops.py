@@ -1,0 +1,284 @@
+"""Functional wrappers over the C ABI (include/tbi_sm100.h) for torch CUDA tensors.
+
+Each function allocates its outputs with torch and enqueues libtbi_sm100.so kernels on the current
+stream.  Layouts are the reference's (Keras): activations NHWC, Conv2D kernels HWIO (grouped:
+[k,k,cin/groups,cout]), Conv2DTranspose kernels HWOI.  Used by the parity tests and microbenches;
+the model executor (engine.py) calls the same C entry points with prebuilt descriptors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_ELU, ACT_NONE, BF16, F32, IMPL_AUTO, Epilogue, SplitAtt, View, check
+
+BN_EPS = 1e-3
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported storage dtype {t.dtype}")
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def view(t: torch.Tensor, c: Optional[int] = None, coff: int = 0) -> View:
+    assert t.is_cuda and t.dim() == 4 and t.is_contiguous(), "NHWC contiguous CUDA tensor expected"
+    _, h, w, ct = t.shape
+    return View(t.data_ptr(), h, w, ct if c is None else c, ct, coff)
+
+
+def _vp(v: Optional[View]):
+    return None if v is None else C.byref(v)
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _f32(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def fold_bn(cout, bias, bn, device):
+    """-> (scale or None, folded bias) on device, via tbi_bn_fold"""
+    L = _lib.lib()
+    scale = torch.empty(cout, dtype=torch.float32, device=device)
+    fbias = torch.empty(cout, dtype=torch.float32, device=device)
+    b = _f32(bias)
+    if bn is not None:
+        g, be, m, v = (_f32(t) for t in bn)
+        check(L.tbi_bn_fold(cout, _p(g), _p(be), _p(m), _p(v), _p(b), BN_EPS, _p(scale), _p(fbias), _st()), "bn_fold")
+        return scale, fbias
+    check(L.tbi_bn_fold(cout, None, None, None, None, _p(b), BN_EPS, _p(scale), _p(fbias), _st()), "bn_fold")
+    return None, fbias
+
+
+def pack_conv(w_hwio: torch.Tensor, groups: int, mode: int, dtype: torch.dtype, scale=None) -> torch.Tensor:
+    L = _lib.lib()
+    k, _, cin_g, cout = w_hwio.shape
+    w32 = _f32(w_hwio)
+    out = torch.empty(w32.numel(), dtype=dtype, device=w32.device)
+    check(L.tbi_pack_conv_weights(F32 if dtype == torch.float32 else BF16, mode, k, groups, cin_g, cout, _p(w32), _p(scale), _p(out), _st()), "pack_conv")
+    return out
+
+
+def pack_convt(w_hwoi: torch.Tensor, mode: int, dtype: torch.dtype, scale=None) -> torch.Tensor:
+    L = _lib.lib()
+    k, _, cout, cin = w_hwoi.shape
+    w32 = _f32(w_hwoi)
+    out = torch.empty(w32.numel(), dtype=dtype, device=w32.device)
+    check(L.tbi_pack_convt_weights(F32 if dtype == torch.float32 else BF16, mode, k, cin, cout, _p(w32), _p(scale), _p(out), _st()), "pack_convt")
+    return out
+
+
+def _epi(out, bias=None, act=ACT_NONE, residual=None, keep=None, dact=ACT_NONE, dact_ref=None, dact_keep=None,
+         out2=None, split_c=0, residual2=None, out_f32=0) -> Epilogue:
+    e = Epilogue()
+    e.bias = _p(bias); e.act = act; e.out = view(out); e.out_stride = 1; e.out_f32 = out_f32
+    e.drop_keep = _p(keep)
+    if residual is not None:
+        e.residual = view(residual)
+    e.dact = dact
+    if dact_ref is not None:
+        e.dact_ref = view(dact_ref)
+    e.dact_keep = _p(dact_keep)
+    if out2 is not None:
+        e.out2 = view(out2); e.split_c = split_c
+    if residual2 is not None:
+        e.residual2 = view(residual2)
+    return e
+
+
+# ------------------------------------------------------------------------------------------ Conv2D
+def conv2d(x, w_hwio, bias=None, *, dilation=1, groups=1, bn=None, act=ACT_NONE, residual=None, x2=None,
+           impl=IMPL_AUTO, out_f32=False):
+    """Conv2D(strides=1, padding='SAME') [+ BN-inference] [+ act] [+ residual]; x2 = second source of a
+    virtual channel concat.  (TBI_ResNest.py:83-91,140-148,162-170)"""
+    L = _lib.lib()
+    n, h, w, _ = x.shape
+    k, cout = w_hwio.shape[0], w_hwio.shape[3]
+    scale, fbias = fold_bn(cout, bias if bias is not None else torch.zeros(cout, device=x.device), bn, x.device)
+    wp = pack_conv(w_hwio, groups, 0, x.dtype, scale)
+    y = torch.empty(n, h, w, cout, dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
+    e = _epi(y, fbias, act, residual, out_f32=int(out_f32))
+    check(L.tbi_conv2d_fwd(_dt(x), impl, n, h, w, k, dilation, groups, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
+                           cout, _p(wp), C.byref(e), _st()), "conv2d_fwd")
+    return y
+
+
+def conv2d_grads(x, w_hwio, dz, *, dilation=1, groups=1, scale=None, x2=None, impl=IMPL_AUTO, need_dx=True,
+                 dact=ACT_NONE, dact_ref=None):
+    """gradients of the conv w.r.t. (input[s], HWIO kernel, bias) given dz = dL/d(conv output, pre-activation).
+    ``scale`` = folded BN scale the forward used (dx flows through W*scale; dw/db returned are RAW: A^T dz)."""
+    L = _lib.lib()
+    n, h, w, c0 = x.shape
+    k, _, cin_g, cout = w_hwio.shape
+    cin = c0 + (x2.shape[3] if x2 is not None else 0)
+    dw = torch.zeros(w_hwio.shape, dtype=torch.float32, device=x.device)
+    db = torch.zeros(cout, dtype=torch.float32, device=x.device)
+    check(L.tbi_conv2d_wgrad(_dt(x), impl, n, h, w, k, dilation, groups, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
+                             _vp(view(dz)), _p(dw), _p(db), None, 0, _st()), "conv2d_wgrad")
+    if not need_dx:
+        return None, dw, db
+    wb = pack_conv(w_hwio, groups, 1, x.dtype, scale)
+    dx = torch.empty_like(x)
+    dx2 = torch.empty_like(x2) if x2 is not None else None
+    e = _epi(dx, dact=dact, dact_ref=dact_ref, out2=dx2, split_c=c0 if x2 is not None else 0)
+    check(L.tbi_conv2d_dgrad(_dt(x), impl, n, h, w, k, dilation, groups, _vp(view(dz)), cin, _p(wb), C.byref(e), _st()), "conv2d_dgrad")
+    return (dx if x2 is None else (dx, dx2)), dw, db
+
+
+# ------------------------------------------------------------------------------------------ Conv2DTranspose s2
+def conv2d_transpose_s2(x, w_hwoi, bias=None, *, bn=None, act=ACT_NONE, keep=None, x2=None, impl=IMPL_AUTO, out_f32=False):
+    """Conv2DTranspose(k in {3,4}, strides=2, padding='same') [+BN] [+dropout multiplier] [+act]
+    (TBI_ResNest.py:124,209-220; Decoder.py:57-59,120)"""
+    L = _lib.lib()
+    n, h, w, _ = x.shape
+    k, cout = w_hwoi.shape[0], w_hwoi.shape[2]
+    scale, fbias = fold_bn(cout, bias if bias is not None else torch.zeros(cout, device=x.device), bn, x.device)
+    wp = pack_convt(w_hwoi, 0, x.dtype, scale)
+    y = torch.empty(n, 2 * h, 2 * w, cout, dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
+    e = _epi(y, fbias, act, keep=keep, out_f32=int(out_f32))
+    check(L.tbi_conv2d_transpose_s2_fwd(_dt(x), impl, n, h, w, k, _vp(view(x)), _vp(view(x2)) if x2 is not None else None, cout,
+                                        _p(wp), C.byref(e), _st()), "convT_fwd")
+    return y
+
+
+def conv2d_transpose_s2_grads(x, w_hwoi, dz, *, scale=None, x2=None, impl=IMPL_AUTO, need_dx=True):
+    L = _lib.lib()
+    n, h, w, c0 = x.shape
+    k, _, cout, cin = w_hwoi.shape
+    dw = torch.zeros(w_hwoi.shape, dtype=torch.float32, device=x.device)
+    db = torch.zeros(cout, dtype=torch.float32, device=x.device)
+    check(L.tbi_conv2d_transpose_s2_wgrad(_dt(x), impl, n, h, w, k, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
+                                          _vp(view(dz)), _p(dw), _p(db), None, 0, _st()), "convT_wgrad")
+    if not need_dx:
+        return None, dw, db
+    wb = pack_convt(w_hwoi, 1, x.dtype, scale)
+    dx = torch.empty_like(x)
+    dx2 = torch.empty_like(x2) if x2 is not None else None
+    e = _epi(dx, out2=dx2, split_c=c0 if x2 is not None else 0)
+    check(L.tbi_conv2d_transpose_s2_dgrad(_dt(x), impl, n, h, w, k, _vp(view(dz)), cin, _p(wb), C.byref(e), _st()), "convT_dgrad")
+    return (dx if x2 is None else (dx, dx2)), dw, db
+
+
+def bn_param_grad(w, dw_raw, bias, dbias_raw, bn, kind="conv"):
+    """in place: dw_raw -> dw, dbias_raw -> dbias; returns (dgamma, dbeta).  w: HWIO (conv) or HWOI (convt)."""
+    L = _lib.lib()
+    g, _, m, v = (_f32(t) for t in bn)
+    if kind == "conv":
+        k, _, cin_g, cout = w.shape
+        lay = (k * k * cin_g, 1, cout, 1)
+    else:
+        k, _, cout, cin = w.shape
+        lay = (k * k, cin, cout * cin, cin)
+    dgamma = torch.zeros(cout, dtype=torch.float32, device=w.device)
+    dbeta = torch.zeros(cout, dtype=torch.float32, device=w.device)
+    w32, b32 = _f32(w), _f32(bias)
+    check(L.tbi_bn_param_grad(cout, *lay, _p(w32), _p(dw_raw), _p(b32), _p(dbias_raw), _p(g), _p(m), _p(v), BN_EPS,
+                              _p(dgamma), _p(dbeta), _st()), "bn_param_grad")
+    return dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------ pooling etc.
+def avgpool2x2(x):
+    L = _lib.lib()
+    n, h, w, c = x.shape
+    y = torch.empty(n, h // 2, w // 2, c, dtype=x.dtype, device=x.device)
+    check(L.tbi_avgpool2x2_fwd(_dt(x), n, h, w, _vp(view(x)), _vp(view(y)), _st()), "avgpool_fwd")
+    return y
+
+
+def avgpool2x2_bwd(dy, *, dact=ACT_NONE, dact_ref=None, accumulate_into=None):
+    L = _lib.lib()
+    n, ho, wo, c = dy.shape
+    dx = accumulate_into if accumulate_into is not None else torch.empty(n, 2 * ho, 2 * wo, c, dtype=dy.dtype, device=dy.device)
+    check(L.tbi_avgpool2x2_bwd(_dt(dy), n, 2 * ho, 2 * wo, _vp(view(dy)), _vp(view(dx)), int(accumulate_into is not None), dact,
+                               _vp(view(dact_ref)) if dact_ref is not None else None, _st()), "avgpool_bwd")
+    return dx
+
+
+def act_bwd(dy, y_ref, act, keep=None):
+    L = _lib.lib()
+    n, h, w, c = dy.shape
+    dz = torch.empty_like(dy)
+    check(L.tbi_act_bwd(_dt(dy), n * h * w, act, _vp(view(dy)), _vp(view(y_ref)), _p(keep), _vp(view(dz)), _st()), "act_bwd")
+    return dz
+
+
+def colsum(x):
+    L = _lib.lib()
+    n, h, w, c = x.shape
+    out = torch.zeros(c, dtype=torch.float32, device=x.device)
+    check(L.tbi_colsum(_dt(x), n * h * w, _vp(view(x)), _p(out), _st()), "colsum")
+    return out
+
+
+class SplitAttention:
+    """Radix split-attention tail for K cardinal groups at once (TBI_ResNest.py:175-207).
+    u: [n,h,w,K*R*c] (channel order k,r,c) -> v: [n,h,w,K*c].  Parameters are fp32 tensors:
+    w1 [K,c,c/2], b1 [K,c/2], gamma/beta/mean/var [K,c/2], w2 [K,R,c/2,c], b2 [K,R,c]."""
+
+    def __init__(self, kpaths, radix, c, w1, b1, gamma, beta, mean, var, w2, b2, act=ACT_ELU):
+        self.K, self.R, self.c, self.act = kpaths, radix, c, act
+        self.params = [_f32(t) for t in (w1, b1, gamma, beta, mean, var, w2, b2)]
+
+    def _desc(self, u):
+        n, h, w, _ = u.shape
+        dev = u.device
+        self.gap = torch.empty(n, self.K, self.c, dtype=torch.float32, device=dev)
+        self.h1 = torch.empty(n, self.K, self.c // 2, dtype=torch.float32, device=dev)
+        self.att = torch.empty(n, self.K, self.R, self.c, dtype=torch.float32, device=dev)
+        return SplitAtt(_dt(u), n, h, w, self.K, self.R, self.c, self.act, BN_EPS, *[_p(t) for t in self.params],
+                        _p(self.gap), _p(self.h1), _p(self.att))
+
+    def forward(self, u):
+        L = _lib.lib()
+        n, h, w, _ = u.shape
+        self.desc = self._desc(u)
+        v = torch.empty(n, h, w, self.K * self.c, dtype=u.dtype, device=u.device)
+        check(L.tbi_split_attention_fwd(C.byref(self.desc), _vp(view(u)), _vp(view(v)), _st()), "split_attention_fwd")
+        return v
+
+    def backward(self, u, dv):
+        """-> (dz_u = dL/du * act'(u), dict of parameter gradients)"""
+        L = _lib.lib()
+        n = u.shape[0]
+        K, R, c = self.K, self.R, self.c
+        dev = u.device
+        du = torch.empty_like(u)
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        g = dict(w1=z(K, c, c // 2), b1=z(K, c // 2), gamma=z(K, c // 2), beta=z(K, c // 2), w2=z(K, R, c // 2, c), b2=z(K, R, c))
+        scratch = torch.empty(n * K * (R * c + 2 * c), dtype=torch.float32, device=dev)
+        check(L.tbi_split_attention_bwd(C.byref(self.desc), _vp(view(u)), _vp(view(dv)), _vp(view(du)), _p(g["w1"]), _p(g["b1"]),
+                                        _p(g["gamma"]), _p(g["beta"]), _p(g["w2"]), _p(g["b2"]), _p(scratch), _st()), "split_attention_bwd")
+        return du, g
+
+
+def softmax_loss(logits, y, dlogits_dtype=torch.float32):
+    """softmax + my_loss_cat + accuracy count + dlogits (TBI_ResNest.py:125,234-248,48-51)"""
+    L = _lib.lib()
+    n, h, w, nc = logits.shape
+    dev = logits.device
+    probs = torch.empty_like(logits)
+    loss = torch.empty(h, w, dtype=torch.float32, device=dev)
+    correct = torch.zeros(1, dtype=torch.int32, device=dev)
+    dlog = torch.empty(n, h, w, nc, dtype=dlogits_dtype, device=dev)
+    check(L.tbi_softmax_loss_fwd_bwd(F32 if dlogits_dtype == torch.float32 else BF16, n, h, w, nc, _p(logits), _p(y), _p(probs),
+                                     _p(loss), _p(correct), _p(dlog), _st()), "softmax_loss")
+    return probs, loss, correct, dlog
+
+
+def adam_step(p, g, m, v, step_count, lr, b1=0.9, b2=0.999, eps=1e-7, grad_scale=1.0):
+    L = _lib.lib()
+    check(L.tbi_adam_multi(p.numel(), _p(p), _p(g), _p(m), _p(v), _p(step_count), lr, b1, b2, eps, grad_scale, _st()), "adam")
+    check(L.tbi_adam_advance(_p(step_count), _st()), "adam_advance")

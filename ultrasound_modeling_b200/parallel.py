@@ -1,0 +1,69 @@
+"""Data-parallel gradient exchange for the TBI_ResNest step (reference: tf.distribute.MirroredStrategy,
+MainParallel.py:16,130 -- replicated variables, one all-reduce(SUM) of the gradients per step).
+
+One process per GPU; parameters, Adam state and the flat gradient buffer are replicated; the batch is
+sharded (weak scaling).  The only collective is the all-reduce of the flat fp32 gradient buffer, cut
+into contiguous buckets in BACKWARD order and launched on a side stream as soon as the backward
+program has finalised a bucket, so NCCL over NVLink/NVSwitch overlaps the remaining backward kernels.
+Adam then applies grad_scale = 1/world (average).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def plan_buckets(marks: Sequence[Tuple[int, int]], total: int, bucket_elems: int) -> List[Tuple[int, int, int]]:
+    """marks: (calls_issued, watermark) in backward order, watermark non-increasing; everything at flat
+    offset >= watermark is final once `calls_issued` backward calls have been enqueued.
+    -> [(calls_issued, lo, hi)]: after that many calls, all-reduce flat[lo:hi].  Buckets tile [0,total)
+    exactly once, each >= bucket_elems except possibly the last."""
+    out: List[Tuple[int, int, int]] = []
+    hi = total
+    for calls, wm in marks:
+        wm = min(wm, hi)
+        if hi - wm >= bucket_elems or (wm == 0 and hi > 0):
+            out.append((calls, wm, hi))
+            hi = wm
+    if hi > 0:                                   # marks never reached 0 (should not happen): flush at the end
+        out.append((marks[-1][0] if marks else 0, 0, hi))
+    return out
+
+
+class GradSync:
+    def __init__(self, process_group=None, bucket_bytes: int = 25 << 20):
+        if not dist.is_initialized():
+            raise RuntimeError("GradSync needs torch.distributed to be initialised (backend nccl on GPUs)")
+        self.pg = process_group
+        self.world_size = dist.get_world_size(process_group)
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self.comm_stream: Optional[torch.cuda.Stream] = None
+        self._plan = None
+        self._plan_key = None
+
+    def allreduce(self, flat_slice: torch.Tensor):
+        dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def backward_and_sync(self, engine):
+        """run engine.prog_bwd, interleaving bucket all-reduces on a side stream"""
+        key = (id(engine), engine.N)
+        if self._plan_key != key:
+            self._plan = plan_buckets(engine.bwd_marks, engine.P.total, self.bucket_elems)
+            self._plan_key = key
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=engine.device)
+        cur = torch.cuda.current_stream(engine.device)
+        engine.grads.zero_()
+        pos = 0
+        for calls, lo, hi in self._plan:
+            engine._run(engine.prog_bwd[pos:calls], cur.cuda_stream)
+            pos = calls
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                self.allreduce(engine.grads[lo:hi])
+        engine._run(engine.prog_bwd[pos:], cur.cuda_stream)
+        cur.wait_stream(self.comm_stream)
