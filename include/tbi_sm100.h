@@ -90,6 +90,12 @@ typedef struct {
     int32_t  ntaps;
     int32_t  dy[TBI_MAX_TAPS], dx[TBI_MAX_TAPS];
     const void* w;
+    /* nphase == 4: the four output-parity phases of a k=4 stride-2 transposed conv in ONE launch.
+     * Phase p uses taps ph_dy/ph_dx[p][0..ntaps), writes to (2*gy+ph_off_y[p], 2*gx+ph_off_x[p]) and its
+     * weights are rows [p*cout_total, (p+1)*cout_total) of w.  nphase <= 1: dy/dx/epi offsets as given. */
+    int32_t  nphase;
+    int32_t  ph_dy[4][4], ph_dx[4][4];
+    int32_t  ph_off_y[4], ph_off_x[4];
     tbi_epilogue epi;
 } tbi_tapgemm;
 

@@ -224,6 +224,7 @@ class TBIResNestOracle:
         self.adam_m = {k: torch.zeros_like(v) for k, v in self.params.items() if is_trainable(k)}
         self.adam_v = {k: torch.zeros_like(v) for k, v in self.params.items() if is_trainable(k)}
         self.adam_t = 0
+        self._inter = None
 
     # -- helpers -----------------------------------------------------------------------
     def _conv(self, x, name, dilation=1):
@@ -253,7 +254,11 @@ class TBIResNestOracle:
         us = []
         for r in range(self.radix):
             t = F.elu(self._bn(self._conv(x, f"{name}1_r{r}"), f"{name}1_{r}bn"))
+            if self._inter is not None:
+                self._inter[f"{name}/T1_r{r}"] = t
             t = F.elu(self._bn(self._conv(t, f"{name}2_r{r}"), f"{name}2_{r}bn"))
+            if self._inter is not None:
+                self._inter[f"{name}/U_r{r}"] = t
             us.append(t)
         return self.split_attention(us, f"{name}_att")
 
@@ -261,6 +266,8 @@ class TBIResNestOracle:
         """TBI_ResNest.py:130-151."""
         cards = [self.cardinal(x, f"{stage}_car_k{k}") for k in range(self.kpaths)]
         c1 = torch.cat(cards, dim=3)
+        if self._inter is not None:
+            self._inter[f"{stage}/V"] = c1
         c2 = self._conv(c1, auto_conv_name(auto_idx))
         if x.shape[-1] != out:
             x = F.elu(self._bn(self._conv(x, f"{stage}_cc"), f"{stage}_scbn"))
@@ -281,6 +288,7 @@ class TBIResNestOracle:
         disable dropout (deterministic parity)."""
         x = x.to(self.dtype)
         inter = {}
+        self._inter = inter if return_intermediates else None
         t = F.elu(self._conv(x, "Conv1"))
         t = F.elu(self._conv(t, "conv2_1_1"))
         t = F.elu(self._bn(self._conv(t, "conv2_1_2"), "conv2_1_2bn"))
@@ -288,6 +296,7 @@ class TBIResNestOracle:
         for i, (stage, out) in enumerate(STAGES):
             s = self.residual_S(pools[-1], stage, out, i)
             inter[stage] = s
+            inter[f"pool_{i + 1}"] = pools[-1]
             pools.append(avgpool2(s))                         # conv2_pool .. conv6_pool
         up = pools[5]
         for i, (_, drop) in enumerate(UPSAMPLES):

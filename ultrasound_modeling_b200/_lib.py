@@ -6,6 +6,7 @@ not sm_100, every op raises.
 from __future__ import annotations
 
 import ctypes as C
+import hashlib
 import os
 import subprocess
 from pathlib import Path
@@ -13,7 +14,8 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 LIB_PATH = _PKG / "libtbi_sm100.so"
-SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "bandwidth.cu"]
+HASH_PATH = _PKG / "libtbi_sm100.so.hash"
+SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapwgrad_tc.cu", "bandwidth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -23,18 +25,32 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 MAX_TAPS = 16
 
 
+def _source_hash() -> str:
+    """content hash of everything the library is built from (mtimes do not survive a snapshot copy)"""
+    h = hashlib.sha256()
+    deps = sorted(_CSRC.glob("*.cu")) + sorted(_CSRC.glob("*.cuh")) + [_PKG.parent / "include" / "tbi_sm100.h"]
+    for d in deps:
+        h.update(d.name.encode()); h.update(d.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    return not (LIB_PATH.exists() and HASH_PATH.exists() and HASH_PATH.read_text().strip() == _source_hash())
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile csrc/*.cu into libtbi_sm100.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [_CSRC / s for s in SOURCES]
-    deps = srcs + [_CSRC / "tbi_common.cuh", _PKG.parent / "include" / "tbi_sm100.h"]
-    deps += sorted(_CSRC.glob("*.cuh"))
-    if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
+    """Compile csrc/*.cu into libtbi_sm100.so for sm_100a (nvcc cross-compiles without a GPU).
+    Rebuilds only when the sources' content hash differs from the one recorded beside the .so."""
+    if not force and not is_stale():
         return LIB_PATH
+    srcs = [_CSRC / s for s in SOURCES]
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, srcs)]
     if verbose:
         print(" ".join(cmd))
     subprocess.run(cmd, check=True, cwd=str(_CSRC))
+    HASH_PATH.write_text(_source_hash() + "\n")
     return LIB_PATH
 
 
@@ -54,7 +70,9 @@ class TapGemm(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("impl", C.c_int32), ("n", C.c_int32), ("gh", C.c_int32), ("gw", C.c_int32),
                 ("groups", C.c_int32), ("cin_g", C.c_int32), ("cout_g", C.c_int32), ("src", View * 2),
                 ("in_stride", C.c_int32), ("ntaps", C.c_int32), ("dy", C.c_int32 * MAX_TAPS),
-                ("dx", C.c_int32 * MAX_TAPS), ("w", C.c_void_p), ("epi", Epilogue)]
+                ("dx", C.c_int32 * MAX_TAPS), ("w", C.c_void_p), ("nphase", C.c_int32),
+                ("ph_dy", (C.c_int32 * 4) * 4), ("ph_dx", (C.c_int32 * 4) * 4), ("ph_off_y", C.c_int32 * 4),
+                ("ph_off_x", C.c_int32 * 4), ("epi", Epilogue)]
 
 
 class TapWgrad(C.Structure):
@@ -124,7 +142,7 @@ def lib() -> C.CDLL:
     """Load (building first if the .so is absent and nvcc is present).  Raises if it cannot."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
+        if is_stale():                      # sources changed (or never built): rebuild in-tree; raises if nvcc fails
             build()
         L = C.CDLL(str(LIB_PATH))
         for name, (res, args) in SIGNATURES.items():

@@ -136,6 +136,20 @@ extern "C" int tbi_conv2d_transpose_s2_fwd(int dtype, int impl, int n, int h, in
                                            void* stream) {
     TBI_CHECK(ksize == 3 || ksize == 4, TBI_ERR_UNSUPPORTED, "convT: ksize %d", ksize);
     const int cin = src0->c + ((src1 && src1->ptr) ? src1->c : 0);
+    if (ksize == 4) {                    // every phase has 2x2 taps: one descriptor, one launch on the tcgen05 path
+        tbi_tapgemm d; memset(&d, 0, sizeof(d));
+        d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = 1;
+        d.src[0] = *src0; if (src1 && src1->ptr) d.src[1] = *src1;
+        d.cin_g = cin; d.cout_g = cout; d.in_stride = 1; d.w = w_packed; d.epi = *epi; d.epi.out_stride = 2;
+        d.nphase = 4;
+        for (int ph = 0; ph < 4; ++ph) {
+            int ky[TBI_MAX_TAPS], kx[TBI_MAX_TAPS], dy[TBI_MAX_TAPS], dx[TBI_MAX_TAPS];
+            d.ntaps = tbi_convt_phase_taps(ksize, ph >> 1, ph & 1, ky, kx, dy, dx);
+            for (int t = 0; t < d.ntaps; ++t) { d.ph_dy[ph][t] = dy[t]; d.ph_dx[ph][t] = dx[t]; }
+            d.ph_off_y[ph] = ph >> 1; d.ph_off_x[ph] = ph & 1;
+        }
+        return tbi_tapgemm_run(&d, stream);
+    }
     size_t woff = 0;
     for (int ph = 0; ph < 4; ++ph) {
         tbi_tapgemm d; memset(&d, 0, sizeof(d));

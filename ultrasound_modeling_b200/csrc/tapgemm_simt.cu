@@ -209,7 +209,20 @@ __global__ void __launch_bounds__(NT) tapwgrad_simt_kernel(const __grid_constant
 
 }  // namespace
 
-int tbi_tapgemm_simt(const tbi_tapgemm* d, cudaStream_t s) {
+int tbi_tapgemm_simt(const tbi_tapgemm* dd, cudaStream_t s) {
+    if (dd->nphase > 1) {                                  // one launch per parity phase on this path
+        for (int p = 0; p < dd->nphase; ++p) {
+            tbi_tapgemm q = *dd;
+            q.nphase = 0;
+            for (int t = 0; t < dd->ntaps; ++t) { q.dy[t] = dd->ph_dy[p][t]; q.dx[t] = dd->ph_dx[p][t]; }
+            q.epi.out_stride = 2; q.epi.out_off_y = dd->ph_off_y[p]; q.epi.out_off_x = dd->ph_off_x[p];
+            q.w = (const char*)dd->w + (size_t)p * dd->cout_g * dd->groups * dd->ntaps * dd->cin_g * tbi_dtype_size(dd->dtype);
+            int rc = tbi_tapgemm_simt(&q, s);
+            if (rc) return rc;
+        }
+        return TBI_OK;
+    }
+    const tbi_tapgemm* d = dd;
     TBI_CHECK(d->ntaps >= 1 && d->ntaps <= TBI_MAX_TAPS, TBI_ERR_BAD_SHAPE, "tapgemm: ntaps=%d", d->ntaps);
     TBI_CHECK(d->groups >= 1 && (d->groups == 1 || d->src[1].ptr == nullptr), TBI_ERR_UNSUPPORTED,
               "tapgemm: groups>1 needs a single source");

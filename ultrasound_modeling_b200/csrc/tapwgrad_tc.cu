@@ -1,0 +1,275 @@
+// tcgen05 weight-gradient tap-GEMM (bf16 in, fp32 accumulate in TMEM) for sm_100a.
+//
+//   dw[tap][ci][co] += sum_pixels a[pixel + a_off(tap)][ci] * b[pixel + b_off(tap)][co]
+//
+// Per tap this is a GEMM with M = ci, N = co and K = PIXELS.  Activations are NHWC, so both operands
+// arrive "MN-major" (the M/N index -- the channel -- is the contiguous one): every K-step loads, per
+// 64-channel block, one 5-D TMA box [64 pixels x 64 channels] (128-byte rows, 128B swizzle) which is
+// exactly the canonical MN-major SW128 UMMA layout (atom = 64 channels x 8 pixels; SBO = 1024 B between
+// 8-pixel groups; LBO = one box = 8192 B between 64-channel blocks).  Shifted / stride-2 taps are box
+// coordinates, out-of-image pixels are zero-filled by TMA (== they contribute nothing).
+// One CTA owns one (tap, 128-ci, BN-co) tile of dw and a contiguous range of pixel tiles (split-K); the
+// partial result is reduced into the fp32 gradient with red.global.add (caller zeroes dw).
+// Warp roles as in tapgemm_tc.cu.
+#include "tbi_common.cuh"
+#include "tc_common.cuh"
+#include <mutex>
+#include <string.h>
+
+namespace {
+
+constexpr int WG_THREADS = 192;
+constexpr int KP = 64;                       // pixels per K-step
+constexpr uint32_t BOX_BYTES = KP * 128;     // one [64 px x 64 ch] bf16 box
+
+struct alignas(64) TcWgradParams {
+    CUtensorMap a[2];
+    CUtensorMap b;
+    int n, gh, gw;
+    int ltw, lth;                 // pixel tile: tw x th x tn = 64
+    int tiles_x, tiles_y, tiles_b;
+    int cin_g, cout_g, groups, c0;
+    int ci_tiles, co_tiles, ntaps;
+    int nb;                       // 64-channel blocks of the co tile (BN = 64*nb)
+    int stages, tiles_per_cta;
+    int b_cbase, b_cpix;
+    signed char aqy[16], aqx[16], bqy[16], bqx[16], bay[16], bax[16];
+    float* dw;
+    long long tap_stride, ci_stride, co_stride;
+};
+
+__device__ __forceinline__ void wg_wait(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!tc::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("tbi tcgen05 wgrad: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    }
+}
+
+template <int NB>
+__global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_constant__ TcWgradParams p) {
+    constexpr int BN = 64 * NB;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    const int stages = p.stages;
+    constexpr uint32_t STAGE_BYTES = (2 + NB) * BOX_BYTES;
+    uint8_t* bar_base = smem + (size_t)stages * STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
+    uint64_t* empty = full + stages;
+    uint64_t* tfull = empty + stages;
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&p.a[0]); tc::prefetch_tmap(&p.b);
+        for (int s = 0; s < stages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(tfull, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<BN>(tslot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tslot;
+
+    int t = blockIdx.x;
+    const int tap = t % p.ntaps; t /= p.ntaps;
+    const int co_t = t % p.co_tiles; const int ci_t = t / p.co_tiles;
+    const int g = blockIdx.z;
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+    const int tile_beg = blockIdx.y * p.tiles_per_cta;
+    const int tile_end = min(total_tiles, tile_beg + p.tiles_per_cta);
+    const int iters = tile_end - tile_beg;
+    const int tw = 1 << p.ltw, th = 1 << p.lth, tn = KP >> (p.ltw + p.lth);
+    const int ci0 = ci_t * 128, co0 = co_t * BN;
+
+    if (warp == 0) {
+        if (lane == 0 && iters > 0) {
+            // ===== TMA producer =====
+            // channel coordinates of the two 64-wide A blocks (virtual concat: a block lives in one source)
+            int asrc[2], ach[2];
+            for (int j = 0; j < 2; ++j) {
+                int ch = ci0 + 64 * j + (p.groups > 1 ? g * p.cin_g : 0);
+                int src = 0;
+                if (p.groups == 1 && ch >= p.c0 && p.c0 < p.cin_g) { src = 1; ch -= p.c0; }
+                asrc[j] = src; ach[j] = ch;
+            }
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % stages;
+                wg_wait(&empty[s], (((uint32_t)(it / stages)) & 1u) ^ 1u);
+                int tt = tile_beg + it;
+                const int tix = tt % p.tiles_x; tt /= p.tiles_x;
+                const int tiy = tt % p.tiles_y; const int tib = tt / p.tiles_y;
+                const int x0 = tix * tw, y0 = tiy * th, n0 = tib * tn;
+                uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+                tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    tc::tma_load_5d(st + j * BOX_BYTES, &p.a[asrc[j]], &full[s], ach[j], x0 + (int)p.aqx[tap], 0, y0 + (int)p.aqy[tap], n0);
+#pragma unroll
+                for (int j = 0; j < NB; ++j)
+                    tc::tma_load_5d(st + (2 + j) * BOX_BYTES, &p.b, &full[s], p.b_cbase + g * p.cout_g + co0 + 64 * j + (int)p.bax[tap] * p.b_cpix,
+                                    x0 + (int)p.bqx[tap], (int)p.bay[tap], y0 + (int)p.bqy[tap], n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && iters > 0) {
+            // ===== MMA issuer: D[ci][co] += A^T[ci][px] * B[px][co], both operands MN-major =====
+            const uint32_t idesc = tc::make_idesc_bf16(128, BN, 1, 1);
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % stages;
+                wg_wait(&full[s], ((uint32_t)(it / stages)) & 1u);
+                tc::tc_fence_after();
+                const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint32_t b_addr = a_addr + 2 * BOX_BYTES;
+#pragma unroll
+                for (int k = 0; k < KP / 16; ++k) {
+                    // 16 pixels = 2 swizzle atoms along K: +2048 B per step; LBO = box (next 64 channels), SBO = 1024 B
+                    const uint64_t da = tc::make_smem_desc(a_addr + k * 2048, BOX_BYTES, 1024, 2u);
+                    const uint64_t db = tc::make_smem_desc(b_addr + k * 2048, BOX_BYTES, 1024, 2u);
+                    tc::umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                }
+                tc::umma_commit(&empty[s]);
+            }
+            tc::umma_commit(tfull);
+        }
+        __syncwarp();
+    } else if (iters > 0) {
+        // ===== epilogue: lane = ci row, columns = co; reduce into the fp32 gradient =====
+        const int q = warp & 3;
+        const int ci = ci0 + q * 32 + lane;
+        const bool row_ok = ci < p.cin_g;
+        wg_wait(tfull, 0);
+        tc::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* base = p.dw + (size_t)tap * p.tap_stride + (size_t)ci * p.ci_stride;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tc::tmem_ld32(taddr + c, r);
+            tc::tmem_ld_wait();
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = co0 + c + j;
+                    if (co < p.cout_g) atomicAdd(base + (size_t)(g * p.cout_g + co) * p.co_stride, __uint_as_float(r[j]));
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<BN>(tmem_base);
+}
+
+bool wg_aligned_view(const tbi_view& v) {
+    return v.ptr == nullptr || (v.cstride % 8 == 0 && v.coff % 8 == 0 && v.c % 8 == 0 && ((uintptr_t)v.ptr & 15) == 0);
+}
+int wg_ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// 5-D activation map with a [64 ch x tw x 1 x th x tn] box (see make_act_tmap in tapgemm_tc.cu)
+int wg_act_tmap(CUtensorMap* out, const tbi_view& v, int n, int stride, int tw, int th, int tn, int* cbase, int* cpix) {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5] = {64u, (uint32_t)tw, 1u, (uint32_t)th, (uint32_t)tn};
+    const uint64_t px = (uint64_t)v.cstride * 2;
+    void* base;
+    if (stride == 1) {
+        dims[0] = (uint64_t)v.c; dims[1] = (uint64_t)v.w; dims[2] = 1; dims[3] = (uint64_t)v.h; dims[4] = (uint64_t)n;
+        strides[0] = px; strides[1] = px * v.w; strides[2] = px * v.w; strides[3] = px * v.w * v.h;
+        base = (char*)v.ptr + (size_t)v.coff * 2;
+        *cbase = 0; *cpix = 0;
+    } else {
+        dims[0] = (uint64_t)v.cstride * 2; dims[1] = (uint64_t)v.w / 2; dims[2] = 2; dims[3] = (uint64_t)v.h / 2; dims[4] = (uint64_t)n;
+        strides[0] = px * 2; strides[1] = px * v.w; strides[2] = px * v.w * 2; strides[3] = px * v.w * v.h;
+        base = v.ptr;
+        *cbase = v.coff; *cpix = v.cstride;
+    }
+    return tbi_make_tmap_bf16(out, base, 5, dims, strides, box, 128);
+}
+
+template <int NB>
+int launch_wg(const TcWgradParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tapwgrad_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (attr_err != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    tapwgrad_tc_kernel<NB><<<grid, WG_THREADS, smem, s>>>(p);
+    TBI_CUDA_LAUNCH_CHECK("tapwgrad_tc");
+    return TBI_OK;
+}
+
+}  // namespace
+
+bool tbi_tapwgrad_tc_supported(const tbi_tapwgrad* d, const char** why) {
+#define NO(msg) do { *why = msg; return false; } while (0)
+    if (d->dtype != TBI_BF16) NO("storage dtype is not bf16");
+    if (!tbi_get_encode_tiled()) NO("no cuTensorMapEncodeTiled");
+    if (d->ntaps < 1 || d->ntaps > TBI_MAX_TAPS) NO("ntaps");
+    if (d->a_stride != 1) NO("a_stride");
+    if (d->b_stride != 1 && d->b_stride != 2) NO("b_stride");
+    if (d->groups > 1 && d->a_src[1].ptr) NO("groups with two sources");
+    if (d->a_src[1].ptr && d->a_src[0].c % 64 != 0) NO("first source of a concat must be a multiple of 64 channels");
+    if (d->cin_g % 8 != 0 || d->cout_g % 8 != 0) NO("channels per group must be multiples of 8");
+    if (d->cin_g < 16 || d->cout_g < 16) NO("too few channels for the tensor-core path");
+    if (!wg_aligned_view(d->a_src[0]) || !wg_aligned_view(d->a_src[1]) || !wg_aligned_view(d->b_src)) NO("view not 16-byte aligned");
+    if (d->b_stride == 2 && ((d->b_src.h | d->b_src.w) & 1)) NO("stride-2 gather needs even dims");
+    for (int t = 0; t < d->ntaps; ++t)
+        if (d->a_dy[t] < -64 || d->a_dy[t] > 64 || d->a_dx[t] < -64 || d->a_dx[t] > 64 || d->b_dy[t] < -64 || d->b_dy[t] > 64 || d->b_dx[t] < -64 || d->b_dx[t] > 64) NO("tap offset range");
+    return true;
+#undef NO
+}
+
+int64_t tbi_tapwgrad_tc_workspace(const tbi_tapwgrad*) { return 0; }   // partials are reduced with red.global.add: no workspace
+
+int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s) {
+    const char* why = "";
+    if (!tbi_tapwgrad_tc_supported(d, &why)) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapwgrad_tc: %s", why);
+    TcWgradParams p; memset(&p, 0, sizeof(p));
+    int ltw = wg_ilog2_ceil(d->gw); if (ltw > 3) ltw = 3;
+    int lth = wg_ilog2_ceil(d->gh); if (lth > 6 - ltw) lth = 6 - ltw;
+    const int tw = 1 << ltw, th = 1 << lth, tn = KP >> (ltw + lth);
+    p.n = d->n; p.gh = d->gh; p.gw = d->gw; p.ltw = ltw; p.lth = lth;
+    p.tiles_x = (d->gw + tw - 1) / tw; p.tiles_y = (d->gh + th - 1) / th; p.tiles_b = (d->n + tn - 1) / tn;
+    p.cin_g = d->cin_g; p.cout_g = d->cout_g; p.groups = d->groups;
+    p.c0 = d->groups > 1 ? d->cin_g : d->a_src[0].c;
+    p.ntaps = d->ntaps;
+    p.ci_tiles = (d->cin_g + 127) / 128;
+    p.nb = d->cout_g > 64 ? 2 : 1;
+    const int bn = 64 * p.nb;
+    p.co_tiles = (d->cout_g + bn - 1) / bn;
+    for (int t = 0; t < d->ntaps; ++t) {
+        p.aqy[t] = (signed char)d->a_dy[t]; p.aqx[t] = (signed char)d->a_dx[t];
+        if (d->b_stride == 1) { p.bqy[t] = (signed char)d->b_dy[t]; p.bqx[t] = (signed char)d->b_dx[t]; p.bay[t] = 0; p.bax[t] = 0; }
+        else {
+            const int ay = d->b_dy[t] & 1, ax = d->b_dx[t] & 1;
+            p.bay[t] = (signed char)ay; p.bax[t] = (signed char)ax;
+            p.bqy[t] = (signed char)((d->b_dy[t] - ay) / 2); p.bqx[t] = (signed char)((d->b_dx[t] - ax) / 2);
+        }
+    }
+    int cb, cp;
+    int rc = wg_act_tmap(&p.a[0], d->a_src[0], d->n, 1, tw, th, tn, &cb, &cp); if (rc) return rc;
+    if (d->groups == 1 && d->a_src[1].ptr) { rc = wg_act_tmap(&p.a[1], d->a_src[1], d->n, 1, tw, th, tn, &cb, &cp); if (rc) return rc; }
+    else p.a[1] = p.a[0];
+    rc = wg_act_tmap(&p.b, d->b_src, d->n, d->b_stride, tw, th, tn, &p.b_cbase, &p.b_cpix); if (rc) return rc;
+    p.dw = d->dw; p.tap_stride = d->tap_stride; p.ci_stride = d->ci_stride; p.co_stride = d->co_stride;
+
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+    const long long out_tiles = (long long)d->ntaps * p.ci_tiles * p.co_tiles * d->groups;
+    long long ksplit = (4LL * tbi_sm_count() + out_tiles - 1) / out_tiles;      // ~4 CTAs per SM in flight overall
+    if (ksplit > total_tiles) ksplit = total_tiles;
+    if (ksplit < 1) ksplit = 1;
+    p.tiles_per_cta = (int)((total_tiles + ksplit - 1) / ksplit);
+    ksplit = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    const uint32_t stage_bytes = (2 + p.nb) * BOX_BYTES;
+    int stages = (int)(96 * 1024 / stage_bytes);
+    if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    dim3 grid((unsigned)(d->ntaps * p.ci_tiles * p.co_tiles), (unsigned)ksplit, (unsigned)d->groups);
+    rc = p.nb == 2 ? launch_wg<2>(p, grid, smem, s) : launch_wg<1>(p, grid, smem, s);
+    if (rc) return rc;
+    if (d->dbias)                      // bias gradient = column sum of the (unshifted) output gradient
+        return tbi_colsum(d->dtype, (int64_t)d->n * d->b_src.h * d->b_src.w, &d->b_src, d->dbias, (void*)s);
+    return TBI_OK;
+}

@@ -116,7 +116,7 @@ def conv2d(x, w_hwio, bias=None, *, dilation=1, groups=1, bn=None, act=ACT_NONE,
 
 
 def conv2d_grads(x, w_hwio, dz, *, dilation=1, groups=1, scale=None, x2=None, impl=IMPL_AUTO, need_dx=True,
-                 dact=ACT_NONE, dact_ref=None):
+                 dact=ACT_NONE, dact_ref=None, wgrad_impl=None):
     """gradients of the conv w.r.t. (input[s], HWIO kernel, bias) given dz = dL/d(conv output, pre-activation).
     ``scale`` = folded BN scale the forward used (dx flows through W*scale; dw/db returned are RAW: A^T dz)."""
     L = _lib.lib()
@@ -125,7 +125,7 @@ def conv2d_grads(x, w_hwio, dz, *, dilation=1, groups=1, scale=None, x2=None, im
     cin = c0 + (x2.shape[3] if x2 is not None else 0)
     dw = torch.zeros(w_hwio.shape, dtype=torch.float32, device=x.device)
     db = torch.zeros(cout, dtype=torch.float32, device=x.device)
-    check(L.tbi_conv2d_wgrad(_dt(x), impl, n, h, w, k, dilation, groups, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
+    check(L.tbi_conv2d_wgrad(_dt(x), impl if wgrad_impl is None else wgrad_impl, n, h, w, k, dilation, groups, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
                              _vp(view(dz)), _p(dw), _p(db), None, 0, _st()), "conv2d_wgrad")
     if not need_dx:
         return None, dw, db
@@ -153,13 +153,13 @@ def conv2d_transpose_s2(x, w_hwoi, bias=None, *, bn=None, act=ACT_NONE, keep=Non
     return y
 
 
-def conv2d_transpose_s2_grads(x, w_hwoi, dz, *, scale=None, x2=None, impl=IMPL_AUTO, need_dx=True):
+def conv2d_transpose_s2_grads(x, w_hwoi, dz, *, scale=None, x2=None, impl=IMPL_AUTO, need_dx=True, wgrad_impl=None):
     L = _lib.lib()
     n, h, w, c0 = x.shape
     k, _, cout, cin = w_hwoi.shape
     dw = torch.zeros(w_hwoi.shape, dtype=torch.float32, device=x.device)
     db = torch.zeros(cout, dtype=torch.float32, device=x.device)
-    check(L.tbi_conv2d_transpose_s2_wgrad(_dt(x), impl, n, h, w, k, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
+    check(L.tbi_conv2d_transpose_s2_wgrad(_dt(x), impl if wgrad_impl is None else wgrad_impl, n, h, w, k, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
                                           _vp(view(dz)), _p(dw), _p(db), None, 0, _st()), "convT_wgrad")
     if not need_dx:
         return None, dw, db
