@@ -163,9 +163,11 @@ int tbi_conv2d_transpose_s2_dgrad(int dtype, int impl, int n, int h, int w, int 
                                   const void* w_packed_dgrad, const tbi_epilogue* epi, void* stream);
 /* wgrad into Keras HWOI [k,k,cout,cin] fp32, ADDED.                                             */
 int tbi_conv2d_transpose_s2_wgrad(int dtype, int impl, int n, int h, int w, int ksize,
-                                  const tbi_view* x0, const tbi_view* x1, const tbi_view* dz,
+                                  const tbi_view* x0, const tbi_view* x1, const tbi_view* dz, int cout,
                                   float* dw_hwoi, float* dbias, void* workspace, int64_t workspace_bytes,
                                   void* stream);
+/* (cout <= dz->c: dz may be zero-padded along channels to keep its pixel records 16-byte aligned,
+ *  e.g. the 3-class head gradient stored with 16 channels; only the first cout are real.)             */
 
 /* ---- weight packing (master fp32 Keras layout -> K-major compute copies, BN scale folded) ----
  * scale: per-output-channel multiplier (gamma/sqrt(var+eps)) or NULL.
@@ -177,8 +179,10 @@ int tbi_pack_conv_weights(int dtype, int mode, int ksize, int groups, int cin_g,
 /* W is HWOI [k,k,cout,cin].
  * mode 0 = FWD  : out[phase=(a,b)][co][t][ci] with t over the taps of that phase (order = tbi_convt_phase_taps)
  * mode 1 = DGRAD: out[ci][ky*k+kx][co]         = W[ky][kx][co][ci] * scale[co]                   */
-int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout,
+int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout, int cout_pad,
                            const float* w_hwoi, const float* scale, void* out, void* stream);
+/* cout_pad (mode 1 only; 0 or >= cout): the co axis of the DGRAD pack is zero-padded to cout_pad so that it
+ * matches a channel-padded gradient tensor.                                                            */
 /* taps of output-parity phase (a,b): returns count; ky/kx = kernel index, dy/dx = input offset.  */
 int tbi_convt_phase_taps(int ksize, int a, int b, int* ky, int* kx, int* dy, int* dx);
 
@@ -233,7 +237,9 @@ int tbi_splitatt_combine(const tbi_splitatt* p, const tbi_view* u, const tbi_vie
  * correct: int32 counter (ADDED; caller zeroes); dlogits (may be NULL; stored as dlogits_dtype)
  * = d sum(loss_map) / d logits.                                                                  */
 int tbi_softmax_loss_fwd_bwd(int dlogits_dtype, int n, int h, int w, int nc, const float* logits, const float* y,
-                             float* probs, float* loss_map, int32_t* correct, void* dlogits, void* stream);
+                             float* probs, float* loss_map, int32_t* correct, void* dlogits, int dlogits_cstride,
+                             void* stream);
+/* dlogits_cstride >= nc: elements per pixel record of dlogits (channels >= nc are left untouched).     */
 
 /* dz = dy * act'(y_ref) [* keep]     (standalone activation backward where it cannot be fused)   */
 int tbi_act_bwd(int dtype, int64_t npix, int act, const tbi_view* dy, const tbi_view* y_ref,

@@ -143,3 +143,49 @@ def test_convt_wgrad_tc_vs_simt(ops, case):
     y = O.conv2d_transpose_s2_same(xc, wr, None)
     gw, = torch.autograd.grad((y * dz.double().cpu()).sum(), [wr])
     assert rel(res[0][0], gw) < 1e-4
+
+
+def test_head_shapes_on_tensor_cores(ops):
+    """f_tran: Conv2DTranspose 160 -> 3 (TBI_ResNest.py:124): narrow fp32-out epilogue, 16-channel padded gradient."""
+    torch.manual_seed(5)
+    n, h, w, c1, c2, nc = 2, 16, 16, 128, 32, 3
+    x1 = rnd(n, h, w, c1); x2 = rnd(n, h, w, c2)
+    wt = torch.randn(4, 4, nc, c1 + c2, device="cuda") * 0.05
+    b = torch.randn(nc, device="cuda") * 0.1
+    ys = [ops.conv2d_transpose_s2(x1, wt, b, x2=x2, impl=impl, out_f32=True) for impl in (ops._lib.IMPL_TCGEN05, ops._lib.IMPL_SIMT)]
+    assert ys[0].dtype == torch.float32 and rel(ys[0], ys[1]) < 1e-5
+    xc = torch.cat([x1, x2], 3).double().cpu()
+    want = O.conv2d_transpose_s2_same(xc, wt.to(BF).double().cpu(), b.double().cpu())
+    assert rel(ys[0], want) < 1e-5
+    dz = torch.zeros(n, 2 * h, 2 * w, 16, device="cuda", dtype=BF)
+    dz[..., :nc] = rnd(n, 2 * h, 2 * w, nc)
+    res = []
+    for impl in (ops._lib.IMPL_TCGEN05, ops._lib.IMPL_SIMT):
+        (dx1, dx2), dw, db = ops.conv2d_transpose_s2_grads(x1, wt, dz, x2=x2, impl=impl)
+        res.append((dx1, dx2, dw, db))
+    torch.cuda.synchronize()
+    assert rel(res[0][0], res[1][0]) < 1e-2 and rel(res[0][1], res[1][1]) < 1e-2
+    assert rel(res[0][2], res[1][2]) < 1e-4 and rel(res[0][3], res[1][3]) < 1e-4
+    wr = wt.double().cpu().requires_grad_(True)
+    xr = xc.clone().requires_grad_(True)
+    y = O.conv2d_transpose_s2_same(xr, wr, None)
+    gx, gw = torch.autograd.grad((y * dz[..., :nc].double().cpu()).sum(), [xr, wr])
+    assert rel(res[0][2], gw) < 1e-4 and res[0][2].shape == (4, 4, nc, c1 + c2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, BF])
+def test_stem_conv1_direct_kernels(ops, dtype):
+    """Conv1: 1 -> 16 (TBI_ResNest.py:83) runs on the direct few-channel kernels under IMPL_AUTO"""
+    torch.manual_seed(6)
+    n, h, w = 2, 40, 36
+    x = torch.randn(n, h, w, 1, device="cuda").to(dtype)
+    wt = torch.randn(3, 3, 1, 16, device="cuda") * 0.3
+    b = torch.randn(16, device="cuda") * 0.1
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    y = ops.conv2d(x, wt, b, act=ops.ACT_ELU)
+    y_s = ops.conv2d(x, wt, b, act=ops.ACT_ELU, impl=ops._lib.IMPL_SIMT)
+    assert rel(y, y_s) < tol
+    dz = torch.randn(n, h, w, 16, device="cuda").to(dtype)
+    _, dw, db = ops.conv2d_grads(x, wt, dz, need_dx=False)
+    _, dw_s, db_s = ops.conv2d_grads(x, wt, dz, need_dx=False, impl=ops._lib.IMPL_SIMT)
+    assert rel(dw, dw_s) < 1e-4 and rel(db, db_s) < 1e-4

@@ -163,7 +163,7 @@ class ResNest:
         out = torch.empty(h, w, dtype=torch.float32, device=e.device)
         correct = torch.zeros(1, dtype=torch.int32, device=e.device)
         _lib.check(e.L.tbi_softmax_loss_fwd_bwd(_lib.F32, n, h, w, c, logits.data_ptr(), y_true.data_ptr(), probs.data_ptr(),
-                                                out.data_ptr(), correct.data_ptr(), None, e.stream()), "softmax_loss")
+                                                out.data_ptr(), correct.data_ptr(), None, 0, e.stream()), "softmax_loss")
         # the kernel normalises by the model's H*W like the reference does (self.height*self.width)
         return out * (float(h * w) / float(self.height * self.width))
 

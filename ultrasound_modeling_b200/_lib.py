@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 LIB_PATH = _PKG / "libtbi_sm100.so"
 HASH_PATH = _PKG / "libtbi_sm100.so.hash"
-SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapwgrad_tc.cu", "bandwidth.cu"]
+SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapwgrad_tc.cu", "direct_small.cu", "bandwidth.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -109,9 +109,9 @@ SIGNATURES = {
     "tbi_conv2d_wgrad": (_I, [_I, _I, _I, _I, _I, _I, _I, _I, _PV, _PV, _PV, _VP, _VP, _VP, _I64, _VP]),
     "tbi_conv2d_transpose_s2_fwd": (_I, [_I, _I, _I, _I, _I, _I, _PV, _PV, _I, _VP, _PE, _VP]),
     "tbi_conv2d_transpose_s2_dgrad": (_I, [_I, _I, _I, _I, _I, _I, _PV, _I, _VP, _PE, _VP]),
-    "tbi_conv2d_transpose_s2_wgrad": (_I, [_I, _I, _I, _I, _I, _I, _PV, _PV, _PV, _VP, _VP, _VP, _I64, _VP]),
+    "tbi_conv2d_transpose_s2_wgrad": (_I, [_I, _I, _I, _I, _I, _I, _PV, _PV, _PV, _I, _VP, _VP, _VP, _I64, _VP]),
     "tbi_pack_conv_weights": (_I, [_I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP]),
-    "tbi_pack_convt_weights": (_I, [_I, _I, _I, _I, _I, _VP, _VP, _VP, _VP]),
+    "tbi_pack_convt_weights": (_I, [_I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "tbi_convt_phase_taps": (_I, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "tbi_bn_fold": (_I, [_I, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP]),
     "tbi_bn_param_grad": (_I, [_I, _I64, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP]),
@@ -121,7 +121,7 @@ SIGNATURES = {
     "tbi_split_attention_bwd": (_I, [C.POINTER(SplitAtt), _PV, _PV, _PV, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tbi_splitatt_gap": (_I, [C.POINTER(SplitAtt), _PV, _VP]),
     "tbi_splitatt_combine": (_I, [C.POINTER(SplitAtt), _PV, _PV, _VP]),
-    "tbi_softmax_loss_fwd_bwd": (_I, [_I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tbi_softmax_loss_fwd_bwd": (_I, [_I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "tbi_act_bwd": (_I, [_I, _I64, _I, _PV, _PV, _VP, _PV, _VP]),
     "tbi_accumulate": (_I, [_I, _I64, _PV, _PV, _VP]),
     "tbi_colsum": (_I, [_I, _I64, _PV, _VP, _VP]),

@@ -425,7 +425,7 @@ __global__ void splitatt_param_grad_kernel(tbi_splitatt p, const float* scratch,
 template <int NC, typename TD>
 __global__ void softmax_loss_kernel(int N, int hw, const float* __restrict__ logits, const float* __restrict__ y,
                                     float* __restrict__ probs, float* __restrict__ loss_map, int32_t* correct,
-                                    TD* __restrict__ dlogits) {
+                                    TD* __restrict__ dlogits, int dl_cs) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     int ok = 0;
     if (p < hw) {
@@ -467,7 +467,7 @@ __global__ void softmax_loss_kernel(int N, int hw, const float* __restrict__ log
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 probs[o + c] = z[c];
-                if (dlogits) stf(dlogits + o + c, z[c] * (dldp[c] - dot));
+                if (dlogits) stf(dlogits + ((size_t)n * hw + p) * dl_cs + c, z[c] * (dldp[c] - dot));
             }
         }
         loss_map[p] = -ce;
@@ -501,9 +501,9 @@ __global__ void pack_conv_kernel(int mode, int ntaps, int groups, int cin_g, int
 struct ConvtTapTable { int n[4]; int off[4]; int ky[4][4]; int kx[4][4]; };
 
 template <typename T>
-__global__ void pack_convt_kernel(int mode, int k, int cin, int cout, ConvtTapTable tt, const float* __restrict__ w,
+__global__ void pack_convt_kernel(int mode, int k, int cin, int cout, int cpad, ConvtTapTable tt, const float* __restrict__ w,
                                   const float* __restrict__ scale, T* __restrict__ out) {
-    const long long total = (long long)k * k * cin * cout;
+    const long long total = (long long)k * k * cin * (mode == 1 ? cpad : cout);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int ky, kx, ci, co;
         if (mode == 0) {            // out[phase][co][t][ci], phase blocks at tt.off[ph]*cout*cin
@@ -512,8 +512,9 @@ __global__ void pack_convt_kernel(int mode, int k, int cin, int cout, ConvtTapTa
             ci = (int)(r % cin); long long t = r / cin; const int tp = (int)(t % tt.n[ph]); co = (int)(t / tt.n[ph]);
             ky = tt.ky[ph][tp]; kx = tt.kx[ph][tp];
         } else {                    // out[ci][ky*k+kx][co]
-            co = (int)(i % cout); long long t = i / cout; const int tap = (int)(t % (k * k)); ci = (int)(t / (k * k));
+            co = (int)(i % cpad); long long t = i / cpad; const int tap = (int)(t % (k * k)); ci = (int)(t / (k * k));
             ky = tap / k; kx = tap % k;
+            if (co >= cout) { stf(out + i, 0.f); continue; }
         }
         float v = w[(((size_t)ky * k + kx) * cout + co) * cin + ci];
         if (scale) v *= scale[co];
@@ -783,17 +784,20 @@ extern "C" int tbi_split_attention_bwd(const tbi_splitatt* p, const tbi_view* u,
 }
 
 extern "C" int tbi_softmax_loss_fwd_bwd(int dlogits_dtype, int n, int h, int w, int nc, const float* logits, const float* y,
-                                        float* probs, float* loss_map, int32_t* correct, void* dlogits, void* stream) {
+                                        float* probs, float* loss_map, int32_t* correct, void* dlogits, int dlogits_cstride,
+                                        void* stream) {
+    const int dl_cs = dlogits_cstride > 0 ? dlogits_cstride : nc;
+    TBI_CHECK(dl_cs >= nc, TBI_ERR_BAD_SHAPE, "softmax_loss: dlogits_cstride %d < num_class %d", dl_cs, nc);
     TBI_CHECK(nc >= 3 && nc <= 4, TBI_ERR_UNSUPPORTED, "softmax_loss: num_class %d (my_loss_cat hard-codes 3 classes; 3..4 supported)", nc);
     cudaStream_t s = (cudaStream_t)stream;
     const int hw = h * w;
     const unsigned g = (hw + 127) / 128;
     if (dlogits_dtype == TBI_F32) {
-        if (nc == 3) softmax_loss_kernel<3, float><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits);
-        else         softmax_loss_kernel<4, float><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits);
+        if (nc == 3) softmax_loss_kernel<3, float><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
+        else         softmax_loss_kernel<4, float><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
     } else if (dlogits_dtype == TBI_BF16) {
-        if (nc == 3) softmax_loss_kernel<3, __nv_bfloat16><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits);
-        else         softmax_loss_kernel<4, __nv_bfloat16><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits);
+        if (nc == 3) softmax_loss_kernel<3, __nv_bfloat16><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
+        else         softmax_loss_kernel<4, __nv_bfloat16><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
     } else return tbi_set_error(TBI_ERR_UNSUPPORTED, "softmax_loss: dlogits dtype");
     TBI_CUDA_LAUNCH_CHECK("softmax_loss");
     return TBI_OK;
@@ -826,9 +830,10 @@ extern "C" int tbi_pack_conv_weights(int dtype, int mode, int ksize, int groups,
     return TBI_OK;
 }
 
-extern "C" int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout, const float* w_hwoi, const float* scale,
-                                      void* out, void* stream) {
+extern "C" int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout, int cout_pad, const float* w_hwoi,
+                                      const float* scale, void* out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    const int cpad = (mode == 1 && cout_pad > cout) ? cout_pad : cout;
     ConvtTapTable tt{};
     int off = 0;
     for (int ph = 0; ph < 4; ++ph) {
@@ -838,9 +843,9 @@ extern "C" int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, i
         tt.n[ph] = n; tt.off[ph] = off; off += n;
         for (int t = 0; t < n; ++t) { tt.ky[ph][t] = ky[t]; tt.kx[ph][t] = kx[t]; }
     }
-    const unsigned g = grid_for((long long)ksize * ksize * cin * cout, 256);
-    if (dtype == TBI_F32) pack_convt_kernel<float><<<g, 256, 0, s>>>(mode, ksize, cin, cout, tt, w_hwoi, scale, (float*)out);
-    else if (dtype == TBI_BF16) pack_convt_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(mode, ksize, cin, cout, tt, w_hwoi, scale, (__nv_bfloat16*)out);
+    const unsigned g = grid_for((long long)ksize * ksize * cin * cpad, 256);
+    if (dtype == TBI_F32) pack_convt_kernel<float><<<g, 256, 0, s>>>(mode, ksize, cin, cout, cpad, tt, w_hwoi, scale, (float*)out);
+    else if (dtype == TBI_BF16) pack_convt_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(mode, ksize, cin, cout, cpad, tt, w_hwoi, scale, (__nv_bfloat16*)out);
     else return tbi_set_error(TBI_ERR_UNSUPPORTED, "pack dtype");
     TBI_CUDA_LAUNCH_CHECK("pack_convt");
     return TBI_OK;

@@ -39,7 +39,9 @@ extern "C" int tbi_tapgemm_run(const tbi_tapgemm* d, void* stream) {
         if (!ok) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapgemm: tcgen05 path does not take this shape: %s", why);
         return tbi_tapgemm_tc(d, s);
     }
-    return ok ? tbi_tapgemm_tc(d, s) : tbi_tapgemm_simt(d, s);
+    if (ok) return tbi_tapgemm_tc(d, s);
+    if (tbi_tapgemm_direct_supported(d)) return tbi_tapgemm_direct(d, s);
+    return tbi_tapgemm_simt(d, s);
 }
 
 extern "C" int tbi_tapwgrad_run(const tbi_tapwgrad* d, void* stream) {
@@ -51,7 +53,9 @@ extern "C" int tbi_tapwgrad_run(const tbi_tapwgrad* d, void* stream) {
         if (!ok) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapwgrad: tcgen05 path does not take this shape: %s", why);
         return tbi_tapwgrad_tc(d, s);
     }
-    return ok ? tbi_tapwgrad_tc(d, s) : tbi_tapwgrad_simt(d, s);
+    if (ok) return tbi_tapwgrad_tc(d, s);
+    if (tbi_tapwgrad_direct_supported(d)) return tbi_tapwgrad_direct(d, s);
+    return tbi_tapwgrad_simt(d, s);
 }
 
 extern "C" int64_t tbi_workspace_bytes(const tbi_tapwgrad* d) {
@@ -184,25 +188,26 @@ extern "C" int tbi_conv2d_transpose_s2_dgrad(int dtype, int impl, int n, int h, 
 }
 
 extern "C" int tbi_conv2d_transpose_s2_wgrad(int dtype, int impl, int n, int h, int w, int ksize, const tbi_view* x0,
-                                             const tbi_view* x1, const tbi_view* dz, float* dw_hwoi, float* dbias,
+                                             const tbi_view* x1, const tbi_view* dz, int cout, float* dw_hwoi, float* dbias,
                                              void* workspace, int64_t workspace_bytes, void* stream) {
     TBI_CHECK(ksize == 3 || ksize == 4, TBI_ERR_UNSUPPORTED, "convT: ksize %d", ksize);
     TBI_CHECK(dz->h == 2 * h && dz->w == 2 * w, TBI_ERR_BAD_SHAPE, "convT wgrad: dz dims");
+    TBI_CHECK(cout >= 1 && cout <= dz->c, TBI_ERR_BAD_SHAPE, "convT wgrad: cout %d vs dz channels %d", cout, dz->c);
     const int pad = ksize == 4 ? 1 : 0;
     tbi_tapwgrad d; memset(&d, 0, sizeof(d));
     d.dtype = dtype; d.impl = impl; d.n = n; d.gh = h; d.gw = w; d.groups = 1;
     d.a_src[0] = *x0; if (x1 && x1->ptr) d.a_src[1] = *x1;
     d.b_src = *dz;
     const int cin = x0->c + ((x1 && x1->ptr) ? x1->c : 0);
-    d.cin_g = cin; d.cout_g = dz->c; d.a_stride = 1; d.b_stride = 2;
+    d.cin_g = cin; d.cout_g = cout; d.a_stride = 1; d.b_stride = 2;
     d.ntaps = 0;
     for (int ky = 0; ky < ksize; ++ky)
         for (int kx = 0; kx < ksize; ++kx) { d.b_dy[d.ntaps] = ky - pad; d.b_dx[d.ntaps] = kx - pad; ++d.ntaps; }
     d.dw = dw_hwoi;
-    d.tap_stride = (int64_t)cin * dz->c; d.ci_stride = 1; d.co_stride = cin;
+    d.tap_stride = (int64_t)cin * cout; d.ci_stride = 1; d.co_stride = cin;
     d.dbias = nullptr;                   // a tap of a stride-2 gather does not visit every dz pixel: use colsum
     d.workspace = workspace; d.workspace_bytes = workspace_bytes;
     int rc = tbi_tapwgrad_run(&d, stream); if (rc) return rc;
-    if (dbias) return tbi_colsum(dtype, (int64_t)n * dz->h * dz->w, dz, dbias, stream);
+    if (dbias) { tbi_view real = *dz; real.c = cout; return tbi_colsum(dtype, (int64_t)n * dz->h * dz->w, &real, dbias, stream); }
     return TBI_OK;
 }

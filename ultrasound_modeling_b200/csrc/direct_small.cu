@@ -1,0 +1,171 @@
+// Direct (CUDA-core) kernels for convolutions whose input has a handful of channels (the 1 -> 16 stem
+// conv, TBI_ResNest.py:83).  K = taps*cin <= 36 is far below one UMMA K-step worth of useful work and the
+// layer is purely HBM-bound (writes 32 B per pixel), so: one thread per pixel, weights in shared memory,
+// 16-byte stores; the weight gradient is a per-thread register reduction + warp shuffles + one atomic
+// per (block, element).
+#include "tbi_common.cuh"
+
+namespace {
+
+constexpr int MAXK = 36;
+
+template <typename T, int V> struct alignas(sizeof(T) * V) PackD { T v[V]; };
+
+template <typename T, int COUT>
+__global__ void __launch_bounds__(256) smallcin_fwd_kernel(const __grid_constant__ tbi_tapgemm d) {
+    __shared__ float ws[COUT * MAXK];
+    __shared__ float bs[COUT];
+    const int cin = d.cin_g, Kg = d.ntaps * cin;
+    for (int i = threadIdx.x; i < COUT * Kg; i += blockDim.x) ws[i] = ldf((const T*)d.w + i);
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = d.epi.bias ? d.epi.bias[i] : 0.f;
+    __syncthreads();
+    const tbi_epilogue& e = d.epi;
+    const bool fast = e.drop_keep == nullptr && e.residual.ptr == nullptr && e.dact == TBI_ACT_NONE && e.split_c == 0 && !e.out_f32 &&
+                      e.out.cstride == COUT && e.out.coff == 0 && e.out_stride == 1 && (((uintptr_t)e.out.ptr) & 15) == 0;
+    const long long M = (long long)d.n * d.gh * d.gw;
+    const T* src = (const T*)d.src[0].ptr;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < M; p += (long long)gridDim.x * blockDim.x) {
+        const int gx = (int)(p % d.gw); long long t = p / d.gw; const int gy = (int)(t % d.gh); const int n = (int)(t / d.gh);
+        float acc[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+        for (int tap = 0; tap < d.ntaps; ++tap) {
+            const int iy = gy + d.dy[tap], ix = gx + d.dx[tap];
+            if (iy < 0 || iy >= d.src[0].h || ix < 0 || ix >= d.src[0].w) continue;
+            const T* px = src + view_off(d.src[0], n, iy, ix, 0);
+            for (int ci = 0; ci < cin; ++ci) {
+                const float a = ldf(px + ci);
+                const float* wk = ws + tap * cin + ci;
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(a, wk[c * Kg], acc[c]);
+            }
+        }
+        if (fast) {
+            constexpr int V = 16 / sizeof(T);
+            T* o = (T*)e.out.ptr + (size_t)p * COUT;
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += V) {
+                PackD<T, V> q;
+#pragma unroll
+                for (int j = 0; j < V; ++j) stf(&q.v[j], act_apply(e.act, acc[c0 + j] + bs[c0 + j]));
+                *reinterpret_cast<PackD<T, V>*>(o + c0) = q;
+            }
+        } else {
+            const int oy = gy * e.out_stride + e.out_off_y, ox = gx * e.out_stride + e.out_off_x;
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) epilogue_store<T>(e, n, oy, ox, c, acc[c]);
+        }
+    }
+}
+
+// blockIdx.y = tap; each thread accumulates acc[cin][COUT] over its pixels
+template <typename T, int COUT, int CIN>
+__global__ void __launch_bounds__(256) smallcin_wgrad_kernel(const __grid_constant__ tbi_tapwgrad d) {
+    __shared__ float red[8][CIN * COUT + COUT];
+    const int tap = blockIdx.y;
+    const bool do_bias = d.dbias != nullptr && tap == 0;
+    float acc[CIN][COUT];
+    float bacc[COUT];
+#pragma unroll
+    for (int i = 0; i < CIN; ++i)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[i][c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bacc[c] = 0.f;
+    const long long M = (long long)d.n * d.gh * d.gw;
+    const T* a = (const T*)d.a_src[0].ptr;
+    const T* b = (const T*)d.b_src.ptr;
+    constexpr int V = 16 / sizeof(T);
+    const bool vec = d.b_src.cstride % V == 0 && d.b_src.coff % V == 0 && (((uintptr_t)d.b_src.ptr) & 15) == 0;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < M; p += (long long)gridDim.x * blockDim.x) {
+        const int gx = (int)(p % d.gw); long long t = p / d.gw; const int gy = (int)(t % d.gh); const int n = (int)(t / d.gh);
+        const int ay = gy + d.a_dy[tap], ax = gx + d.a_dx[tap];
+        const bool a_ok = ay >= 0 && ay < d.a_src[0].h && ax >= 0 && ax < d.a_src[0].w;
+        if (!a_ok && !do_bias) continue;
+        float g[COUT];
+        const T* bp = b + view_off(d.b_src, n, gy, gx, 0);
+        if (vec) {
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += V) {
+                const PackD<T, V> q = *reinterpret_cast<const PackD<T, V>*>(bp + c0);
+#pragma unroll
+                for (int j = 0; j < V; ++j) g[c0 + j] = ldf(&q.v[j]);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) g[c] = ldf(bp + c);
+        }
+        if (do_bias) {
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) bacc[c] += g[c];
+        }
+        if (a_ok) {
+            const T* ap = a + view_off(d.a_src[0], n, ay, ax, 0);
+#pragma unroll
+            for (int i = 0; i < CIN; ++i) {
+                const float x = ldf(ap + i);
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) acc[i][c] = fmaf(x, g[c], acc[i][c]);
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < CIN; ++i)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { const float v = warp_sum(acc[i][c]); if (lane == 0) red[warp][i * COUT + c] = v; }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { const float v = warp_sum(bacc[c]); if (lane == 0) red[warp][CIN * COUT + c] = v; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CIN * COUT + COUT; i += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][i];
+        if (i < CIN * COUT) {
+            const int ci = i / COUT, co = i % COUT;
+            atomicAdd(d.dw + (size_t)tap * d.tap_stride + (size_t)ci * d.ci_stride + (size_t)co * d.co_stride, v);
+        } else if (do_bias) {
+            atomicAdd(d.dbias + (i - CIN * COUT), v);
+        }
+    }
+}
+
+}  // namespace
+
+bool tbi_tapgemm_direct_supported(const tbi_tapgemm* d) {
+    return d->groups == 1 && d->src[1].ptr == nullptr && d->in_stride == 1 && d->nphase <= 1 && d->cout_g == 16 &&
+           d->ntaps * d->cin_g <= MAXK && d->src[0].c == d->cin_g && (d->dtype == TBI_F32 || d->dtype == TBI_BF16);
+}
+
+int tbi_tapgemm_direct(const tbi_tapgemm* d, cudaStream_t s) {
+    TBI_CHECK(tbi_tapgemm_direct_supported(d), TBI_ERR_UNSUPPORTED, "direct small-cin conv: unsupported shape");
+    const long long M = (long long)d->n * d->gh * d->gw;
+    long long blocks = (M + 255) / 256;
+    const long long cap = (long long)tbi_sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    if (d->dtype == TBI_F32) smallcin_fwd_kernel<float, 16><<<(unsigned)blocks, 256, 0, s>>>(*d);
+    else smallcin_fwd_kernel<__nv_bfloat16, 16><<<(unsigned)blocks, 256, 0, s>>>(*d);
+    TBI_CUDA_LAUNCH_CHECK("smallcin_fwd");
+    return TBI_OK;
+}
+
+bool tbi_tapwgrad_direct_supported(const tbi_tapwgrad* d) {
+    if (!(d->groups == 1 && d->a_src[1].ptr == nullptr && d->a_stride == 1 && d->b_stride == 1 && d->cout_g == 16 && d->cin_g == 1 &&
+          d->a_src[0].c == 1 && d->b_src.c == 16 && d->ntaps <= 9 && (d->dtype == TBI_F32 || d->dtype == TBI_BF16))) return false;
+    for (int t = 0; t < d->ntaps; ++t) if (d->b_dy[t] != 0 || d->b_dx[t] != 0) return false;
+    return true;
+}
+
+int tbi_tapwgrad_direct(const tbi_tapwgrad* d, cudaStream_t s) {
+    TBI_CHECK(tbi_tapwgrad_direct_supported(d), TBI_ERR_UNSUPPORTED, "direct small-cin wgrad: unsupported shape");
+    const long long M = (long long)d->n * d->gh * d->gw;
+    long long blocks = (M + 256 * 8 - 1) / (256 * 8);
+    const long long cap = (long long)tbi_sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, (unsigned)d->ntaps);
+    if (d->dtype == TBI_F32) smallcin_wgrad_kernel<float, 16, 1><<<grid, 256, 0, s>>>(*d);
+    else smallcin_wgrad_kernel<__nv_bfloat16, 16, 1><<<grid, 256, 0, s>>>(*d);
+    TBI_CUDA_LAUNCH_CHECK("smallcin_wgrad");
+    return TBI_OK;
+}

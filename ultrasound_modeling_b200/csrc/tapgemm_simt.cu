@@ -254,7 +254,7 @@ int tbi_tapwgrad_simt(const tbi_tapwgrad* d, cudaStream_t s) {
     const int ctot = d->a_src[0].c + (d->a_src[1].ptr ? d->a_src[1].c : 0);
     TBI_CHECK(ctot == d->cin_g * d->groups, TBI_ERR_BAD_SHAPE, "tapwgrad: source channels %d != groups*cin_g %d",
               ctot, d->cin_g * d->groups);
-    TBI_CHECK(d->b_src.c == d->cout_g * d->groups, TBI_ERR_BAD_SHAPE, "tapwgrad: dz channels %d != groups*cout_g %d",
+    TBI_CHECK(d->b_src.c == d->cout_g * d->groups || (d->groups == 1 && d->b_src.c > d->cout_g), TBI_ERR_BAD_SHAPE, "tapwgrad: dz channels %d != groups*cout_g %d",
               d->b_src.c, d->cout_g * d->groups);
     const long long M = (long long)d->n * d->gh * d->gw;
     TBI_CHECK(M > 0, TBI_ERR_BAD_SHAPE, "tapwgrad: empty problem");

@@ -34,6 +34,7 @@ struct alignas(64) TcGemmParams {
     int kc, stages;
     int nphase, ntaps;
     int out_stride;
+    int narrow;                   // cout_g < 8 (e.g. the 3-class head): scalar epilogue, fp32 output allowed
     int a_cbase[2], a_cpix[2];
     int ph_off_y[4], ph_off_x[4];
     signed char qy[4][16], qx[4][16], ay[4][16], ax[4][16];
@@ -222,7 +223,10 @@ __global__ void __launch_bounds__(NUM_THREADS) tapgemm_tc_kernel(const __grid_co
             uint32_t r[16];
             tc::tmem_ld16(taddr, r);
             tc::tmem_ld_wait();
-            if (valid) {
+            if (valid && p.narrow) {
+                for (int j = 0; j < 16; ++j)
+                    if (nc0 + j < p.cout_g) epilogue_store<__nv_bfloat16>(p.epi, n, oy, ox, g * p.cout_g + nc0 + j, __uint_as_float(r[j]));
+            } else if (valid) {
 #pragma unroll
                 for (int j = 0; j < 16; j += 8) {
                     const int col = nc0 + j;
@@ -316,15 +320,18 @@ bool tbi_tapgemm_tc_supported(const tbi_tapgemm* d, const char** why) {
     if (d->in_stride != 1 && d->in_stride != 2) NO("in_stride");
     if (d->groups > 1 && d->src[1].ptr) NO("groups with two sources");
     if (pick_kc(d) == 0) NO("input channels per source are not a multiple of 16");
-    if (d->cout_g % 8 != 0) NO("output channels per group are not a multiple of 8");
+    const bool narrow = d->cout_g < 8 && d->groups == 1;
+    if (d->cout_g % 8 != 0 && !narrow) NO("output channels per group are not a multiple of 8");
     if (!aligned_view(d->src[0]) || !aligned_view(d->src[1])) NO("source view not 16-byte aligned");
     if (d->in_stride == 2 && ((d->src[0].h | d->src[0].w) & 1)) NO("stride-2 gather needs even source dims");
     const tbi_epilogue& e = d->epi;
-    if (e.out_f32) NO("fp32 output");
-    if (!aligned_view(e.out) || !aligned_view(e.residual) || !aligned_view(e.dact_ref) || !aligned_view(e.out2) || !aligned_view(e.residual2))
-        NO("epilogue view not 16-byte aligned");
-    if (e.split_c % 8 != 0) NO("split_c");
-    if (e.bias && ((uintptr_t)e.bias & 15)) NO("bias alignment");
+    if (e.out_f32 && !narrow) NO("fp32 output");
+    if (!narrow) {
+        if (!aligned_view(e.out) || !aligned_view(e.residual) || !aligned_view(e.dact_ref) || !aligned_view(e.out2) || !aligned_view(e.residual2))
+            NO("epilogue view not 16-byte aligned");
+        if (e.split_c % 8 != 0) NO("split_c");
+    }
+    if (e.bias && ((uintptr_t)e.bias & 15) && !narrow) NO("bias alignment");
     if (((uintptr_t)d->w & 15)) NO("weight alignment");
     if ((e.drop_keep && (((uintptr_t)e.drop_keep & 7) || e.out.c != e.out.cstride)) ||
         (e.dact_keep && (((uintptr_t)e.dact_keep & 7) || e.dact_ref.c != e.dact_ref.cstride))) NO("dropout mask layout");
@@ -357,6 +364,7 @@ int tbi_tapgemm_tc(const tbi_tapgemm* d, cudaStream_t s) {
     p.cin_g = d->cin_g; p.cout_g = d->cout_g; p.groups = d->groups; p.cout_total = d->cout_g * d->groups;
     p.c0 = d->groups > 1 ? d->cin_g * d->groups : d->src[0].c;
     p.kc = kc; p.nphase = d->nphase > 1 ? d->nphase : 1; p.ntaps = d->ntaps;
+    p.narrow = (d->cout_g < 8 && d->groups == 1) ? 1 : 0;
     p.epi = d->epi;
     p.out_stride = d->nphase > 1 ? 2 : (d->epi.out_stride ? d->epi.out_stride : 1);
     for (int ph = 0; ph < p.nphase; ++ph) {

@@ -209,8 +209,10 @@ bool tbi_tapwgrad_tc_supported(const tbi_tapwgrad* d, const char** why) {
     if (d->b_stride != 1 && d->b_stride != 2) NO("b_stride");
     if (d->groups > 1 && d->a_src[1].ptr) NO("groups with two sources");
     if (d->a_src[1].ptr && d->a_src[0].c % 64 != 0) NO("first source of a concat must be a multiple of 64 channels");
-    if (d->cin_g % 8 != 0 || d->cout_g % 8 != 0) NO("channels per group must be multiples of 8");
-    if (d->cin_g < 16 || d->cout_g < 16) NO("too few channels for the tensor-core path");
+    if (d->cin_g % 8 != 0) NO("input channels per group must be a multiple of 8");
+    if (d->groups > 1 && d->cout_g % 8 != 0) NO("grouped: output channels per group must be a multiple of 8");
+    if (d->cin_g < 16) NO("too few input channels for the tensor-core path");
+    if (d->b_src.c < d->cout_g * d->groups) NO("gradient view has fewer channels than cout");
     if (!wg_aligned_view(d->a_src[0]) || !wg_aligned_view(d->a_src[1]) || !wg_aligned_view(d->b_src)) NO("view not 16-byte aligned");
     if (d->b_stride == 2 && ((d->b_src.h | d->b_src.w) & 1)) NO("stride-2 gather needs even dims");
     for (int t = 0; t < d->ntaps; ++t)

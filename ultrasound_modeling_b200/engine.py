@@ -328,7 +328,10 @@ class Engine:
             self.keep.append(torch.ones(n, h, w, u["out"], dtype=torch.uint8, device=dev) if u["drop"] else None)
         self.logits = torch.empty(n, H, W, self.num_class, dtype=torch.float32, device=dev)
         self.probs = torch.empty(n, H, W, self.num_class, dtype=torch.float32, device=dev)
-        self.dlogits = E(n, H, W, self.num_class)
+        # bf16: the head gradient is stored with 16 channels per pixel (3 real + zeros) so that its pixel records are
+        # 16-byte aligned for TMA; the loss kernel writes the real channels only, the padding stays zero
+        self.dl_c = 16 if self.dt == BF16 else self.num_class
+        self.dlogits = torch.zeros(n, H, W, self.dl_c, dtype=td, device=dev)
         self.loss_map = torch.empty(H, W, dtype=torch.float32, device=dev)
         self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
         # packed compute weights + folded BN
@@ -336,7 +339,8 @@ class Engine:
         self.packed = {}
         for L in self.convs.values():
             nel = L.k * L.k * L.cin_g * L.cout
-            self.packed[L.name] = dict(wf=torch.empty(nel, dtype=td, device=dev), wb=torch.empty(nel, dtype=td, device=dev),
+            nel_b = L.k * L.k * L.cin * self.dl_c if L is self.head else nel
+            self.packed[L.name] = dict(wf=torch.empty(nel, dtype=td, device=dev), wb=torch.empty(nel_b, dtype=td, device=dev),
                                        scale=torch.empty(L.cout, dtype=torch.float32, device=dev),
                                        fbias=torch.empty(L.cout, dtype=torch.float32, device=dev))
         self._assemble()
@@ -396,8 +400,9 @@ class Engine:
                 self.prog_prepare.append((L.tbi_pack_conv_weights, (dt, 0, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, sc, _ptr(pk["wf"]))))
                 self.prog_prepare.append((L.tbi_pack_conv_weights, (dt, 1, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, sc, _ptr(pk["wb"]))))
             else:
-                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 0, Lr.k, Lr.cin, Lr.cout, wp, sc, _ptr(pk["wf"]))))
-                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 1, Lr.k, Lr.cin, Lr.cout, wp, sc, _ptr(pk["wb"]))))
+                cpad = self.dl_c if Lr is self.head else 0
+                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 0, Lr.k, Lr.cin, Lr.cout, 0, wp, sc, _ptr(pk["wf"]))))
+                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 1, Lr.k, Lr.cin, Lr.cout, cpad, wp, sc, _ptr(pk["wb"]))))
 
         for Lr in self.convs.values():
             prepare(Lr)
@@ -421,7 +426,7 @@ class Engine:
                 wargs = [dt, impl, n, h, w, Lr.k, 1, Lr.groups, bref(x0), bref(x1) if x1 is not None else None, bref(dz), dw, db, None, 0]
                 self.prog_bwd.append((L.tbi_conv2d_wgrad, wargs))
             else:
-                wargs = [dt, impl, n, h, w, Lr.k, bref(x0), bref(x1) if x1 is not None else None, bref(dz), dw, db, None, 0]
+                wargs = [dt, impl, n, h, w, Lr.k, bref(x0), bref(x1) if x1 is not None else None, bref(dz), Lr.cout, dw, db, None, 0]
                 self.prog_bwd.append((L.tbi_conv2d_transpose_s2_wgrad, wargs))
             wgrads.append((Lr, wargs, n, h, w, x0, x1, dz))
             if Lr.bn:
@@ -477,7 +482,7 @@ class Engine:
         conv_fwd(self.head, H // 2, W // 2, view(self.up[4]), view(self.pool[0]), epi(out=view(self.logits), out_f32=1))
         # ---------------- loss ----------------
         self.prog_loss.append((L.tbi_softmax_loss_fwd_bwd, (dt, n, H, W, self.num_class, _ptr(self.logits), _ptr(self.y_in), _ptr(self.probs),
-                                                            _ptr(self.loss_map), _ptr(self.correct), _ptr(self.dlogits))))
+                                                            _ptr(self.loss_map), _ptr(self.correct), _ptr(self.dlogits), self.dl_c)))
         # ---------------- backward ----------------
         # head: d(up4) gets ReLU' of up4 (no dropout on upsample_4); d(pool[0]) plain write
         conv_bwd(self.head, H // 2, W // 2, view(self.up[4]), view(self.pool[0]), view(self.dlogits),

@@ -71,12 +71,13 @@ def pack_conv(w_hwio: torch.Tensor, groups: int, mode: int, dtype: torch.dtype, 
     return out
 
 
-def pack_convt(w_hwoi: torch.Tensor, mode: int, dtype: torch.dtype, scale=None) -> torch.Tensor:
+def pack_convt(w_hwoi: torch.Tensor, mode: int, dtype: torch.dtype, scale=None, cout_pad: int = 0) -> torch.Tensor:
     L = _lib.lib()
     k, _, cout, cin = w_hwoi.shape
     w32 = _f32(w_hwoi)
-    out = torch.empty(w32.numel(), dtype=dtype, device=w32.device)
-    check(L.tbi_pack_convt_weights(F32 if dtype == torch.float32 else BF16, mode, k, cin, cout, _p(w32), _p(scale), _p(out), _st()), "pack_convt")
+    cp = cout_pad if (mode == 1 and cout_pad > cout) else cout
+    out = torch.empty(k * k * cin * cp, dtype=dtype, device=w32.device)
+    check(L.tbi_pack_convt_weights(F32 if dtype == torch.float32 else BF16, mode, k, cin, cout, cout_pad, _p(w32), _p(scale), _p(out), _st()), "pack_convt")
     return out
 
 
@@ -154,16 +155,18 @@ def conv2d_transpose_s2(x, w_hwoi, bias=None, *, bn=None, act=ACT_NONE, keep=Non
 
 
 def conv2d_transpose_s2_grads(x, w_hwoi, dz, *, scale=None, x2=None, impl=IMPL_AUTO, need_dx=True, wgrad_impl=None):
+    """dz may carry more channels than the kernel's cout (zero-padded gradient records, e.g. the head)."""
     L = _lib.lib()
     n, h, w, c0 = x.shape
     k, _, cout, cin = w_hwoi.shape
+    cpad = dz.shape[3]
     dw = torch.zeros(w_hwoi.shape, dtype=torch.float32, device=x.device)
     db = torch.zeros(cout, dtype=torch.float32, device=x.device)
     check(L.tbi_conv2d_transpose_s2_wgrad(_dt(x), impl if wgrad_impl is None else wgrad_impl, n, h, w, k, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
-                                          _vp(view(dz)), _p(dw), _p(db), None, 0, _st()), "convT_wgrad")
+                                          _vp(view(dz)), cout, _p(dw), _p(db), None, 0, _st()), "convT_wgrad")
     if not need_dx:
         return None, dw, db
-    wb = pack_convt(w_hwoi, 1, x.dtype, scale)
+    wb = pack_convt(w_hwoi, 1, x.dtype, scale, cout_pad=cpad)
     dx = torch.empty_like(x)
     dx2 = torch.empty_like(x2) if x2 is not None else None
     e = _epi(dx, out2=dx2, split_c=c0 if x2 is not None else 0)
@@ -274,7 +277,7 @@ def softmax_loss(logits, y, dlogits_dtype=torch.float32):
     correct = torch.zeros(1, dtype=torch.int32, device=dev)
     dlog = torch.empty(n, h, w, nc, dtype=dlogits_dtype, device=dev)
     check(L.tbi_softmax_loss_fwd_bwd(F32 if dlogits_dtype == torch.float32 else BF16, n, h, w, nc, _p(logits), _p(y), _p(probs),
-                                     _p(loss), _p(correct), _p(dlog), _st()), "softmax_loss")
+                                     _p(loss), _p(correct), _p(dlog), nc, _st()), "softmax_loss")
     return probs, loss, correct, dlog
 
 
