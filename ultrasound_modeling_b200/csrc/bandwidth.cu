@@ -675,7 +675,8 @@ extern "C" int tbi_accumulate(int dtype, int64_t npix, const tbi_view* src, cons
 
 extern "C" int tbi_colsum(int dtype, int64_t npix, const tbi_view* x, float* out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    long long blocks = (npix + 511) / 512;
+    // enough blocks to fill the machine even for the small deep-stage tensors (>= 16 pixels per block)
+    long long blocks = (npix + 15) / 16;
     const long long cap = (long long)tbi_sm_count() * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
