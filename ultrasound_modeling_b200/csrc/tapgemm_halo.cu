@@ -1,0 +1,388 @@
+// Persistent, halo-addressed tcgen05 tap-GEMM (bf16 in, fp32 accumulate in TMEM) for sm_100a.
+//
+// Same contract as tapgemm_tc.cu, different schedule, for spatial sizes >= 16 x 8:
+//   * the 128 output pixels of a tile are a 16 x 8 patch of ONE image;
+//   * per 64-channel K chunk the producer issues ONE TMA box covering the patch plus its halo
+//     ((16+ey) x (8+ex) pixels); every tap's A operand is a UMMA descriptor into that box, starting at
+//     row (dy-oy)*(8+ex) + (dx-ox) with stride-byte-offset (8+ex)*row_bytes.  This works because the
+//     hardware swizzle follows absolute shared-memory address bits (profiles/r1_umma_descriptor_probe.md).
+//     A 3x3 conv thus reads its input once from L2 instead of 9 times; the 4 parity phases of a k4 s2
+//     transposed conv share one 3x3 halo; the 16 taps of its dgrad use 4 halos (one per input parity).
+//   * CTAs are persistent (grid = resident CTAs, static round-robin over tiles, N-tile fastest so
+//     neighbouring CTAs hit the same halo in L2); two TMEM accumulator buffers let the epilogue of tile
+//     i run under the TMA/MMA main loop of tile i+1; separate A (halo) and B (weights) smem rings.
+// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include "tbi_common.cuh"
+#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
+#include <mutex>
+#include <string.h>
+#include <stdlib.h>
+
+namespace {
+
+constexpr int HT_THREADS = 192;
+constexpr int TW = 8, TH = 16;                 // tile = 16 rows x 8 columns of pixels = 128 GEMM rows
+
+struct alignas(64) HaloParams {
+    CUtensorMap a[2];
+    CUtensorMap b;
+    int n, gh, gw;
+    int tiles_x, tiles_y, m_tiles, n_tiles, cgroups, nphase, total_tiles;
+    int cin_g, cout_g, c0, cout_total;
+    int kc, nchunks;
+    int a_stages, b_stages, a_stage_bytes, b_stage_bytes, a_tx, b_tx;
+    int pitch, row_bytes;
+    int ngroups, ntaps;
+    int g_ox[4], g_oy[4], g_ax[4], g_ay[4];
+    unsigned short t_row[4][16];
+    unsigned char t_grp[4][16], t_kidx[4][16];
+    int a_cbase[2], a_cpix[2];
+    int out_stride, ph_off_y[4], ph_off_x[4];
+    int narrow;
+    tbi_epilogue epi;
+};
+
+__device__ __forceinline__ void ht_wait(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    while (!tc::mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) { printf("tbi tcgen05 halo: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+
+struct TileCoord { int x0, y0, n0, nc0, cg, ph; };
+
+__device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile, int BN) {
+    TileCoord t;
+    const int nt = tile % p.n_tiles; tile /= p.n_tiles;
+    t.ph = tile % p.nphase; tile /= p.nphase;
+    t.cg = tile % p.cgroups; tile /= p.cgroups;
+    const int tix = tile % p.tiles_x; tile /= p.tiles_x;
+    const int tiy = tile % p.tiles_y; t.n0 = tile / p.tiles_y;
+    t.x0 = tix * TW; t.y0 = tiy * TH; t.nc0 = nt * BN;
+    return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_constant__ HaloParams p) {
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;            // columns per accumulator buffer
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* a_ring = smem;
+    uint8_t* b_ring = smem + (size_t)p.a_stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_stages * p.b_stage_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + p.a_stages;
+    uint64_t* b_full = a_empty + p.a_stages;
+    uint64_t* b_empty = b_full + p.b_stages;
+    uint64_t* t_full = b_empty + p.b_stages;               // [2]
+    uint64_t* t_empty = t_full + 2;                        // [2]
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&p.a[0]); tc::prefetch_tmap(&p.b);
+        if (p.c0 < p.cin_g * p.cgroups) tc::prefetch_tmap(&p.a[1]);
+        for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tslot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tslot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            uint32_t a_it = 0, b_it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile, BN);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    const int ch = c * p.kc;
+                    int src = 0, cch = ch + (p.cgroups > 1 ? t.cg * p.cin_g : 0);
+                    if (p.cgroups == 1 && cch >= p.c0) { src = 1; cch -= p.c0; }
+                    int tap = 0;
+                    for (int grp = 0; grp < p.ngroups; ++grp) {
+                        const uint32_t sa = a_it % p.a_stages;
+                        ht_wait(&a_empty[sa], ((a_it / p.a_stages) & 1u) ^ 1u);
+                        tc::mbar_expect_tx(&a_full[sa], p.a_tx);
+                        tc::tma_load_5d(a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], &a_full[sa],
+                                        p.a_cbase[src] + cch + p.g_ax[grp] * p.a_cpix[src], t.x0 + p.g_ox[grp], p.g_ay[grp], t.y0 + p.g_oy[grp], t.n0);
+                        ++a_it;
+                        while (tap < p.ntaps && p.t_grp[t.ph][tap] == grp) {
+                            const uint32_t sb = b_it % p.b_stages;
+                            ht_wait(&b_empty[sb], ((b_it / p.b_stages) & 1u) ^ 1u);
+                            tc::mbar_expect_tx(&b_full[sb], p.b_tx);
+                            tc::tma_load_2d(b_ring + (size_t)sb * p.b_stage_bytes, &p.b, &b_full[sb], (int)p.t_kidx[t.ph][tap] * p.cin_g + ch,
+                                            t.ph * p.cout_total + t.cg * p.cout_g + t.nc0);
+                            ++b_it; ++tap;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer =====================
+            const uint32_t idesc = tc::make_idesc_bf16(128, BN, 0, 0);
+            const uint32_t layout = p.kc == 64 ? 2u : p.kc == 32 ? 4u : 6u;
+            const uint32_t sbo_a = (uint32_t)p.pitch * p.row_bytes;       // 8-row group == one tile row of the halo
+            const uint32_t sbo_b = 8u * p.row_bytes;
+            const int ksteps = p.kc / 16;
+            uint32_t a_it = 0, b_it = 0, acc_it = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++acc_it) {
+                const TileCoord t = decode_tile(p, tile, BN);
+                const uint32_t buf = acc_it & 1u;
+                ht_wait(&t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator
+                tc::tc_fence_after();
+                const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+                uint32_t first = 1;
+                for (int c = 0; c < p.nchunks; ++c) {
+                    int tap = 0;
+                    for (int grp = 0; grp < p.ngroups; ++grp) {
+                        const uint32_t sa = a_it % p.a_stages;
+                        ht_wait(&a_full[sa], (a_it / p.a_stages) & 1u);
+                        const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
+                        while (tap < p.ntaps && p.t_grp[t.ph][tap] == grp) {
+                            const uint32_t sb = b_it % p.b_stages;
+                            ht_wait(&b_full[sb], (b_it / p.b_stages) & 1u);
+                            tc::tc_fence_after();
+                            const uint32_t a_tap = a_addr + (uint32_t)p.t_row[t.ph][tap] * p.row_bytes;
+                            const uint32_t b_addr = tc::smem_u32(b_ring + (size_t)sb * p.b_stage_bytes);
+                            for (int k = 0; k < ksteps; ++k) {
+                                const uint64_t da = tc::make_smem_desc(a_tap + k * 32, 16, sbo_a, layout);
+                                const uint64_t db = tc::make_smem_desc(b_addr + k * 32, 16, sbo_b, layout);
+                                tc::umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
+                                first = 0;
+                            }
+                            tc::umma_commit(&b_empty[sb]);
+                            ++b_it; ++tap;
+                        }
+                        tc::umma_commit(&a_empty[sa]);
+                        ++a_it;
+                    }
+                }
+                tc::umma_commit(&t_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warp w owns TMEM lanes [32*(w%4), +32)) =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int xx = m & (TW - 1), yy = m >> 3;
+        uint32_t acc_it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++acc_it) {
+            const TileCoord t = decode_tile(p, tile, BN);
+            const uint32_t buf = acc_it & 1u;
+            const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
+            const bool valid = gx < p.gw && gy < p.gh;
+            const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
+            const int ox = gx * p.out_stride + (p.nphase > 1 ? p.ph_off_x[t.ph] : p.epi.out_off_x);
+            ht_wait(&t_full[buf], (acc_it >> 1) & 1u);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            if constexpr (BN >= 32) {
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + c, r);
+                    tc::tmem_ld_wait();
+                    if (c + 32 >= BN) {                                   // last read of this buffer: hand it back to the MMA warp
+                        tc::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) tc::mbar_arrive(&t_empty[buf]);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const int col = t.nc0 + c + j;
+                            if (col < p.cout_g) {
+                                float v[8];
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+                                epilogue_store8(p.epi, n, oy, ox, t.cg * p.cout_g + col, v);
+                            }
+                        }
+                    }
+                }
+            } else {
+                uint32_t r[16];
+                tc::tmem_ld16(taddr, r);
+                tc::tmem_ld_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&t_empty[buf]);
+                if (valid && p.narrow) {
+                    for (int j = 0; j < 16; ++j)
+                        if (t.nc0 + j < p.cout_g) epilogue_store<__nv_bfloat16>(p.epi, n, oy, ox, t.cg * p.cout_g + t.nc0 + j, __uint_as_float(r[j]));
+                } else if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                        const int col = t.nc0 + j;
+                        if (col < p.cout_g) {
+                            float v[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+                            epilogue_store8(p.epi, n, oy, ox, t.cg * p.cout_g + col, v);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+inline uint32_t r1024(uint32_t x) { return (x + 1023u) & ~1023u; }
+
+// 5-D activation map with a halo box [kc x (TW+ex) x 1 x (TH+ey) x 1]
+int halo_act_tmap(CUtensorMap* out, const tbi_view& v, int n, int stride, int kc, int bw, int bh, int* cbase, int* cpix) {
+    uint64_t dims[5], strides[4];
+    uint32_t box[5] = {(uint32_t)kc, (uint32_t)bw, 1u, (uint32_t)bh, 1u};
+    const uint64_t px = (uint64_t)v.cstride * 2;
+    void* base;
+    if (stride == 1) {
+        dims[0] = (uint64_t)v.c; dims[1] = (uint64_t)v.w; dims[2] = 1; dims[3] = (uint64_t)v.h; dims[4] = (uint64_t)n;
+        strides[0] = px; strides[1] = px * v.w; strides[2] = px * v.w; strides[3] = px * v.w * v.h;
+        base = (char*)v.ptr + (size_t)v.coff * 2;
+        *cbase = 0; *cpix = 0;
+    } else {
+        dims[0] = (uint64_t)v.cstride * 2; dims[1] = (uint64_t)v.w / 2; dims[2] = 2; dims[3] = (uint64_t)v.h / 2; dims[4] = (uint64_t)n;
+        strides[0] = px * 2; strides[1] = px * v.w; strides[2] = px * v.w * 2; strides[3] = px * v.w * v.h;
+        base = v.ptr;
+        *cbase = v.coff; *cpix = v.cstride;
+    }
+    return tbi_make_tmap_bf16(out, base, 5, dims, strides, box, kc * 2);
+}
+
+template <int BN>
+int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t s) {
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tapgemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    if (attr_err != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
+    tapgemm_halo_kernel<BN><<<grid, HT_THREADS, smem, s>>>(p);
+    TBI_CUDA_LAUNCH_CHECK("tapgemm_halo");
+    return TBI_OK;
+}
+
+int halo_pick_kc(const tbi_tapgemm* d) {
+    const int c0 = d->groups > 1 ? d->cin_g : d->src[0].c;
+    const int c1 = (d->groups == 1 && d->src[1].ptr) ? d->src[1].c : 0;
+    for (int kc = 64; kc >= 16; kc >>= 1)
+        if (c0 % kc == 0 && c1 % kc == 0) return kc;
+    return 0;
+}
+
+struct TapPlan { int ngroups, ex, ey; int ox[4], oy[4], ax[4], ay[4]; int grp[4][16], row_dy[4][16], row_dx[4][16], kidx[4][16]; };
+
+// group taps by input parity (stride 2) or into one group (stride 1); returns false if the halo would be too large
+bool plan_taps(const tbi_tapgemm* d, TapPlan* tp) {
+    const int nph = d->nphase > 1 ? d->nphase : 1;
+    memset(tp, 0, sizeof(*tp));
+    int lo_x[4], hi_x[4], lo_y[4], hi_y[4]; bool used[4] = {false, false, false, false};
+    int qy[4][16], qx[4][16], g[4][16];
+    for (int ph = 0; ph < nph; ++ph)
+        for (int t = 0; t < d->ntaps; ++t) {
+            const int dy = d->nphase > 1 ? d->ph_dy[ph][t] : d->dy[t], dx = d->nphase > 1 ? d->ph_dx[ph][t] : d->dx[t];
+            int grp = 0, y = dy, x = dx, ay = 0, ax = 0;
+            if (d->in_stride == 2) { ay = dy & 1; ax = dx & 1; y = (dy - ay) / 2; x = (dx - ax) / 2; grp = ay * 2 + ax; }
+            qy[ph][t] = y; qx[ph][t] = x; g[ph][t] = grp;
+            if (!used[grp]) { used[grp] = true; lo_x[grp] = hi_x[grp] = x; lo_y[grp] = hi_y[grp] = y; tp->ax[grp] = ax; tp->ay[grp] = ay; }
+            else { if (x < lo_x[grp]) lo_x[grp] = x; if (x > hi_x[grp]) hi_x[grp] = x; if (y < lo_y[grp]) lo_y[grp] = y; if (y > hi_y[grp]) hi_y[grp] = y; }
+        }
+    // compact group ids in increasing order
+    int remap[4], ng = 0;
+    for (int i = 0; i < 4; ++i) { remap[i] = -1; if (used[i]) { remap[i] = ng; tp->ox[ng] = lo_x[i]; tp->oy[ng] = lo_y[i]; tp->ax[ng] = tp->ax[i]; tp->ay[ng] = tp->ay[i];
+                                                               if (hi_x[i] - lo_x[i] > tp->ex) tp->ex = hi_x[i] - lo_x[i]; if (hi_y[i] - lo_y[i] > tp->ey) tp->ey = hi_y[i] - lo_y[i]; ++ng; } }
+    tp->ngroups = ng;
+    if (tp->ex > 2 || tp->ey > 2) return false;
+    if (nph > 1 && ng != 1) return false;
+    // per phase: taps sorted by group (stable), remember original tap index for the weight column block
+    for (int ph = 0; ph < nph; ++ph) {
+        int k = 0;
+        for (int gi = 0; gi < ng; ++gi)
+            for (int t = 0; t < d->ntaps; ++t)
+                if (remap[g[ph][t]] == gi) { tp->grp[ph][k] = gi; tp->row_dy[ph][k] = qy[ph][t] - tp->oy[gi]; tp->row_dx[ph][k] = qx[ph][t] - tp->ox[gi]; tp->kidx[ph][k] = t; ++k; }
+    }
+    return true;
+}
+
+}  // namespace
+
+bool tbi_tapgemm_halo_supported(const tbi_tapgemm* d) {
+    static const bool disabled = getenv("TBI_TC_NO_HALO") != nullptr;
+    if (disabled) return false;
+    if (d->gh < 16 || d->gw < 8) return false;
+    TapPlan tp;
+    return plan_taps(d, &tp);
+}
+
+// precondition: tbi_tapgemm_tc_supported(d) (alignment, dtype, channel multiples) and tbi_tapgemm_halo_supported(d)
+int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
+    HaloParams p; memset(&p, 0, sizeof(p));
+    TapPlan tp;
+    if (!plan_taps(d, &tp)) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapgemm_halo: tap pattern");
+    const int kc = halo_pick_kc(d);
+    p.n = d->n; p.gh = d->gh; p.gw = d->gw;
+    p.tiles_x = (d->gw + TW - 1) / TW; p.tiles_y = (d->gh + TH - 1) / TH; p.m_tiles = d->n * p.tiles_x * p.tiles_y;
+    p.cgroups = d->groups; p.nphase = d->nphase > 1 ? d->nphase : 1;
+    p.cin_g = d->cin_g; p.cout_g = d->cout_g; p.cout_total = d->cout_g * d->groups;
+    p.c0 = d->groups > 1 ? d->cin_g * d->groups : d->src[0].c;
+    p.kc = kc; p.nchunks = d->cin_g / kc; p.row_bytes = kc * 2;
+    p.ngroups = tp.ngroups; p.ntaps = d->ntaps; p.pitch = TW + tp.ex;
+    p.narrow = (d->cout_g < 8 && d->groups == 1) ? 1 : 0;
+    p.epi = d->epi;
+    p.out_stride = d->nphase > 1 ? 2 : (d->epi.out_stride ? d->epi.out_stride : 1);
+    for (int gi = 0; gi < tp.ngroups; ++gi) { p.g_ox[gi] = tp.ox[gi]; p.g_oy[gi] = tp.oy[gi]; p.g_ax[gi] = tp.ax[gi]; p.g_ay[gi] = tp.ay[gi]; }
+    for (int ph = 0; ph < p.nphase; ++ph) {
+        p.ph_off_y[ph] = d->ph_off_y[ph]; p.ph_off_x[ph] = d->ph_off_x[ph];
+        for (int t = 0; t < d->ntaps; ++t) {
+            p.t_row[ph][t] = (unsigned short)(tp.row_dy[ph][t] * p.pitch + tp.row_dx[ph][t]);
+            p.t_grp[ph][t] = (unsigned char)tp.grp[ph][t]; p.t_kidx[ph][t] = (unsigned char)tp.kidx[ph][t];
+        }
+    }
+    const int bw = TW + tp.ex, bh = TH + tp.ey;
+    int rc = halo_act_tmap(&p.a[0], d->src[0], d->n, d->in_stride, kc, bw, bh, &p.a_cbase[0], &p.a_cpix[0]); if (rc) return rc;
+    if (d->groups == 1 && d->src[1].ptr) { rc = halo_act_tmap(&p.a[1], d->src[1], d->n, d->in_stride, kc, bw, bh, &p.a_cbase[1], &p.a_cpix[1]); if (rc) return rc; }
+    else p.a[1] = p.a[0];
+    int bn = 128;
+    while (bn > 16 && bn / 2 >= d->cout_g) bn >>= 1;
+    {
+        const uint64_t K = (uint64_t)d->ntaps * d->cin_g;
+        uint64_t dims[2] = {K, (uint64_t)p.cout_total * p.nphase};
+        uint64_t strides[1] = {K * 2};
+        uint32_t box[2] = {(uint32_t)kc, (uint32_t)bn};
+        rc = tbi_make_tmap_bf16(&p.b, const_cast<void*>(d->w), 2, dims, strides, box, kc * 2);
+        if (rc) return rc;
+    }
+    p.n_tiles = (d->cout_g + bn - 1) / bn;
+    p.total_tiles = p.m_tiles * p.cgroups * p.nphase * p.n_tiles;
+    p.a_tx = bw * bh * kc * 2; p.b_tx = bn * kc * 2;
+    p.a_stage_bytes = (int)r1024((uint32_t)p.a_tx); p.b_stage_bytes = (int)r1024((uint32_t)p.b_tx);
+    // ~104 KB per CTA so that two CTAs share an SM
+    const int budget = 104 * 1024;
+    p.a_stages = 2;
+    if (3 * p.a_stage_bytes + 4 * p.b_stage_bytes <= budget) p.a_stages = 3;
+    int bs = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+    if (bs > 8) bs = 8;
+    if (bs < 2) bs = 2;
+    p.b_stages = bs;
+    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512;
+    int grid = 2 * tbi_sm_count();
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    switch (bn) {
+        case 128: return launch_halo<128>(p, grid, smem, s);
+        case 64:  return launch_halo<64>(p, grid, smem, s);
+        case 32:  return launch_halo<32>(p, grid, smem, s);
+        default:  return launch_halo<16>(p, grid, smem, s);
+    }
+}
