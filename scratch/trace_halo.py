@@ -1,0 +1,26 @@
+import sys, ctypes, torch
+sys.path.insert(0, '.')
+from ultrasound_modeling_b200 import ops, _lib
+case = sys.argv[1] if len(sys.argv) > 1 else "s32"
+L = _lib.lib()
+BF = torch.bfloat16
+C = int(case[1:]); k = 3 if case[0] == 's' else 1
+x = torch.randn(64, 256, 256, C, device="cuda").to(BF); w = torch.randn(k, k, C, 32, device="cuda") * 0.05; b = torch.zeros(32, device="cuda")
+f = lambda: ops.conv2d(x, w, b, act=ops.ACT_ELU)
+for _ in range(2): f()
+tr = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
+fn = L.tbi_debug_set_halo_trace; fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p]
+assert fn(tr.data_ptr()) == 0
+f(); torch.cuda.synchronize()
+fn(None)
+t = tr.cpu().view(3, 64, 8)
+t0 = int(t[t > 0].min())
+rel = lambda v: (int(v) - t0) if int(v) > 0 else -1
+print("cycles relative to first event; producer: [wait_start, got_empty] per halo load")
+for i in range(12): print("P %2d" % i, [rel(v) for v in t[0, i, :2]])
+print("MMA: [loop_start, got_t_empty, got_a_full, committed]")
+for i in range(12): print("M %2d" % i, [rel(v) for v in t[1, i, :4]])
+print("EPI warp2: [loop_start, got_t_full, ld_done, arrived, stores_issued]")
+for i in range(12): print("E %2d" % i, [rel(v) for v in t[2, i, :5]])
+d = [int(t[1, i + 1, 3]) - int(t[1, i, 3]) for i in range(20, 40)]
+print("steady-state cycles per tile (MMA commit to commit):", sum(d) / len(d))

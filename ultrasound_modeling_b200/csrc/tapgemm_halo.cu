@@ -11,7 +11,8 @@
 //   * CTAs are persistent (grid = resident CTAs, static round-robin over tiles, N-tile fastest so
 //     neighbouring CTAs hit the same halo in L2); two TMEM accumulator buffers let the epilogue of tile
 //     i run under the TMA/MMA main loop of tile i+1; separate A (halo) and B (weights) smem rings.
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+// Warp roles (320 threads): warps 0..7 epilogue (two per TMEM lane quadrant), warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
+// (highest ids = highest scheduler priority for the two single-issuer warps).
 #include "tbi_common.cuh"
 #include "tc_common.cuh"
 #include "tc_epilogue.cuh"
@@ -21,7 +22,8 @@
 
 namespace {
 
-constexpr int HT_THREADS = 192;
+constexpr int HT_EPI_WARPS = 8;                // two per TMEM lane quadrant, each takes half of the columns
+constexpr int HT_THREADS = 64 + 32 * HT_EPI_WARPS;
 constexpr int TW = 8, TH = 16;                 // tile = 16 rows x 8 columns of pixels = 128 GEMM rows
 
 struct alignas(64) HaloParams {
@@ -40,14 +42,15 @@ struct alignas(64) HaloParams {
     int a_cbase[2], a_cpix[2];
     int out_stride, ph_off_y[4], ph_off_x[4];
     int narrow;
+    int resident, nslabs;          // weights-resident mode: a CTA keeps one (N tile, group, phase) weight slab in smem
+    int sh_x, sh_y;                // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1 (divide)
     tbi_epilogue epi;
 };
 
-__device__ __forceinline__ void ht_wait(uint64_t* bar, uint32_t parity) {
-    const long long t0 = clock64();
-    while (!tc::mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) { printf("tbi tcgen05 halo: mbarrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-    }
+// optional timeline trace (debug): block 0 writes clock64 stamps, [role][tile][event]; enabled by tbi_debug_set_trace()
+__device__ unsigned long long* g_halo_trace = nullptr;
+__device__ __forceinline__ void trace(unsigned long long* tr, int role, int tile, int ev) {
+    if (tr && blockIdx.x == 0 && tile < 64) tr[(role * 64 + tile) * 8 + ev] = clock64();
 }
 
 struct TileCoord { int x0, y0, n0, nc0, cg, ph; };
@@ -62,6 +65,104 @@ __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile, 
     t.x0 = tix * TW; t.y0 = tiy * TH; t.nc0 = nt * BN;
     return t;
 }
+// resident mode: the slab part (nc0, cg, ph) is fixed per CTA, only the M-tile index moves
+__device__ __forceinline__ void decode_mtile(const HaloParams& p, int mt, int& x0, int& y0, int& n0) {
+    if (p.sh_x >= 0) {
+        x0 = (mt & (p.tiles_x - 1)) * TW; mt >>= p.sh_x;
+        y0 = (mt & (p.tiles_y - 1)) * TH; n0 = mt >> p.sh_y;
+    } else {
+        x0 = (mt % p.tiles_x) * TW; mt /= p.tiles_x;
+        y0 = (mt % p.tiles_y) * TH; n0 = mt / p.tiles_y;
+    }
+}
+// lane 0 does the divisions, the warp gets the result by shuffle
+__device__ __forceinline__ TileCoord decode_tile_warp(const HaloParams& p, int tile, int BN, int lane, const TileCoord& slab_t, int mt) {
+    if (p.resident) { TileCoord t = slab_t; decode_mtile(p, mt, t.x0, t.y0, t.n0); return t; }
+    TileCoord t{};
+    if (lane == 0) t = decode_tile(p, tile, BN);
+    t.x0 = __shfl_sync(0xffffffffu, t.x0, 0); t.y0 = __shfl_sync(0xffffffffu, t.y0, 0); t.n0 = __shfl_sync(0xffffffffu, t.n0, 0);
+    t.nc0 = __shfl_sync(0xffffffffu, t.nc0, 0); t.cg = __shfl_sync(0xffffffffu, t.cg, 0); t.ph = __shfl_sync(0xffffffffu, t.ph, 0);
+    return t;
+}
+
+struct Rings {
+    uint8_t* a_ring; uint8_t* b_ring;
+    uint64_t *a_full, *a_empty, *b_full, *b_empty, *t_full, *t_empty, *b_res;
+    int slab, it_first, it_stride, it_count;
+};
+
+template <int BN, int ACT, int DACT>
+__device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, uint32_t tmem_base, int warp, int lane) {
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    constexpr int HALF = BN >= 32 ? BN / 2 : BN;            // columns per epilogue warp (BN = 16: one warp per quadrant works, the other idles)
+    const int q = warp & 3;
+    const int half = warp >> 2;                             // 0 or 1
+    const int m = q * 32 + lane;
+    const int xx = m & (TW - 1), yy = m >> 3;
+    uint32_t acc_it = 0;
+    TileCoord slab_t{};
+    if (p.resident) slab_t = decode_tile(p, R.slab, BN);
+    unsigned long long* tr = (warp == 0 && lane == 0) ? g_halo_trace : nullptr;
+    for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+        const TileCoord t = decode_tile_warp(p, i, BN, lane, slab_t, i);
+        trace(tr, 2, acc_it, 0);
+        const uint32_t buf = acc_it & 1u;
+        const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
+        const bool valid = gx < p.gw && gy < p.gh;
+        const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
+        const int ox = gx * p.out_stride + (p.nphase > 1 ? p.ph_off_x[t.ph] : p.epi.out_off_x);
+        RowCtx rc{};
+        if (valid && !p.narrow) rc = make_row_ctx(p.epi, n, oy, ox);
+        tc::mbar_wait_bounded<true>(&R.t_full[buf], (acc_it >> 1) & 1u);
+        tc::tc_fence_after();
+        trace(tr, 2, acc_it, 1);
+        const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16) + half * HALF;
+        if constexpr (BN >= 64) {
+#pragma unroll 1
+            for (int c = 0; c < HALF; c += 32) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + c, r);
+                tc::tmem_ld_wait();
+                if (c + 32 >= HALF) {                                     // last read of this buffer: hand it back to the MMA warp
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
+                }
+                if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + half * HALF + c, p.cout_g, t.cg * p.cout_g);
+            }
+        } else if constexpr (BN == 32) {
+            uint32_t r[16];
+            tc::tmem_ld16(taddr, r);
+            tc::tmem_ld_wait();
+            trace(tr, 2, acc_it, 2);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
+            trace(tr, 2, acc_it, 3);
+            if (valid) epilogue_cols<ACT, DACT, 16>(rc, r, t.nc0 + half * HALF, p.cout_g, t.cg * p.cout_g);
+            trace(tr, 2, acc_it, 4);
+        } else {
+            if (half == 1) {                                              // BN = 16: nothing left for the second warp of the quadrant
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
+                continue;
+            }
+            uint32_t r[16];
+            tc::tmem_ld16(taddr, r);
+            tc::tmem_ld_wait();
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
+            if (valid && p.narrow) {
+                for (int j = 0; j < 16; ++j)
+                    if (t.nc0 + j < p.cout_g) epilogue_store<__nv_bfloat16>(p.epi, n, oy, ox, t.cg * p.cout_g + t.nc0 + j, __uint_as_float(r[j]));
+            } else if (valid) {
+                epilogue_cols<ACT, DACT, 16>(rc, r, t.nc0, p.cout_g, t.cg * p.cout_g);
+            }
+        }
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_constant__ HaloParams p) {
@@ -69,176 +170,217 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint8_t* a_ring = smem;
-    uint8_t* b_ring = smem + (size_t)p.a_stages * p.a_stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + (size_t)p.b_stages * p.b_stage_bytes);
-    uint64_t* a_full = bars;
-    uint64_t* a_empty = a_full + p.a_stages;
-    uint64_t* b_full = a_empty + p.a_stages;
-    uint64_t* b_empty = b_full + p.b_stages;
-    uint64_t* t_full = b_empty + p.b_stages;               // [2]
-    uint64_t* t_empty = t_full + 2;                        // [2]
-    uint32_t* tslot = reinterpret_cast<uint32_t*>(t_empty + 2);
+    Rings R;
+    R.a_ring = smem;
+    R.b_ring = smem + (size_t)p.a_stages * p.a_stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(R.b_ring + (size_t)p.b_stages * p.b_stage_bytes);
+    R.a_full = bars;
+    R.a_empty = R.a_full + p.a_stages;
+    R.b_full = R.a_empty + p.a_stages;
+    R.b_empty = R.b_full + p.b_stages;
+    R.t_full = R.b_empty + p.b_stages;                     // [2]
+    R.t_empty = R.t_full + 2;                              // [2]
+    R.b_res = R.t_empty + 2;                               // weights-resident slab loaded
+    uint32_t* tslot = reinterpret_cast<uint32_t*>(R.b_res + 1);
+    uint4* mma_tab = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(tslot + 4) + 15) & ~static_cast<uintptr_t>(15));  // resident mode: one entry per (chunk, tap): {a row offset>>4, b addr>>4, flags, -}
+    // tile iteration: streaming = round-robin over all tiles; resident = this CTA's slab x a strided set of M tiles
+    R.slab = p.resident ? (int)(blockIdx.x % p.nslabs) : 0;
+    R.it_first = p.resident ? (int)(blockIdx.x / p.nslabs) : (int)blockIdx.x;
+    R.it_stride = p.resident ? (int)(gridDim.x / p.nslabs) : (int)gridDim.x;
+    R.it_count = p.resident ? p.m_tiles : p.total_tiles;
 
+    // the scheduler prefers higher warp ids: the two single-issuer warps get the highest ids so the epilogue math cannot starve them
+    constexpr int W_TMA = HT_EPI_WARPS, W_MMA = HT_EPI_WARPS + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 0 && lane == 0) {
+    if (warp == W_TMA && lane == 0) {
         tc::prefetch_tmap(&p.a[0]); tc::prefetch_tmap(&p.b);
         if (p.c0 < p.cin_g * p.cgroups) tc::prefetch_tmap(&p.a[1]);
-        for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&a_full[s], 1); tc::mbar_init(&a_empty[s], 1); }
-        for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&b_full[s], 1); tc::mbar_init(&b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&t_full[s], 1); tc::mbar_init(&t_empty[s], 4); }
+        for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&R.a_full[s], 1); tc::mbar_init(&R.a_empty[s], 1); }
+        for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&R.b_full[s], 1); tc::mbar_init(&R.b_empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&R.t_full[s], 1); tc::mbar_init(&R.t_empty[s], HT_EPI_WARPS); }
+        tc::mbar_init(R.b_res, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tslot);
+    if (warp == W_MMA) tc::tmem_alloc<TMEM_COLS>(tslot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tslot;
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===================== TMA producer =====================
-            uint32_t a_it = 0, b_it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile, BN);
-                for (int c = 0; c < p.nchunks; ++c) {
-                    const int ch = c * p.kc;
-                    int src = 0, cch = ch + (p.cgroups > 1 ? t.cg * p.cin_g : 0);
-                    if (p.cgroups == 1 && cch >= p.c0) { src = 1; cch -= p.c0; }
-                    int tap = 0;
-                    for (int grp = 0; grp < p.ngroups; ++grp) {
-                        const uint32_t sa = a_it % p.a_stages;
-                        ht_wait(&a_empty[sa], ((a_it / p.a_stages) & 1u) ^ 1u);
-                        tc::mbar_expect_tx(&a_full[sa], p.a_tx);
-                        tc::tma_load_5d(a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], &a_full[sa],
+    if (warp == W_TMA) {
+        // ===================== TMA producer: the whole warp walks the loop, one elected lane issues =====================
+        const bool leader = tc::elect_one();
+        uint32_t a_it = 0, b_it = 0;
+        TileCoord slab_t{};
+        if (p.resident) slab_t = decode_tile(p, R.slab, BN);
+        if (p.resident && R.it_first < R.it_count && leader) {            // the whole weight slab, once
+            tc::mbar_expect_tx(R.b_res, (uint32_t)(p.nchunks * p.ntaps) * p.b_tx);
+            for (int c = 0; c < p.nchunks; ++c)
+                for (int tap = 0; tap < p.ntaps; ++tap)
+                    tc::tma_load_2d(R.b_ring + (size_t)(c * p.ntaps + tap) * p.b_stage_bytes, &p.b, R.b_res,
+                                    (int)p.t_kidx[slab_t.ph][tap] * p.cin_g + c * p.kc, slab_t.ph * p.cout_total + slab_t.cg * p.cout_g + slab_t.nc0);
+        }
+        for (int i = R.it_first; i < R.it_count; i += R.it_stride) {
+            TileCoord t;
+            if (p.resident) { t = slab_t; decode_mtile(p, i, t.x0, t.y0, t.n0); } else t = decode_tile(p, i, BN);
+            for (int c = 0; c < p.nchunks; ++c) {
+                const int ch = c * p.kc;
+                int src = 0, cch = ch + (p.cgroups > 1 ? t.cg * p.cin_g : 0);
+                if (p.cgroups == 1 && cch >= p.c0) { src = 1; cch -= p.c0; }
+                int tap = 0;
+                for (int grp = 0; grp < p.ngroups; ++grp) {
+                    const uint32_t sa = a_it % p.a_stages;
+                    trace(g_halo_trace, 0, a_it, 0);
+                    tc::mbar_wait_bounded(&R.a_empty[sa], ((a_it / p.a_stages) & 1u) ^ 1u);
+                    trace(g_halo_trace, 0, a_it, 1);
+                    if (leader) {
+                        tc::mbar_expect_tx(&R.a_full[sa], p.a_tx);
+                        tc::tma_load_5d(R.a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], &R.a_full[sa],
                                         p.a_cbase[src] + cch + p.g_ax[grp] * p.a_cpix[src], t.x0 + p.g_ox[grp], p.g_ay[grp], t.y0 + p.g_oy[grp], t.n0);
-                        ++a_it;
-                        while (tap < p.ntaps && p.t_grp[t.ph][tap] == grp) {
-                            const uint32_t sb = b_it % p.b_stages;
-                            ht_wait(&b_empty[sb], ((b_it / p.b_stages) & 1u) ^ 1u);
-                            tc::mbar_expect_tx(&b_full[sb], p.b_tx);
-                            tc::tma_load_2d(b_ring + (size_t)sb * p.b_stage_bytes, &p.b, &b_full[sb], (int)p.t_kidx[t.ph][tap] * p.cin_g + ch,
+                    }
+                    ++a_it;
+                    if (p.resident) continue;
+                    while (tap < p.ntaps && p.t_grp[t.ph][tap] == grp) {
+                        const uint32_t sb = b_it % p.b_stages;
+                        tc::mbar_wait_bounded(&R.b_empty[sb], ((b_it / p.b_stages) & 1u) ^ 1u);
+                        if (leader) {
+                            tc::mbar_expect_tx(&R.b_full[sb], p.b_tx);
+                            tc::tma_load_2d(R.b_ring + (size_t)sb * p.b_stage_bytes, &p.b, &R.b_full[sb], (int)p.t_kidx[t.ph][tap] * p.cin_g + ch,
                                             t.ph * p.cout_total + t.cg * p.cout_g + t.nc0);
-                            ++b_it; ++tap;
                         }
+                        ++b_it; ++tap;
                     }
                 }
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===================== MMA issuer =====================
-            const uint32_t idesc = tc::make_idesc_bf16(128, BN, 0, 0);
-            const uint32_t layout = p.kc == 64 ? 2u : p.kc == 32 ? 4u : 6u;
-            const uint32_t sbo_a = (uint32_t)p.pitch * p.row_bytes;       // 8-row group == one tile row of the halo
-            const uint32_t sbo_b = 8u * p.row_bytes;
-            const int ksteps = p.kc / 16;
-            uint32_t a_it = 0, b_it = 0, acc_it = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++acc_it) {
-                const TileCoord t = decode_tile(p, tile, BN);
+    } else if (warp == W_MMA) {
+        // ===================== MMA issuer: warp-uniform loop (descriptors live in uniform registers), elected lane issues =====================
+        const bool leader = tc::elect_one();
+        const uint32_t idesc = tc::make_idesc_bf16(128, BN, 0, 0);
+        const uint32_t layout = p.kc == 64 ? 2u : p.kc == 32 ? 4u : 6u;
+        const uint64_t da_base = tc::smem_desc_base(16, (uint32_t)p.pitch * p.row_bytes, layout);       // 8-row group == one halo tile row
+        const uint64_t db_base = tc::smem_desc_base(16, 8u * p.row_bytes, layout);
+        const uint32_t a_lo0 = (uint32_t)da_base, a_hi = (uint32_t)(da_base >> 32), b_lo0 = (uint32_t)db_base, b_hi = (uint32_t)(db_base >> 32);
+        const uint32_t a_ring_lo = (tc::smem_u32(R.a_ring) & 0x3FFFFu) >> 4, a_stage_lo = (uint32_t)p.a_stage_bytes >> 4;
+        const uint32_t b_ring_lo = (tc::smem_u32(R.b_ring) & 0x3FFFFu) >> 4, b_stage_lo = (uint32_t)p.b_stage_bytes >> 4;
+        const uint32_t row_lo = (uint32_t)p.row_bytes >> 4;
+        const int ksteps = p.kc / 16;
+        uint32_t a_it = 0, b_it = 0, acc_it = 0;
+        const int slab_ph = p.resident ? decode_tile(p, R.slab, BN).ph : 0;
+        // per-phase tap table packed into registers: 12 bits per tap = row offset (10) | first-of-group (1) | last-of-group (1),
+        // five taps per 64-bit word, consumed by a running shift -> no memory load sits in front of an MMA
+        unsigned long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0; int cur_ph = -1;
+        auto load_taps = [&](int ph) {
+            tw0 = tw1 = tw2 = tw3 = 0;
+            for (int t = 0; t < p.ntaps; ++t) {
+                const int g = p.t_grp[ph][t];
+                unsigned long long e = (unsigned long long)p.t_row[ph][t] & 0x3FFull;
+                if (t == 0 || p.t_grp[ph][t - 1] != g) e |= 0x400ull;
+                if (t + 1 == p.ntaps || p.t_grp[ph][t + 1] != g) e |= 0x800ull;
+                e <<= 12 * (t % 5);
+                if (t < 5) tw0 |= e; else if (t < 10) tw1 |= e; else if (t < 15) tw2 |= e; else tw3 |= e;
+            }
+            cur_ph = ph;
+        };
+        if (p.resident) {
+            // ---- weights resident: nothing but halo waits, descriptor adds and MMAs in the steady state ----
+            if (R.it_first < R.it_count) { load_taps(slab_ph); tc::mbar_wait_bounded(R.b_res, 0); }
+            uint32_t sa = 0, a_par = 0;
+            const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
+            for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
                 const uint32_t buf = acc_it & 1u;
-                ht_wait(&t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator
+                trace(g_halo_trace, 1, acc_it, 0);
+                tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
                 tc::tc_fence_after();
+                trace(g_halo_trace, 1, acc_it, 1);
                 const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
-                uint32_t first = 1;
+                uint32_t accum = 0, b_lo = b_base, a_lo = 0;
+#pragma unroll 1
                 for (int c = 0; c < p.nchunks; ++c) {
-                    int tap = 0;
-                    for (int grp = 0; grp < p.ngroups; ++grp) {
-                        const uint32_t sa = a_it % p.a_stages;
-                        ht_wait(&a_full[sa], (a_it / p.a_stages) & 1u);
-                        const uint32_t a_addr = tc::smem_u32(a_ring + (size_t)sa * p.a_stage_bytes);
-                        while (tap < p.ntaps && p.t_grp[t.ph][tap] == grp) {
-                            const uint32_t sb = b_it % p.b_stages;
-                            ht_wait(&b_full[sb], (b_it / p.b_stages) & 1u);
+                    unsigned long long cur = tw0;
+#pragma unroll 1
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        if (tap == 5) cur = tw1; else if (tap == 10) cur = tw2; else if (tap == 15) cur = tw3;
+                        const uint32_t e = (uint32_t)cur & 0xFFFu;
+                        cur >>= 12;
+                        if (e & 0x400u) {
+                            tc::mbar_wait_bounded(&R.a_full[sa], a_par);
                             tc::tc_fence_after();
-                            const uint32_t a_tap = a_addr + (uint32_t)p.t_row[t.ph][tap] * p.row_bytes;
-                            const uint32_t b_addr = tc::smem_u32(b_ring + (size_t)sb * p.b_stage_bytes);
-                            for (int k = 0; k < ksteps; ++k) {
-                                const uint64_t da = tc::make_smem_desc(a_tap + k * 32, 16, sbo_a, layout);
-                                const uint64_t db = tc::make_smem_desc(b_addr + k * 32, 16, sbo_b, layout);
-                                tc::umma_bf16(tmem_d, da, db, idesc, first ? 0u : 1u);
-                                first = 0;
-                            }
-                            tc::umma_commit(&b_empty[sb]);
-                            ++b_it; ++tap;
+                            trace(g_halo_trace, 1, acc_it, 2);
+                            a_lo = a_base + sa * a_stage_lo;
                         }
-                        tc::umma_commit(&a_empty[sa]);
-                        ++a_it;
+                        const uint32_t al = a_lo + (e & 0x3FFu) * row_lo;
+                        if (leader) {
+#pragma unroll 1
+                            for (int k = 0; k < ksteps; ++k) { tc::umma_bf16_lh(tmem_d, al + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accum); accum = 1; }
+                        }
+                        b_lo += b_stage_lo;
+                        if (e & 0x800u) {
+                            if (leader) tc::umma_commit(&R.a_empty[sa]);
+                            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+                        }
                     }
                 }
-                tc::umma_commit(&t_full[buf]);
+                if (leader) tc::umma_commit(&R.t_full[buf]);
+                trace(g_halo_trace, 1, acc_it, 3);
             }
+        } else
+        for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+            const int ph = (p.nphase > 1 ? decode_tile(p, i, BN).ph : 0);
+            if (ph != cur_ph) load_taps(ph);
+            const uint32_t buf = acc_it & 1u;
+            trace(g_halo_trace, 1, acc_it, 0);
+            tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator
+            tc::tc_fence_after();
+            trace(g_halo_trace, 1, acc_it, 1);
+            const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+            uint32_t accum = 0;
+            for (int c = 0; c < p.nchunks; ++c) {
+                uint32_t sa = 0, a_lo = 0;
+                uint32_t b_res_lo = b_lo0 + b_ring_lo + (uint32_t)(c * p.ntaps) * b_stage_lo;
+                unsigned long long cur = tw0;
+#pragma unroll 1
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    if (tap == 5) cur = tw1; else if (tap == 10) cur = tw2; else if (tap == 15) cur = tw3;
+                    const uint32_t e = (uint32_t)cur & 0xFFFu;
+                    cur >>= 12;
+                    if (e & 0x400u) {
+                        sa = a_it % p.a_stages;
+                        tc::mbar_wait_bounded(&R.a_full[sa], (a_it / p.a_stages) & 1u);
+                        tc::tc_fence_after();
+                        trace(g_halo_trace, 1, acc_it, 2);
+                        a_lo = a_lo0 + a_ring_lo + sa * a_stage_lo;
+                    }
+                    uint32_t sb = 0, b_lo;
+                    if (p.resident) {
+                        b_lo = b_res_lo; b_res_lo += b_stage_lo;
+                    } else {
+                        sb = b_it % p.b_stages;
+                        tc::mbar_wait_bounded(&R.b_full[sb], (b_it / p.b_stages) & 1u);
+                        tc::tc_fence_after();
+                        b_lo = b_lo0 + b_ring_lo + sb * b_stage_lo;
+                    }
+                    const uint32_t al = a_lo + (e & 0x3FFu) * row_lo;
+                    if (leader) {
+                        for (int k = 0; k < ksteps; ++k) { tc::umma_bf16_lh(tmem_d, al + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accum); accum = 1; }
+                    }
+                    accum = 1;
+                    if (!p.resident) { if (leader) tc::umma_commit(&R.b_empty[sb]); ++b_it; }
+                    if (e & 0x800u) { if (leader) tc::umma_commit(&R.a_empty[sa]); ++a_it; }
+                }
+            }
+            if (leader) tc::umma_commit(&R.t_full[buf]);
+            trace(g_halo_trace, 1, acc_it, 3);
         }
         __syncwarp();
     } else {
         // ===================== epilogue (warp w owns TMEM lanes [32*(w%4), +32)) =====================
-        const int q = warp & 3;
-        const int m = q * 32 + lane;
-        const int xx = m & (TW - 1), yy = m >> 3;
-        uint32_t acc_it = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++acc_it) {
-            const TileCoord t = decode_tile(p, tile, BN);
-            const uint32_t buf = acc_it & 1u;
-            const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
-            const bool valid = gx < p.gw && gy < p.gh;
-            const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
-            const int ox = gx * p.out_stride + (p.nphase > 1 ? p.ph_off_x[t.ph] : p.epi.out_off_x);
-            ht_wait(&t_full[buf], (acc_it >> 1) & 1u);
-            tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
-            if constexpr (BN >= 32) {
-#pragma unroll 1
-                for (int c = 0; c < BN; c += 32) {
-                    uint32_t r[32];
-                    tc::tmem_ld32(taddr + c, r);
-                    tc::tmem_ld_wait();
-                    if (c + 32 >= BN) {                                   // last read of this buffer: hand it back to the MMA warp
-                        tc::tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) tc::mbar_arrive(&t_empty[buf]);
-                    }
-                    if (valid) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const int col = t.nc0 + c + j;
-                            if (col < p.cout_g) {
-                                float v[8];
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
-                                epilogue_store8(p.epi, n, oy, ox, t.cg * p.cout_g + col, v);
-                            }
-                        }
-                    }
-                }
-            } else {
-                uint32_t r[16];
-                tc::tmem_ld16(taddr, r);
-                tc::tmem_ld_wait();
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&t_empty[buf]);
-                if (valid && p.narrow) {
-                    for (int j = 0; j < 16; ++j)
-                        if (t.nc0 + j < p.cout_g) epilogue_store<__nv_bfloat16>(p.epi, n, oy, ox, t.cg * p.cout_g + t.nc0 + j, __uint_as_float(r[j]));
-                } else if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 8) {
-                        const int col = t.nc0 + j;
-                        if (col < p.cout_g) {
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
-                            epilogue_store8(p.epi, n, oy, ox, t.cg * p.cout_g + col, v);
-                        }
-                    }
-                }
-            }
-        }
+        TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_role<BN, A_, D_>(p, R, tmem_base, warp, lane)));
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (warp == W_MMA) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 inline uint32_t r1024(uint32_t x) { return (x + 1023u) & ~1023u; }
@@ -318,6 +460,12 @@ bool plan_taps(const tbi_tapgemm* d, TapPlan* tp) {
 
 }  // namespace
 
+// debug: device buffer of 3*64*8 uint64 (or nullptr to disable); not part of the public header
+extern "C" int tbi_debug_set_halo_trace(void* buf) {
+    unsigned long long* p = (unsigned long long*)buf;
+    return cudaMemcpyToSymbol(g_halo_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -4;
+}
+
 bool tbi_tapgemm_halo_supported(const tbi_tapgemm* d) {
     static const bool disabled = getenv("TBI_TC_NO_HALO") != nullptr;
     if (disabled) return false;
@@ -370,15 +518,38 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     p.a_stage_bytes = (int)r1024((uint32_t)p.a_tx); p.b_stage_bytes = (int)r1024((uint32_t)p.b_tx);
     // ~104 KB per CTA so that two CTAs share an SM
     const int budget = 104 * 1024;
-    p.a_stages = 2;
-    if (3 * p.a_stage_bytes + 4 * p.b_stage_bytes <= budget) p.a_stages = 3;
-    int bs = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
-    if (bs > 8) bs = 8;
-    if (bs < 2) bs = 2;
-    p.b_stages = bs;
-    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512;
-    int grid = 2 * tbi_sm_count();
-    if (grid > p.total_tiles) grid = p.total_tiles;
+    const int max_ctas = 2 * tbi_sm_count();
+    p.nslabs = p.n_tiles * p.cgroups * p.nphase;
+    const long long slab_bytes = (long long)p.nchunks * d->ntaps * p.b_stage_bytes;
+    static const bool no_resident = getenv("TBI_TC_NO_RESIDENT") != nullptr;
+    p.resident = (!no_resident && slab_bytes <= 72 * 1024 && p.nslabs <= max_ctas && slab_bytes + 2 * p.a_stage_bytes <= budget &&
+                  p.nchunks * d->ntaps <= 192) ? 1 : 0;
+    auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
+    p.sh_x = lg2(p.tiles_x); p.sh_y = lg2(p.tiles_y);
+    if (p.sh_x < 0 || p.sh_y < 0) p.sh_x = p.sh_y = -1;
+    int grid;
+    if (p.resident) {
+        // weights stay in smem for the CTA's lifetime; everything else is a deep ring of halo tiles
+        p.b_stages = p.nchunks * d->ntaps;
+        int as = (int)((budget - slab_bytes) / p.a_stage_bytes);
+        if (as > 8) as = 8;
+        p.a_stages = as;
+        int per_slab = max_ctas / p.nslabs;
+        if (per_slab > p.m_tiles) per_slab = p.m_tiles;
+        if (per_slab < 1) per_slab = 1;
+        grid = per_slab * p.nslabs;
+    } else {
+        p.a_stages = 2;
+        if (3 * p.a_stage_bytes + 4 * p.b_stage_bytes <= budget) p.a_stages = 3;
+        int bs = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
+        if (bs > 8) bs = 8;
+        if (bs < 2) bs = 2;
+        p.b_stages = bs;
+        grid = max_ctas;
+        if (grid > p.total_tiles) grid = p.total_tiles;
+    }
+    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512 +
+                        (p.resident ? (size_t)p.nchunks * d->ntaps * 16 + 64 : 0) + (size_t)(2 * (p.a_stages + p.b_stages)) * 8;
     switch (bn) {
         case 128: return launch_halo<128>(p, grid, smem, s);
         case 64:  return launch_halo<64>(p, grid, smem, s);

@@ -44,10 +44,7 @@ struct alignas(64) TcGemmParams {
 
 __device__ __forceinline__ void mbar_wait_guard(uint64_t* bar, uint32_t parity) {
     // a wrong descriptor must become an error, not a hung GPU: trap after ~2 s of waiting
-    const long long t0 = clock64();
-    while (!tc::mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) { printf("tbi tcgen05: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
-    }
+    tc::mbar_wait_bounded(bar, parity);
 }
 
 __host__ __device__ constexpr uint32_t round1024(uint32_t x) { return (x + 1023u) & ~1023u; }
@@ -141,6 +138,8 @@ __global__ void __launch_bounds__(NUM_THREADS) tapgemm_tc_kernel(const __grid_co
         const int os = p.out_stride;
         const int oy = gy * os + (p.nphase > 1 ? p.ph_off_y[ph] : p.epi.out_off_y);
         const int ox = gx * os + (p.nphase > 1 ? p.ph_off_x[ph] : p.epi.out_off_x);
+        RowCtx rc{};
+        if (valid && !p.narrow) rc = make_row_ctx(p.epi, n, oy, ox);
         mbar_wait_guard(tfull, 0);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -150,18 +149,7 @@ __global__ void __launch_bounds__(NUM_THREADS) tapgemm_tc_kernel(const __grid_co
                 uint32_t r[32];
                 tc::tmem_ld32(taddr + c, r);
                 tc::tmem_ld_wait();
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        const int col = nc0 + c + j;
-                        if (col < p.cout_g) {
-                            float v[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
-                            epilogue_store8(p.epi, n, oy, ox, g * p.cout_g + col, v);
-                        }
-                    }
-                }
+                if (valid) TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_cols<A_, D_, 32>(rc, r, nc0 + c, p.cout_g, g * p.cout_g)));
             }
         } else {
             uint32_t r[16];
@@ -171,16 +159,7 @@ __global__ void __launch_bounds__(NUM_THREADS) tapgemm_tc_kernel(const __grid_co
                 for (int j = 0; j < 16; ++j)
                     if (nc0 + j < p.cout_g) epilogue_store<__nv_bfloat16>(p.epi, n, oy, ox, g * p.cout_g + nc0 + j, __uint_as_float(r[j]));
             } else if (valid) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 8) {
-                    const int col = nc0 + j;
-                    if (col < p.cout_g) {
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
-                        epilogue_store8(p.epi, n, oy, ox, g * p.cout_g + col, v);
-                    }
-                }
+                TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_cols<A_, D_, 16>(rc, r, nc0, p.cout_g, g * p.cout_g)));
             }
         }
     }
@@ -270,6 +249,7 @@ bool tbi_tapgemm_tc_supported(const tbi_tapgemm* d, const char** why) {
     if (d->in_stride == 2 && ((d->src[0].h | d->src[0].w) & 1)) NO("stride-2 gather needs even source dims");
     const tbi_epilogue& e = d->epi;
     if (e.out_f32 && !narrow) NO("fp32 output");
+    if (e.act != TBI_ACT_NONE && e.dact != TBI_ACT_NONE) NO("activation and activation-derivative in one epilogue");
     if (!narrow) {
         if (!aligned_view(e.out) || !aligned_view(e.residual) || !aligned_view(e.dact_ref) || !aligned_view(e.out2) || !aligned_view(e.residual2))
             NO("epilogue view not 16-byte aligned");

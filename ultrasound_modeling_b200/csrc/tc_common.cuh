@@ -35,6 +35,31 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
+// bounded wait.  Fast path = one try_wait, inlined; the polling loop (with the watchdog that turns a wrong descriptor /
+// byte count into a trap the host sees instead of a hung GPU) is out of line so hot loops stay small.
+template <bool RELAXED>
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+#pragma unroll 1
+        for (int i = 0; i < 4096; ++i) {
+            if (RELAXED) __nanosleep(64);          // epilogue warps: leave the issue slots to the TMA / MMA warps
+            if (mbar_try_wait(bar, parity)) return;
+        }
+        if (clock64() - t0 > 6000000000LL) { printf("tbi tcgen05: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
+    }
+}
+template <bool RELAXED = false>
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+    if (!mbar_try_wait(bar, parity)) mbar_wait_slow<RELAXED>(bar, parity);
+}
+
+// one lane of a converged warp (warp-uniform control flow around it keeps addresses/descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 // ---------------- TMA ----------------
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
@@ -73,6 +98,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same, descriptors given as (lo, hi) 32-bit halves: the issue loop only ever adds to the 14-bit address field in lo
+__device__ __forceinline__ void umma_bf16_lh(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 // arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -113,6 +148,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     d |= (uint64_t)(layout & 7u) << 61;
     return d;
 }
+// the part of the descriptor that does not depend on the address, and the cheap per-MMA completion
+__device__ __forceinline__ uint64_t smem_desc_base(uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    return make_smem_desc(0, lbo_bytes, sbo_bytes, layout);
+}
+__device__ __forceinline__ uint64_t smem_desc_at(uint64_t base, uint32_t saddr) { return base | (uint64_t)((saddr & 0x3FFFFu) >> 4); }
 // instruction descriptor for kind::f16, bf16 x bf16 -> fp32:
 //   [4,6) D fmt (1 = f32) | [7,10) A fmt (1 = bf16) | [10,13) B fmt | [15] A major (0 = K, 1 = MN) | [16] B major
 //   [17,23) N >> 3 | [24,29) M >> 4
