@@ -105,6 +105,12 @@ def test_convt_fwd_dgrad_tc_vs_simt(ops, case):
     (2, 16, 16, (128, 64), 96, 3, 1),     # two sources, partial N tile
     (5, 4, 4, (512, 0), 256, 3, 1),       # pixel tile spans images
     (1, 40, 24, (64, 0), 64, 3, 1),       # non power-of-two spatial
+    (2, 32, 32, (32, 0), 32, 3, 1),       # small-channel kernel: stem 32->32 (SW64 x, 3 dx taps packed in M)
+    (2, 32, 24, (16, 0), 32, 3, 1),       # small-channel kernel: stem 16->32 (SW32 x, 8 M blocks)
+    (2, 32, 32, (32, 0), 64, 3, 1),       # small-channel kernel: 32->64 (N = 64)
+    (3, 16, 16, (32, 0), 64, 1, 1),       # small-channel kernel: 1x1 shortcut 32->64
+    (2, 32, 32, (32, 0), 64, 3, 2),       # small-channel kernel, grouped 16->32 (stage-1 cardinal conv2)
+    (1, 20, 12, (24, 0), 40, 3, 1),       # small-channel kernel: odd channel counts + partial tiles
 ])
 def test_conv_wgrad_tc_vs_simt(ops, case):
     torch.manual_seed(3)

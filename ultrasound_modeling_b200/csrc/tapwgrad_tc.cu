@@ -205,6 +205,11 @@ bool tbi_tapwgrad_tc_supported(const tbi_tapwgrad* d, const char** why) {
     if (d->dtype != TBI_BF16) NO("storage dtype is not bf16");
     if (!tbi_get_encode_tiled()) NO("no cuTensorMapEncodeTiled");
     if (d->ntaps < 1 || d->ntaps > TBI_MAX_TAPS) NO("ntaps");
+    {
+        const bool views_ok = d->a_src[0].cstride % 8 == 0 && d->a_src[0].coff % 8 == 0 && ((uintptr_t)d->a_src[0].ptr & 15) == 0 &&
+                              d->b_src.cstride % 8 == 0 && d->b_src.coff % 8 == 0 && ((uintptr_t)d->b_src.ptr & 15) == 0;
+        if (views_ok && tbi_tapwgrad_small_supported(d)) return true;
+    }
     if (d->a_stride != 1) NO("a_stride");
     if (d->b_stride != 1 && d->b_stride != 2) NO("b_stride");
     if (d->groups > 1 && d->a_src[1].ptr) NO("groups with two sources");
@@ -226,6 +231,7 @@ int64_t tbi_tapwgrad_tc_workspace(const tbi_tapwgrad*) { return 0; }   // partia
 int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s) {
     const char* why = "";
     if (!tbi_tapwgrad_tc_supported(d, &why)) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapwgrad_tc: %s", why);
+    if (tbi_tapwgrad_small_supported(d)) return tbi_tapwgrad_small(d, s);
     TcWgradParams p; memset(&p, 0, sizeof(p));
     int ltw = wg_ilog2_ceil(d->gw); if (ltw > 3) ltw = 3;
     int lth = wg_ilog2_ceil(d->gh); if (lth > 6 - ltw) lth = 6 - ltw;
