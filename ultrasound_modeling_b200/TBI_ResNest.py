@@ -76,7 +76,9 @@ class ResNest:
         """host (numpy/torch, fp64/fp32) or device tensor -> the engine's static fp32 input buffer"""
         if isinstance(arr, np.ndarray):
             arr = torch.from_numpy(np.ascontiguousarray(arr))
-        if arr.device.type == "cpu":
+        if arr.device.type == "cpu" and arr.dtype == torch.float32 and arr.is_contiguous() and arr.is_pinned():
+            dst.copy_(arr.reshape(dst.shape), non_blocking=True)      # caller's pinned fp32 buffer: DMA straight from it
+        elif arr.device.type == "cpu":
             pin = self._pin.get(name)
             if pin is None or pin.shape != dst.shape:
                 pin = torch.empty(dst.shape, dtype=torch.float32, pin_memory=True)
@@ -113,6 +115,20 @@ class ResNest:
                 self._warm.add(key)
                 self._device_step(train, draw)
                 return
+        if train and self.grad_sync is not None:
+            # data parallel: graph segments + eager NCCL between them (collectives are never captured)
+            e = self.engine
+
+            def pre():
+                e.prepare()
+                if draw:
+                    e.draw_dropout()
+                e.forward()
+                e.loss()
+
+            self.grad_sync.step_graphed(e, pre, lambda: e.adam(self.optimizer.learning_rate, 1.0 / self.grad_sync.world_size), key)
+            return
+        if g is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

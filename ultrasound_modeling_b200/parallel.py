@@ -42,16 +42,14 @@ class GradSync:
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self._plan = None
         self._plan_key = None
+        self._seg_graphs = {}
 
     def allreduce(self, flat_slice: torch.Tensor):
         dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.pg)
 
     def backward_and_sync(self, engine):
         """run engine.prog_bwd, interleaving bucket all-reduces on a side stream"""
-        key = (id(engine), engine.N)
-        if self._plan_key != key:
-            self._plan = plan_buckets(engine.bwd_marks, engine.P.total, self.bucket_elems)
-            self._plan_key = key
+        self._ensure_plan(engine)
         if self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream(device=engine.device)
         cur = torch.cuda.current_stream(engine.device)
@@ -67,3 +65,56 @@ class GradSync:
                 self.allreduce(engine.grads[lo:hi])
         engine._run(engine.prog_bwd[pos:], cur.cuda_stream)
         cur.wait_stream(self.comm_stream)
+
+    # ------------------------------------------------------------------ CUDA-graph replay with eager collectives
+    def step_graphed(self, engine, pre_fn, post_fn, key):
+        """One training step as CUDA-graph SEGMENTS: [pre_fn = prepare/forward/loss] , one graph per backward slice
+        between bucket boundaries, [post_fn = Adam].  The bucket all-reduces are launched eagerly on the side stream
+        between segment replays (NCCL calls are never captured), so they overlap the following backward segments
+        exactly as in the eager path."""
+        self._ensure_plan(engine)
+        if self.comm_stream is None:
+            self.comm_stream = torch.cuda.Stream(device=engine.device)
+        cur = torch.cuda.current_stream(engine.device)
+        graphs = self._seg_graphs.get(key)
+        if graphs is None:
+            torch.cuda.synchronize()
+
+            def cap(fn):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    fn()
+                return g
+
+            def pre():
+                pre_fn()
+                engine.grads.zero_()
+
+            segs, pos = [], 0
+            for calls, lo, hi in self._plan:
+                a, b = pos, calls
+                segs.append((cap(lambda a=a, b=b: engine._run(engine.prog_bwd[a:b], engine.stream())) if b > a else None, lo, hi))
+                pos = calls
+            tail = cap(lambda: engine._run(engine.prog_bwd[pos:], engine.stream())) if pos < len(engine.prog_bwd) else None
+            graphs = dict(pre=cap(pre), segs=segs, tail=tail, post=cap(post_fn))
+            self._seg_graphs[key] = graphs
+            cur = torch.cuda.current_stream(engine.device)
+        graphs["pre"].replay()
+        for g, lo, hi in graphs["segs"]:
+            if g is not None:
+                g.replay()
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                self.allreduce(engine.grads[lo:hi])
+        if graphs["tail"] is not None:
+            graphs["tail"].replay()
+        cur.wait_stream(self.comm_stream)
+        graphs["post"].replay()
+
+    def _ensure_plan(self, engine):
+        key = (id(engine), engine.N)
+        if self._plan_key != key:
+            self._plan = plan_buckets(engine.bwd_marks, engine.P.total, self.bucket_elems)
+            self._plan_key = key
