@@ -4,9 +4,19 @@ from ultrasound_modeling_b200 import ops, _lib
 case = sys.argv[1] if len(sys.argv) > 1 else "s32"
 L = _lib.lib()
 BF = torch.bfloat16
-C = int(case[1:]); k = 3 if case[0] == 's' else 1
-x = torch.randn(64, 256, 256, C, device="cuda").to(BF); w = torch.randn(k, k, C, 32, device="cuda") * 0.05; b = torch.zeros(32, device="cuda")
-f = lambda: ops.conv2d(x, w, b, act=ops.ACT_ELU)
+if case == "up4":
+    x1 = torch.randn(64, 64, 64, 256, device="cuda").to(BF); x2 = torch.randn(64, 64, 64, 64, device="cuda").to(BF)
+    w = torch.randn(4, 4, 128, 320, device="cuda") * 0.02; b = torch.zeros(128, device="cuda")
+    f = lambda: ops.conv2d_transpose_s2(x1, w, b, act=ops._lib.ACT_RELU, x2=x2)
+elif case == "headd":
+    x1 = torch.randn(64, 128, 128, 128, device="cuda").to(BF); x2 = torch.randn(64, 128, 128, 32, device="cuda").to(BF)
+    w = torch.randn(4, 4, 3, 160, device="cuda") * 0.02
+    dz = torch.zeros(64, 256, 256, 16, device="cuda", dtype=BF); dz[..., :3] = torch.randn(64, 256, 256, 3, device="cuda").to(BF)
+    f = lambda: ops.conv2d_transpose_s2_grads(x1, w, dz, x2=x2, wgrad_impl=ops._lib.IMPL_TCGEN05)
+else:
+    C = int(case[1:]); k = 3 if case[0] == 's' else 1
+    x = torch.randn(64, 256, 256, C, device="cuda").to(BF); w = torch.randn(k, k, C, 32, device="cuda") * 0.05; b = torch.zeros(32, device="cuda")
+    f = lambda: ops.conv2d(x, w, b, act=ops.ACT_ELU)
 for _ in range(2): f()
 tr = torch.zeros(3 * 64 * 8, dtype=torch.int64, device="cuda")
 fn = L.tbi_debug_set_halo_trace; fn.restype = ctypes.c_int; fn.argtypes = [ctypes.c_void_p]

@@ -163,6 +163,45 @@ __global__ void colsum_kernel(long long npix, tbi_view x, float* out, int pix_pe
     }
 }
 
+// vectorised column sum: a thread owns V consecutive channels and strides over pixels
+template <typename T, int V>
+__global__ void colsum_vec_kernel(long long npix, tbi_view x, float* out, int pix_per_block) {
+    extern __shared__ float sm[];                            // [pl][cl*V]
+    const int cv = x.c / V;
+    const int cl = min(cv, (int)blockDim.x), pl = blockDim.x / cl;
+    const int lane_c = threadIdx.x % cl, lane_p = threadIdx.x / cl;
+    const long long pbeg = (long long)blockIdx.x * pix_per_block;
+    const long long pend = min(npix, pbeg + pix_per_block);
+    for (int cv0 = 0; cv0 < cv; cv0 += cl) {
+        const int ch = (cv0 + lane_c) * V;
+        float s[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) s[k] = 0.f;
+        if (ch < x.c && lane_p < pl) {
+            const T* base = (const T*)x.ptr + x.coff + ch;
+#pragma unroll 4
+            for (long long p = pbeg + lane_p; p < pend; p += pl) {
+                float a[V];
+                ld_pack<T, V>(base + (size_t)p * x.cstride, a);
+#pragma unroll
+                for (int k = 0; k < V; ++k) s[k] += a[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) sm[(size_t)threadIdx.x * V + k] = s[k];
+        __syncthreads();
+        if (lane_p == 0 && ch < x.c) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                float tot = 0.f;
+                for (int q = 0; q < pl; ++q) tot += sm[(size_t)(q * cl + lane_c) * V + k];
+                atomicAdd(out + ch + k, tot);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // split attention
 // ---------------------------------------------------------------------------------------------
@@ -246,7 +285,8 @@ __global__ void splitatt_fc_kernel(tbi_splitatt p) {
     for (int j = threadIdx.x; j < c2; j += blockDim.x) {
         float q = p.b1[k * c2 + j];
         const float* w1 = p.w1 + (size_t)k * c * c2 + j;
-        for (int ch = 0; ch < c; ++ch) q = fmaf(g[ch], w1[(size_t)ch * c2], q);
+#pragma unroll 8
+        for (int ch = 0; ch < c; ++ch) q = fmaf(g[ch], __ldg(w1 + (size_t)ch * c2), q);
         const float sc = p.gamma[k * c2 + j] * rsqrtf(p.var[k * c2 + j] + p.bn_eps);
         q = (q - p.mean[k * c2 + j]) * sc + p.beta[k * c2 + j];
         q = act_apply(p.act, q);
@@ -261,7 +301,8 @@ __global__ void splitatt_fc_kernel(tbi_splitatt p) {
         float lmax = -INFINITY;
         for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
             float z = b2[ch];
-            for (int j = 0; j < c2; ++j) z = fmaf(h1[j], w2[(size_t)j * c + ch], z);
+#pragma unroll 8
+            for (int j = 0; j < c2; ++j) z = fmaf(h1[j], __ldg(w2 + (size_t)j * c + ch), z);
             att[r * c + ch] = z;
             lmax = fmaxf(lmax, z);
         }
@@ -356,16 +397,24 @@ __global__ void splitatt_fc_bwd_kernel(tbi_splitatt p, float* scratch) {
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < c2; j += blockDim.x) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int j = wid; j < c2; j += nwarp) {                  // a warp per output: lanes stride the contiguous channel axis
         float s = 0.f;
         for (int r = 0; r < R; ++r) {
             const float* w2 = p.w2 + (((size_t)k * R + r) * c2 + j) * c;
-            for (int ch = 0; ch < c; ++ch) s = fmaf(dz[r * c + ch], w2[ch], s);
+            for (int ch = lane; ch < c; ch += 32) s = fmaf(dz[r * c + ch], __ldg(w2 + ch), s);
         }
+        s = warp_sum(s);
+        if (lane == 0) dq[j] = s;                            // parked in dq, consumed just below
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < c2; j += blockDim.x) {
+        const float s = dq[j];
         // recompute pre-BN q for xhat
         float q = p.b1[k * c2 + j];
         const float* w1 = p.w1 + (size_t)k * c * c2 + j;
-        for (int ch = 0; ch < c; ++ch) q = fmaf(g[ch], w1[(size_t)ch * c2], q);
+#pragma unroll 8
+        for (int ch = 0; ch < c; ++ch) q = fmaf(g[ch], __ldg(w1 + (size_t)ch * c2), q);
         const float istd = rsqrtf(p.var[k * c2 + j] + p.bn_eps);
         const float xh = (q - p.mean[k * c2 + j]) * istd;
         const float d = s * act_grad_from_out(p.act, h1[j]);
@@ -374,11 +423,12 @@ __global__ void splitatt_fc_bwd_kernel(tbi_splitatt p, float* scratch) {
         dq[j] = d * p.gamma[k * c2 + j] * istd;
     }
     __syncthreads();
-    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    for (int ch = wid; ch < c; ch += nwarp) {
         float s = 0.f;
         const float* w1 = p.w1 + ((size_t)k * c + ch) * c2;
-        for (int j = 0; j < c2; ++j) s = fmaf(dq[j], w1[j], s);
-        dgap[ch] = s;
+        for (int j = lane; j < c2; j += 32) s = fmaf(dq[j], __ldg(w1 + j), s);
+        s = warp_sum(s);
+        if (lane == 0) dgap[ch] = s;
     }
 }
 
@@ -682,6 +732,12 @@ extern "C" int tbi_colsum(int dtype, int64_t npix, const tbi_view* x, float* out
     if (blocks < 1) blocks = 1;
     const int ppb = (int)((npix + blocks - 1) / blocks);
     blocks = (npix + ppb - 1) / ppb;
+    if (pick_vec(dtype, {x}) > 1) {
+        if (dtype == TBI_F32) colsum_vec_kernel<float, 4><<<(unsigned)blocks, 256, 256 * 4 * sizeof(float), s>>>(npix, *x, out, ppb);
+        else colsum_vec_kernel<__nv_bfloat16, 8><<<(unsigned)blocks, 256, 256 * 8 * sizeof(float), s>>>(npix, *x, out, ppb);
+        TBI_CUDA_LAUNCH_CHECK("colsum_vec");
+        return TBI_OK;
+    }
     if (dtype == TBI_F32) colsum_kernel<float><<<(unsigned)blocks, 256, 256 * sizeof(float), s>>>(npix, *x, out, ppb);
     else if (dtype == TBI_BF16) colsum_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 256 * sizeof(float), s>>>(npix, *x, out, ppb);
     else return tbi_set_error(TBI_ERR_UNSUPPORTED, "colsum dtype");
@@ -752,7 +808,7 @@ extern "C" int tbi_split_attention_fwd(const tbi_splitatt* p, const tbi_view* u,
     int rc = tbi_splitatt_gap(p, u, stream); if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = sizeof(float) * (p->c + p->c / 2 + 32);
-    splitatt_fc_kernel<<<dim3(p->n, p->kpaths), 128, smem, s>>>(*p);
+    splitatt_fc_kernel<<<dim3(p->n, p->kpaths), 256, smem, s>>>(*p);
     TBI_CUDA_LAUNCH_CHECK("splitatt_fc");
     return tbi_splitatt_combine(p, u, v, stream);
 }
@@ -765,7 +821,7 @@ extern "C" int tbi_split_attention_bwd(const tbi_splitatt* p, const tbi_view* u,
     cudaStream_t s = (cudaStream_t)stream;
     rc = splitatt_reduce_launch<true>(p, u, dv, scratch, s); if (rc) return rc;
     const int c = p->c, c2 = p->c / 2, K = p->kpaths, R = p->radix, N = p->n;
-    splitatt_fc_bwd_kernel<<<dim3(N, K), 128, sizeof(float) * (2 * c2 + 32), s>>>(*p, scratch);
+    splitatt_fc_bwd_kernel<<<dim3(N, K), 256, sizeof(float) * (2 * c2 + 32), s>>>(*p, scratch);
     TBI_CUDA_LAUNCH_CHECK("splitatt_fc_bwd");
     const long long maxel = (long long)K * R * c2 * c;
     splitatt_param_grad_kernel<<<dim3((unsigned)((maxel + 127) / 128), 4), 128, 0, s>>>(*p, scratch, dw1, db1, dgamma, dbeta, dw2, db2);

@@ -58,18 +58,17 @@ __global__ void __launch_bounds__(256) smallcin_fwd_kernel(const __grid_constant
     }
 }
 
-// blockIdx.y = tap; each thread accumulates acc[cin][COUT] over its pixels
-template <typename T, int COUT, int CIN>
+// one pass over dz: a thread accumulates all NT taps x COUT outputs for its pixels (CIN = 1), then warp shuffles,
+// a block reduction in shared memory and one atomic per (block, element)
+template <typename T, int COUT, int NT>
 __global__ void __launch_bounds__(256) smallcin_wgrad_kernel(const __grid_constant__ tbi_tapwgrad d) {
-    __shared__ float red[8][CIN * COUT + COUT];
-    const int tap = blockIdx.y;
-    const bool do_bias = d.dbias != nullptr && tap == 0;
-    float acc[CIN][COUT];
+    __shared__ float red[8][NT * COUT + COUT];
+    float acc[NT][COUT];
     float bacc[COUT];
 #pragma unroll
-    for (int i = 0; i < CIN; ++i)
+    for (int t = 0; t < NT; ++t)
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[i][c] = 0.f;
+        for (int c = 0; c < COUT; ++c) acc[t][c] = 0.f;
 #pragma unroll
     for (int c = 0; c < COUT; ++c) bacc[c] = 0.f;
     const long long M = (long long)d.n * d.gh * d.gw;
@@ -79,9 +78,6 @@ __global__ void __launch_bounds__(256) smallcin_wgrad_kernel(const __grid_consta
     const bool vec = d.b_src.cstride % V == 0 && d.b_src.coff % V == 0 && (((uintptr_t)d.b_src.ptr) & 15) == 0;
     for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < M; p += (long long)gridDim.x * blockDim.x) {
         const int gx = (int)(p % d.gw); long long t = p / d.gw; const int gy = (int)(t % d.gh); const int n = (int)(t / d.gh);
-        const int ay = gy + d.a_dy[tap], ax = gx + d.a_dx[tap];
-        const bool a_ok = ay >= 0 && ay < d.a_src[0].h && ax >= 0 && ax < d.a_src[0].w;
-        if (!a_ok && !do_bias) continue;
         float g[COUT];
         const T* bp = b + view_off(d.b_src, n, gy, gx, 0);
         if (vec) {
@@ -95,37 +91,34 @@ __global__ void __launch_bounds__(256) smallcin_wgrad_kernel(const __grid_consta
 #pragma unroll
             for (int c = 0; c < COUT; ++c) g[c] = ldf(bp + c);
         }
-        if (do_bias) {
 #pragma unroll
-            for (int c = 0; c < COUT; ++c) bacc[c] += g[c];
-        }
-        if (a_ok) {
-            const T* ap = a + view_off(d.a_src[0], n, ay, ax, 0);
+        for (int c = 0; c < COUT; ++c) bacc[c] += g[c];
 #pragma unroll
-            for (int i = 0; i < CIN; ++i) {
-                const float x = ldf(ap + i);
+        for (int tp = 0; tp < NT; ++tp) {
+            const int ay = gy + d.a_dy[tp], ax = gx + d.a_dx[tp];
+            float x = 0.f;
+            if (ay >= 0 && ay < d.a_src[0].h && ax >= 0 && ax < d.a_src[0].w) x = ldf(a + view_off(d.a_src[0], n, ay, ax, 0));
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[i][c] = fmaf(x, g[c], acc[i][c]);
-            }
+            for (int c = 0; c < COUT; ++c) acc[tp][c] = fmaf(x, g[c], acc[tp][c]);
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < CIN; ++i)
+    for (int tp = 0; tp < NT; ++tp)
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) { const float v = warp_sum(acc[i][c]); if (lane == 0) red[warp][i * COUT + c] = v; }
+        for (int c = 0; c < COUT; ++c) { const float v = warp_sum(acc[tp][c]); if (lane == 0) red[warp][tp * COUT + c] = v; }
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) { const float v = warp_sum(bacc[c]); if (lane == 0) red[warp][CIN * COUT + c] = v; }
+    for (int c = 0; c < COUT; ++c) { const float v = warp_sum(bacc[c]); if (lane == 0) red[warp][NT * COUT + c] = v; }
     __syncthreads();
-    for (int i = threadIdx.x; i < CIN * COUT + COUT; i += blockDim.x) {
+    for (int i = threadIdx.x; i < NT * COUT + COUT; i += blockDim.x) {
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += red[w][i];
-        if (i < CIN * COUT) {
-            const int ci = i / COUT, co = i % COUT;
-            atomicAdd(d.dw + (size_t)tap * d.tap_stride + (size_t)ci * d.ci_stride + (size_t)co * d.co_stride, v);
-        } else if (do_bias) {
-            atomicAdd(d.dbias + (i - CIN * COUT), v);
+        if (i < NT * COUT) {
+            const int tp = i / COUT, co = i % COUT;
+            atomicAdd(d.dw + (size_t)tp * d.tap_stride + (size_t)co * d.co_stride, v);
+        } else if (d.dbias) {
+            atomicAdd(d.dbias + (i - NT * COUT), v);
         }
     }
 }
@@ -151,7 +144,7 @@ int tbi_tapgemm_direct(const tbi_tapgemm* d, cudaStream_t s) {
 
 bool tbi_tapwgrad_direct_supported(const tbi_tapwgrad* d) {
     if (!(d->groups == 1 && d->a_src[1].ptr == nullptr && d->a_stride == 1 && d->b_stride == 1 && d->cout_g == 16 && d->cin_g == 1 &&
-          d->a_src[0].c == 1 && d->b_src.c == 16 && d->ntaps <= 9 && (d->dtype == TBI_F32 || d->dtype == TBI_BF16))) return false;
+          d->a_src[0].c == 1 && d->b_src.c == 16 && d->ntaps == 9 && (d->dtype == TBI_F32 || d->dtype == TBI_BF16))) return false;
     for (int t = 0; t < d->ntaps; ++t) if (d->b_dy[t] != 0 || d->b_dx[t] != 0) return false;
     return true;
 }
@@ -163,9 +156,8 @@ int tbi_tapwgrad_direct(const tbi_tapwgrad* d, cudaStream_t s) {
     const long long cap = (long long)tbi_sm_count() * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    dim3 grid((unsigned)blocks, (unsigned)d->ntaps);
-    if (d->dtype == TBI_F32) smallcin_wgrad_kernel<float, 16, 1><<<grid, 256, 0, s>>>(*d);
-    else smallcin_wgrad_kernel<__nv_bfloat16, 16, 1><<<grid, 256, 0, s>>>(*d);
+    if (d->dtype == TBI_F32) smallcin_wgrad_kernel<float, 16, 9><<<(unsigned)blocks, 256, 0, s>>>(*d);
+    else smallcin_wgrad_kernel<__nv_bfloat16, 16, 9><<<(unsigned)blocks, 256, 0, s>>>(*d);
     TBI_CUDA_LAUNCH_CHECK("smallcin_wgrad");
     return TBI_OK;
 }

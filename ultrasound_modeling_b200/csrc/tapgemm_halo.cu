@@ -124,12 +124,15 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
                 tc::tmem_ld32(taddr + c, r);
                 tc::tmem_ld_wait();
                 if (c + 32 >= HALF) {                                     // last read of this buffer: hand it back to the MMA warp
+                    trace(tr, 2, acc_it, 2);
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
+                    trace(tr, 2, acc_it, 3);
                 }
                 if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + half * HALF + c, p.cout_g, t.cg * p.cout_g);
             }
+            trace(tr, 2, acc_it, 4);
         } else if constexpr (BN == 32) {
             uint32_t r[16];
             tc::tmem_ld16(taddr, r);
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
     if (warp == W_TMA) {
         // ===================== TMA producer: the whole warp walks the loop, one elected lane issues =====================
         const bool leader = tc::elect_one();
-        uint32_t a_it = 0, b_it = 0;
+        uint32_t a_it = 0, sa = 0, a_par = 1, sb = 0, b_par = 1;       // ring stage + parity (empty barriers start "free")
         TileCoord slab_t{};
         if (p.resident) slab_t = decode_tile(p, R.slab, BN);
         if (p.resident && R.it_first < R.it_count && leader) {            // the whole weight slab, once
@@ -229,9 +232,8 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
                 if (p.cgroups == 1 && cch >= p.c0) { src = 1; cch -= p.c0; }
                 int tap = 0;
                 for (int grp = 0; grp < p.ngroups; ++grp) {
-                    const uint32_t sa = a_it % p.a_stages;
                     trace(g_halo_trace, 0, a_it, 0);
-                    tc::mbar_wait_bounded(&R.a_empty[sa], ((a_it / p.a_stages) & 1u) ^ 1u);
+                    tc::mbar_wait_bounded(&R.a_empty[sa], a_par);
                     trace(g_halo_trace, 0, a_it, 1);
                     if (leader) {
                         tc::mbar_expect_tx(&R.a_full[sa], p.a_tx);
@@ -239,16 +241,17 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
                                         p.a_cbase[src] + cch + p.g_ax[grp] * p.a_cpix[src], t.x0 + p.g_ox[grp], p.g_ay[grp], t.y0 + p.g_oy[grp], t.n0);
                     }
                     ++a_it;
+                    if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
                     if (p.resident) continue;
                     while (tap < p.ntaps && p.t_grp[t.ph][tap] == grp) {
-                        const uint32_t sb = b_it % p.b_stages;
-                        tc::mbar_wait_bounded(&R.b_empty[sb], ((b_it / p.b_stages) & 1u) ^ 1u);
+                        tc::mbar_wait_bounded(&R.b_empty[sb], b_par);
                         if (leader) {
                             tc::mbar_expect_tx(&R.b_full[sb], p.b_tx);
                             tc::tma_load_2d(R.b_ring + (size_t)sb * p.b_stage_bytes, &p.b, &R.b_full[sb], (int)p.t_kidx[t.ph][tap] * p.cin_g + ch,
                                             t.ph * p.cout_total + t.cg * p.cout_g + t.nc0);
                         }
-                        ++b_it; ++tap;
+                        if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+                        ++tap;
                     }
                 }
             }
@@ -325,53 +328,52 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
                 if (leader) tc::umma_commit(&R.t_full[buf]);
                 trace(g_halo_trace, 1, acc_it, 3);
             }
-        } else
-        for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
-            const int ph = (p.nphase > 1 ? decode_tile(p, i, BN).ph : 0);
-            if (ph != cur_ph) load_taps(ph);
-            const uint32_t buf = acc_it & 1u;
-            trace(g_halo_trace, 1, acc_it, 0);
-            tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);        // epilogue has drained this accumulator
-            tc::tc_fence_after();
-            trace(g_halo_trace, 1, acc_it, 1);
-            const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
-            uint32_t accum = 0;
-            for (int c = 0; c < p.nchunks; ++c) {
-                uint32_t sa = 0, a_lo = 0;
-                uint32_t b_res_lo = b_lo0 + b_ring_lo + (uint32_t)(c * p.ntaps) * b_stage_lo;
-                unsigned long long cur = tw0;
+        } else {
+            // ---- weights streamed: one B stage per (chunk, tap); wrap-around stage counters, nothing but waits + MMAs ----
+            uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
+            const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
+            for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+                const int ph = (p.nphase > 1 ? decode_tile(p, i, BN).ph : 0);
+                if (ph != cur_ph) load_taps(ph);
+                const uint32_t buf = acc_it & 1u;
+                trace(g_halo_trace, 1, acc_it, 0);
+                tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+                tc::tc_fence_after();
+                trace(g_halo_trace, 1, acc_it, 1);
+                const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+                uint32_t accum = 0, a_lo = 0;
 #pragma unroll 1
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    if (tap == 5) cur = tw1; else if (tap == 10) cur = tw2; else if (tap == 15) cur = tw3;
-                    const uint32_t e = (uint32_t)cur & 0xFFFu;
-                    cur >>= 12;
-                    if (e & 0x400u) {
-                        sa = a_it % p.a_stages;
-                        tc::mbar_wait_bounded(&R.a_full[sa], (a_it / p.a_stages) & 1u);
+                for (int c = 0; c < p.nchunks; ++c) {
+                    unsigned long long cur = tw0;
+#pragma unroll 1
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        if (tap == 5) cur = tw1; else if (tap == 10) cur = tw2; else if (tap == 15) cur = tw3;
+                        const uint32_t e = (uint32_t)cur & 0xFFFu;
+                        cur >>= 12;
+                        if (e & 0x400u) {
+                            tc::mbar_wait_bounded(&R.a_full[sa], a_par);
+                            trace(g_halo_trace, 1, acc_it, 2);
+                            a_lo = a_base + sa * a_stage_lo;
+                        }
+                        tc::mbar_wait_bounded(&R.b_full[sb], b_par);
                         tc::tc_fence_after();
-                        trace(g_halo_trace, 1, acc_it, 2);
-                        a_lo = a_lo0 + a_ring_lo + sa * a_stage_lo;
+                        const uint32_t al = a_lo + (e & 0x3FFu) * row_lo, bl = b_base + sb * b_stage_lo;
+                        if (leader) {
+#pragma unroll 1
+                            for (int k = 0; k < ksteps; ++k) { tc::umma_bf16_lh(tmem_d, al + 2 * k, a_hi, bl + 2 * k, b_hi, idesc, accum); accum = 1; }
+                            tc::umma_commit(&R.b_empty[sb]);
+                        }
+                        accum = 1;
+                        if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+                        if (e & 0x800u) {
+                            if (leader) tc::umma_commit(&R.a_empty[sa]);
+                            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+                        }
                     }
-                    uint32_t sb = 0, b_lo;
-                    if (p.resident) {
-                        b_lo = b_res_lo; b_res_lo += b_stage_lo;
-                    } else {
-                        sb = b_it % p.b_stages;
-                        tc::mbar_wait_bounded(&R.b_full[sb], (b_it / p.b_stages) & 1u);
-                        tc::tc_fence_after();
-                        b_lo = b_lo0 + b_ring_lo + sb * b_stage_lo;
-                    }
-                    const uint32_t al = a_lo + (e & 0x3FFu) * row_lo;
-                    if (leader) {
-                        for (int k = 0; k < ksteps; ++k) { tc::umma_bf16_lh(tmem_d, al + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc, accum); accum = 1; }
-                    }
-                    accum = 1;
-                    if (!p.resident) { if (leader) tc::umma_commit(&R.b_empty[sb]); ++b_it; }
-                    if (e & 0x800u) { if (leader) tc::umma_commit(&R.a_empty[sa]); ++a_it; }
                 }
+                if (leader) tc::umma_commit(&R.t_full[buf]);
+                trace(g_halo_trace, 1, acc_it, 3);
             }
-            if (leader) tc::umma_commit(&R.t_full[buf]);
-            trace(g_halo_trace, 1, acc_it, 3);
         }
         __syncwarp();
     } else {
@@ -516,9 +518,10 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     p.total_tiles = p.m_tiles * p.cgroups * p.nphase * p.n_tiles;
     p.a_tx = bw * bh * kc * 2; p.b_tx = bn * kc * 2;
     p.a_stage_bytes = (int)r1024((uint32_t)p.a_tx); p.b_stage_bytes = (int)r1024((uint32_t)p.b_tx);
-    // ~104 KB per CTA so that two CTAs share an SM
-    const int budget = 104 * 1024;
-    const int max_ctas = 2 * tbi_sm_count();
+    // ~104 KB per CTA so that two CTAs share an SM (TBI_HALO_BUDGET_KB > 113 -> one CTA per SM with deeper rings)
+    static const int budget_kb = getenv("TBI_HALO_BUDGET_KB") ? atoi(getenv("TBI_HALO_BUDGET_KB")) : 104;
+    const int budget = budget_kb * 1024;
+    const int max_ctas = (budget_kb > 113 ? 1 : 2) * tbi_sm_count();
     p.nslabs = p.n_tiles * p.cgroups * p.nphase;
     const long long slab_bytes = (long long)p.nchunks * d->ntaps * p.b_stage_bytes;
     static const bool no_resident = getenv("TBI_TC_NO_RESIDENT") != nullptr;
@@ -539,8 +542,8 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         if (per_slab < 1) per_slab = 1;
         grid = per_slab * p.nslabs;
     } else {
+        // a halo stage feeds ntaps/ngroups weight tiles: two halo stages are enough, the weight ring gets the rest
         p.a_stages = 2;
-        if (3 * p.a_stage_bytes + 4 * p.b_stage_bytes <= budget) p.a_stages = 3;
         int bs = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
         if (bs > 8) bs = 8;
         if (bs < 2) bs = 2;
