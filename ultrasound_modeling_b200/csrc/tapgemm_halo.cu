@@ -44,6 +44,7 @@ struct alignas(64) HaloParams {
     int narrow;
     int resident, nslabs;          // weights-resident mode: a CTA keeps one (N tile, group, phase) weight slab in smem
     int sh_x, sh_y;                // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1 (divide)
+    int rank4;                     // stride-1 sources: 4-D tensor map (C, W, H, N) instead of the 5-D parity view
     tbi_epilogue epi;
 };
 
@@ -93,10 +94,12 @@ struct Rings {
 
 template <int BN, int ACT, int DACT>
 __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, uint32_t tmem_base, int warp, int lane) {
+    // Two groups of four warps (one warp per TMEM lane quadrant).  Group g owns accumulator buffer g, i.e. every
+    // second tile, so the epilogues of consecutive tiles overlap (the per-tile chain wait -> tcgen05.ld -> loads ->
+    // math -> stores is latency-bound for small K).
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
-    constexpr int HALF = BN >= 32 ? BN / 2 : BN;            // columns per epilogue warp (BN = 16: one warp per quadrant works, the other idles)
     const int q = warp & 3;
-    const int half = warp >> 2;                             // 0 or 1
+    const int grp = warp >> 2;                              // 0 or 1 == accumulator buffer
     const int m = q * 32 + lane;
     const int xx = m & (TW - 1), yy = m >> 3;
     uint32_t acc_it = 0;
@@ -104,9 +107,10 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     if (p.resident) slab_t = decode_tile(p, R.slab, BN);
     unsigned long long* tr = (warp == 0 && lane == 0) ? g_halo_trace : nullptr;
     for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+        if ((int)(acc_it & 1u) != grp) continue;
+        const uint32_t buf = (uint32_t)grp;
         const TileCoord t = decode_tile_warp(p, i, BN, lane, slab_t, i);
         trace(tr, 2, acc_it, 0);
-        const uint32_t buf = acc_it & 1u;
         const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
         const bool valid = gx < p.gw && gy < p.gh;
         const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
@@ -116,41 +120,24 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
         tc::mbar_wait_bounded<true>(&R.t_full[buf], (acc_it >> 1) & 1u);
         tc::tc_fence_after();
         trace(tr, 2, acc_it, 1);
-        const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16) + half * HALF;
-        if constexpr (BN >= 64) {
+        const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+        if constexpr (BN >= 32) {
 #pragma unroll 1
-            for (int c = 0; c < HALF; c += 32) {
+            for (int c = 0; c < BN; c += 32) {
                 uint32_t r[32];
                 tc::tmem_ld32(taddr + c, r);
                 tc::tmem_ld_wait();
-                if (c + 32 >= HALF) {                                     // last read of this buffer: hand it back to the MMA warp
+                if (c + 32 >= BN) {                                       // last read of this buffer: hand it back to the MMA warp
                     trace(tr, 2, acc_it, 2);
                     tc::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
                     trace(tr, 2, acc_it, 3);
                 }
-                if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + half * HALF + c, p.cout_g, t.cg * p.cout_g);
+                if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + c, p.cout_g, t.cg * p.cout_g);
             }
-            trace(tr, 2, acc_it, 4);
-        } else if constexpr (BN == 32) {
-            uint32_t r[16];
-            tc::tmem_ld16(taddr, r);
-            tc::tmem_ld_wait();
-            trace(tr, 2, acc_it, 2);
-            tc::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
-            trace(tr, 2, acc_it, 3);
-            if (valid) epilogue_cols<ACT, DACT, 16>(rc, r, t.nc0 + half * HALF, p.cout_g, t.cg * p.cout_g);
             trace(tr, 2, acc_it, 4);
         } else {
-            if (half == 1) {                                              // BN = 16: nothing left for the second warp of the quadrant
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
-                continue;
-            }
             uint32_t r[16];
             tc::tmem_ld16(taddr, r);
             tc::tmem_ld_wait();
@@ -200,7 +187,7 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
         if (p.c0 < p.cin_g * p.cgroups) tc::prefetch_tmap(&p.a[1]);
         for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&R.a_full[s], 1); tc::mbar_init(&R.a_empty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&R.b_full[s], 1); tc::mbar_init(&R.b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&R.t_full[s], 1); tc::mbar_init(&R.t_empty[s], HT_EPI_WARPS); }
+        for (int s = 0; s < 2; ++s) { tc::mbar_init(&R.t_full[s], 1); tc::mbar_init(&R.t_empty[s], 4); }
         tc::mbar_init(R.b_res, 1);
         tc::fence_barrier_init();
     }
@@ -237,8 +224,11 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
                     trace(g_halo_trace, 0, a_it, 1);
                     if (leader) {
                         tc::mbar_expect_tx(&R.a_full[sa], p.a_tx);
-                        tc::tma_load_5d(R.a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], &R.a_full[sa],
-                                        p.a_cbase[src] + cch + p.g_ax[grp] * p.a_cpix[src], t.x0 + p.g_ox[grp], p.g_ay[grp], t.y0 + p.g_oy[grp], t.n0);
+                        if (p.rank4)
+                            tc::tma_load_4d(R.a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], &R.a_full[sa], cch, t.x0 + p.g_ox[grp], t.y0 + p.g_oy[grp], t.n0);
+                        else
+                            tc::tma_load_5d(R.a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], &R.a_full[sa],
+                                            p.a_cbase[src] + cch + p.g_ax[grp] * p.a_cpix[src], t.x0 + p.g_ox[grp], p.g_ay[grp], t.y0 + p.g_oy[grp], t.n0);
                     }
                     ++a_it;
                     if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
@@ -388,7 +378,15 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
 inline uint32_t r1024(uint32_t x) { return (x + 1023u) & ~1023u; }
 
 // 5-D activation map with a halo box [kc x (TW+ex) x 1 x (TH+ey) x 1]
-int halo_act_tmap(CUtensorMap* out, const tbi_view& v, int n, int stride, int kc, int bw, int bh, int* cbase, int* cpix) {
+int halo_act_tmap(CUtensorMap* out, const tbi_view& v, int n, int stride, int kc, int bw, int bh, int* cbase, int* cpix, bool rank4) {
+    if (rank4 && stride == 1) {
+        const uint64_t px4 = (uint64_t)v.cstride * 2;
+        uint64_t d4[4] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)n};
+        uint64_t s4[3] = {px4, px4 * v.w, px4 * v.w * v.h};
+        uint32_t b4[4] = {(uint32_t)kc, (uint32_t)bw, (uint32_t)bh, 1u};
+        *cbase = 0; *cpix = 0;
+        return tbi_make_tmap_bf16(out, (char*)v.ptr + (size_t)v.coff * 2, 4, d4, s4, b4, kc * 2);
+    }
     uint64_t dims[5], strides[4];
     uint32_t box[5] = {(uint32_t)kc, (uint32_t)bw, 1u, (uint32_t)bh, 1u};
     const uint64_t px = (uint64_t)v.cstride * 2;
@@ -501,8 +499,10 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         }
     }
     const int bw = TW + tp.ex, bh = TH + tp.ey;
-    int rc = halo_act_tmap(&p.a[0], d->src[0], d->n, d->in_stride, kc, bw, bh, &p.a_cbase[0], &p.a_cpix[0]); if (rc) return rc;
-    if (d->groups == 1 && d->src[1].ptr) { rc = halo_act_tmap(&p.a[1], d->src[1], d->n, d->in_stride, kc, bw, bh, &p.a_cbase[1], &p.a_cpix[1]); if (rc) return rc; }
+    static const bool no_rank4 = getenv("TBI_TC_NO_RANK4") != nullptr;
+    p.rank4 = (d->in_stride == 1 && !no_rank4) ? 1 : 0;
+    int rc = halo_act_tmap(&p.a[0], d->src[0], d->n, d->in_stride, kc, bw, bh, &p.a_cbase[0], &p.a_cpix[0], p.rank4); if (rc) return rc;
+    if (d->groups == 1 && d->src[1].ptr) { rc = halo_act_tmap(&p.a[1], d->src[1], d->n, d->in_stride, kc, bw, bh, &p.a_cbase[1], &p.a_cpix[1], p.rank4); if (rc) return rc; }
     else p.a[1] = p.a[0];
     int bn = 128;
     while (bn > 16 && bn / 2 >= d->cout_g) bn >>= 1;

@@ -43,7 +43,7 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
     for (;;) {
 #pragma unroll 1
         for (int i = 0; i < 4096; ++i) {
-            if (RELAXED) __nanosleep(64);          // epilogue warps: leave the issue slots to the TMA / MMA warps
+            if (RELAXED) __nanosleep(20);          // epilogue warps: leave the issue slots to the TMA / MMA warps
             if (mbar_try_wait(bar, parity)) return;
         }
         if (clock64() - t0 > 6000000000LL) { printf("tbi tcgen05: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
@@ -69,6 +69,12 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
     asm volatile(
         "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
         ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
