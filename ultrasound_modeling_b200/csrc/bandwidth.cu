@@ -223,6 +223,7 @@ __global__ void splitatt_reduce_kernel(int hw, int R, int c, tbi_view u, tbi_vie
         for (int k = 0; k < V; ++k) s[k] = 0.f;
         if (ch < C && lane_p < pl) {
             const int kk = ch / (R * c), cc = ch % c;        // cardinal index, channel within cvkk
+#pragma unroll 4
             for (int p = pbeg + lane_p; p < pend; p += pl) {
                 float a[V];
                 ld_pack<T, V>(ub + (size_t)p * u.cstride + ch, a);
@@ -265,13 +266,23 @@ __device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) 
 }
 
 // one block per (n,k): gap -> dense1 -> BN -> act -> dense2 x R -> softmax_c / sigmoid
+// STAGE: the cardinal's FC weights are first copied to shared memory with one coalesced cooperative load, so the
+// dependent dot products below never wait on global memory
+template <bool STAGE>
 __global__ void splitatt_fc_kernel(tbi_splitatt p) {
     extern __shared__ float sm[];
     const int c = p.c, c2 = p.c / 2, R = p.radix, K = p.kpaths;
     float* g = sm;                 // [c]
     float* h1 = sm + c;            // [c2]
     float* red = h1 + c2;          // [32]
+    float* sw1 = red + 32;         // [c][c2]      (STAGE)
+    float* sw2 = sw1 + c * c2;     // [R][c2][c]   (STAGE)
     const int n = blockIdx.x, k = blockIdx.y;
+    if (STAGE) {
+        const float* gw1 = p.w1 + (size_t)k * c * c2; const float* gw2 = p.w2 + (size_t)k * R * c2 * c;
+        for (int i = threadIdx.x; i < c * c2; i += blockDim.x) sw1[i] = __ldg(gw1 + i);
+        for (int i = threadIdx.x; i < R * c2 * c; i += blockDim.x) sw2[i] = __ldg(gw2 + i);
+    }
     float* att = p.att + ((size_t)n * K + k) * R * c;
     const float inv_hw = 1.f / (float)(p.h * p.w);
     for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
@@ -284,9 +295,9 @@ __global__ void splitatt_fc_kernel(tbi_splitatt p) {
     __syncthreads();
     for (int j = threadIdx.x; j < c2; j += blockDim.x) {
         float q = p.b1[k * c2 + j];
-        const float* w1 = p.w1 + (size_t)k * c * c2 + j;
+        const float* w1 = STAGE ? sw1 + j : p.w1 + (size_t)k * c * c2 + j;
 #pragma unroll 8
-        for (int ch = 0; ch < c; ++ch) q = fmaf(g[ch], __ldg(w1 + (size_t)ch * c2), q);
+        for (int ch = 0; ch < c; ++ch) q = fmaf(g[ch], w1[(size_t)ch * c2], q);
         const float sc = p.gamma[k * c2 + j] * rsqrtf(p.var[k * c2 + j] + p.bn_eps);
         q = (q - p.mean[k * c2 + j]) * sc + p.beta[k * c2 + j];
         q = act_apply(p.act, q);
@@ -295,14 +306,14 @@ __global__ void splitatt_fc_kernel(tbi_splitatt p) {
     }
     __syncthreads();
     for (int r = 0; r < R; ++r) {
-        const float* w2 = p.w2 + ((size_t)k * R + r) * c2 * c;
+        const float* w2 = STAGE ? sw2 + (size_t)r * c2 * c : p.w2 + ((size_t)k * R + r) * c2 * c;
         const float* b2 = p.b2 + ((size_t)k * R + r) * c;
         // each thread owns channels ch = tid, tid+bd, ... ; z kept in att then normalised
         float lmax = -INFINITY;
         for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
             float z = b2[ch];
 #pragma unroll 8
-            for (int j = 0; j < c2; ++j) z = fmaf(h1[j], __ldg(w2 + (size_t)j * c + ch), z);
+            for (int j = 0; j < c2; ++j) z = fmaf(h1[j], w2[(size_t)j * c + ch], z);
             att[r * c + ch] = z;
             lmax = fmaxf(lmax, z);
         }
@@ -805,10 +816,20 @@ extern "C" int tbi_splitatt_combine(const tbi_splitatt* p, const tbi_view* u, co
 }
 
 extern "C" int tbi_split_attention_fwd(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, void* stream) {
-    int rc = tbi_splitatt_gap(p, u, stream); if (rc) return rc;
+    int rc = splitatt_check(p, u, v); if (rc) return rc;
+    rc = tbi_splitatt_fwd_fused(p, u, v, (cudaStream_t)stream);          // one cooperative launch when it applies (bf16, aligned)
+    if (rc != 0) return rc < 0 ? rc : TBI_OK;
+    rc = tbi_splitatt_gap(p, u, stream); if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = sizeof(float) * (p->c + p->c / 2 + 32);
-    splitatt_fc_kernel<<<dim3(p->n, p->kpaths), 256, smem, s>>>(*p);
+    const size_t base_smem = sizeof(float) * (p->c + p->c / 2 + 32);
+    const size_t w_smem = sizeof(float) * ((size_t)p->c * (p->c / 2) * (1 + p->radix));
+    if (base_smem + w_smem <= 100 * 1024) {
+        static bool attr_done = false;
+        if (!attr_done) { cudaFuncSetAttribute(splitatt_fc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr_done = true; }
+        splitatt_fc_kernel<true><<<dim3(p->n, p->kpaths), 256, base_smem + w_smem, s>>>(*p);
+    } else {
+        splitatt_fc_kernel<false><<<dim3(p->n, p->kpaths), 256, base_smem, s>>>(*p);
+    }
     TBI_CUDA_LAUNCH_CHECK("splitatt_fc");
     return tbi_splitatt_combine(p, u, v, stream);
 }
@@ -819,11 +840,18 @@ extern "C" int tbi_split_attention_bwd(const tbi_splitatt* p, const tbi_view* u,
     int rc = splitatt_check(p, u, dv); if (rc) return rc;
     TBI_CHECK(du->c == u->c, TBI_ERR_BAD_SHAPE, "splitatt bwd: du channels");
     cudaStream_t s = (cudaStream_t)stream;
-    rc = splitatt_reduce_launch<true>(p, u, dv, scratch, s); if (rc) return rc;
     const int c = p->c, c2 = p->c / 2, K = p->kpaths, R = p->radix, N = p->n;
+    const long long maxel = (long long)K * R * c2 * c;
+    rc = tbi_splitatt_bwd_fused(p, u, dv, du, scratch, s);               // da + FC backward + dU in one cooperative launch
+    if (rc < 0) return rc;
+    if (rc == 1) {
+        splitatt_param_grad_kernel<<<dim3((unsigned)((maxel + 127) / 128), 4), 128, 0, s>>>(*p, scratch, dw1, db1, dgamma, dbeta, dw2, db2);
+        TBI_CUDA_LAUNCH_CHECK("splitatt_param_grad");
+        return TBI_OK;
+    }
+    rc = splitatt_reduce_launch<true>(p, u, dv, scratch, s); if (rc) return rc;
     splitatt_fc_bwd_kernel<<<dim3(N, K), 256, sizeof(float) * (2 * c2 + 32), s>>>(*p, scratch);
     TBI_CUDA_LAUNCH_CHECK("splitatt_fc_bwd");
-    const long long maxel = (long long)K * R * c2 * c;
     splitatt_param_grad_kernel<<<dim3((unsigned)((maxel + 127) / 128), 4), 128, 0, s>>>(*p, scratch, dw1, db1, dgamma, dbeta, dw2, db2);
     TBI_CUDA_LAUNCH_CHECK("splitatt_param_grad");
     int V = pick_vec(p->dtype, {u, dv, du});

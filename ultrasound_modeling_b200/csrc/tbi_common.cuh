@@ -88,6 +88,8 @@ bool tbi_tapwgrad_tc_supported(const tbi_tapwgrad* d, const char** why);
 int64_t tbi_tapwgrad_tc_workspace(const tbi_tapwgrad* d);
 bool tbi_tapwgrad_small_supported(const tbi_tapwgrad* d);      // few-input-channel stride-1 conv wgrad (tap-packed M, TMEM-resident)
 int tbi_tapwgrad_small(const tbi_tapwgrad* d, cudaStream_t s);
+int tbi_splitatt_fwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, cudaStream_t s);     // 1 launched, 0 not applicable
+int tbi_splitatt_bwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* dv, const tbi_view* du, float* scratch, cudaStream_t s);
 bool tbi_tapgemm_halo_supported(const tbi_tapgemm* d);          // persistent halo-addressed variant (spatial >= 16x8)
 int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s);
 int tbi_tapgemm_direct(const tbi_tapgemm* d, cudaStream_t s);   // few-input-channel direct conv (stem)
