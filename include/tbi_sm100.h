@@ -183,6 +183,11 @@ int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout, in
                            const float* w_hwoi, const float* scale, void* out, void* stream);
 /* cout_pad (mode 1 only; 0 or >= cout): the co axis of the DGRAD pack is zero-padded to cout_pad so that it
  * matches a channel-padded gradient tensor.                                                            */
+/* Gathered-gradient form of a stride-2 transposed conv's backward (used for the narrow head, f_tran):
+ *   G[n,i,j, (ky*k+kx)*cout + co] = dz[n, 2i-pad+ky, 2j-pad+kx, co]   (0 outside dz; channels >= k*k*cout untouched)
+ * after which dW_hwoi (flattened [k*k*cout][cin]) = G^T X  and  dX = G W' are plain (1-tap) tap-GEMMs.
+ * tbi_pack_convt_weights mode 2 writes W'[ci][q], q = (ky*k+kx)*cout+co, rows zero-padded to cout_pad.       */
+int tbi_convt_gather_dz(int dtype, int n, int h, int w, int ksize, int cout, const tbi_view* dz, const tbi_view* g, void* stream);
 /* taps of output-parity phase (a,b): returns count; ky/kx = kernel index, dy/dx = input offset.  */
 int tbi_convt_phase_taps(int ksize, int a, int b, int* ky, int* kx, int* dy, int* dx);
 

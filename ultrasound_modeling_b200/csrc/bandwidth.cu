@@ -121,6 +121,24 @@ __global__ void act_bwd_kernel(long long npix, int act, tbi_view dy, tbi_view yr
     }
 }
 
+// G[n,i,j,(ky*k+kx)*cout+co] = dz[n,2i-pad+ky,2j-pad+kx,co]; one thread per (pixel, tap)
+template <typename T>
+__global__ void convt_gather_kernel(int n, int h, int w, int k, int pad, int cout, tbi_view dz, tbi_view g) {
+    const long long total = (long long)n * h * w * k * k;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int tap = (int)(i % (k * k)); long long t = i / (k * k);
+        const int x = (int)(t % w); t /= w; const int y = (int)(t % h); const int b = (int)(t / h);
+        const int sy = 2 * y - pad + tap / k, sx = 2 * x - pad + tap % k;
+        T* dst = (T*)g.ptr + view_off(g, b, y, x, tap * cout);
+        if (sy >= 0 && sy < dz.h && sx >= 0 && sx < dz.w) {
+            const T* src = (const T*)dz.ptr + view_off(dz, b, sy, sx, 0);
+            for (int c = 0; c < cout; ++c) dst[c] = src[c];
+        } else {
+            for (int c = 0; c < cout; ++c) stf(dst + c, 0.f);
+        }
+    }
+}
+
 template <typename T, int V>
 __global__ void accumulate_kernel(long long npix, tbi_view src, tbi_view dst) {
     const int cv = dst.c / V;
@@ -564,9 +582,14 @@ struct ConvtTapTable { int n[4]; int off[4]; int ky[4][4]; int kx[4][4]; };
 template <typename T>
 __global__ void pack_convt_kernel(int mode, int k, int cin, int cout, int cpad, ConvtTapTable tt, const float* __restrict__ w,
                                   const float* __restrict__ scale, T* __restrict__ out) {
-    const long long total = (long long)k * k * cin * (mode == 1 ? cpad : cout);
+    const long long total = mode == 2 ? (long long)cin * cpad : (long long)k * k * cin * (mode == 1 ? cpad : cout);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int ky, kx, ci, co;
+        if (mode == 2) {            // out[ci][q], q = (ky*k+kx)*cout + co, zero-padded to cpad
+            const int q = (int)(i % cpad); ci = (int)(i / cpad);
+            if (q >= k * k * cout) { stf(out + i, 0.f); continue; }
+            co = q % cout; const int tap = q / cout; ky = tap / k; kx = tap % k;
+        } else
         if (mode == 0) {            // out[phase][co][t][ci], phase blocks at tt.off[ph]*cout*cin
             long long r = i; int ph = 0;
             while (ph < 3 && r >= (long long)tt.n[ph] * cout * cin) { r -= (long long)tt.n[ph] * cout * cin; ++ph; }
@@ -717,6 +740,20 @@ extern "C" int tbi_act_bwd(int dtype, int64_t npix, int act, const tbi_view* dy,
         (act_bwd_kernel<__nv_bfloat16, 8><<<g, 256, 0, s>>>(npix, act, *dy, *y_ref, keep, *dz)),
         (act_bwd_kernel<__nv_bfloat16, 1><<<g, 256, 0, s>>>(npix, act, *dy, *y_ref, keep, *dz)));
     TBI_CUDA_LAUNCH_CHECK("act_bwd");
+    return TBI_OK;
+}
+
+extern "C" int tbi_convt_gather_dz(int dtype, int n, int h, int w, int ksize, int cout, const tbi_view* dz, const tbi_view* g, void* stream) {
+    TBI_CHECK(ksize == 3 || ksize == 4, TBI_ERR_UNSUPPORTED, "convt_gather: ksize %d", ksize);
+    TBI_CHECK(dz->h == 2 * h && dz->w == 2 * w && dz->c >= cout && g->h == h && g->w == w && g->c >= ksize * ksize * cout, TBI_ERR_BAD_SHAPE,
+              "convt_gather: shapes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned gr = grid_for((long long)n * h * w * ksize * ksize, 256);
+    const int pad = ksize == 4 ? 1 : 0;
+    if (dtype == TBI_F32) convt_gather_kernel<float><<<gr, 256, 0, s>>>(n, h, w, ksize, pad, cout, *dz, *g);
+    else if (dtype == TBI_BF16) convt_gather_kernel<__nv_bfloat16><<<gr, 256, 0, s>>>(n, h, w, ksize, pad, cout, *dz, *g);
+    else return tbi_set_error(TBI_ERR_UNSUPPORTED, "convt_gather dtype");
+    TBI_CUDA_LAUNCH_CHECK("convt_gather");
     return TBI_OK;
 }
 
@@ -918,7 +955,8 @@ extern "C" int tbi_pack_conv_weights(int dtype, int mode, int ksize, int groups,
 extern "C" int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout, int cout_pad, const float* w_hwoi,
                                       const float* scale, void* out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    const int cpad = (mode == 1 && cout_pad > cout) ? cout_pad : cout;
+    const int cpad = ((mode == 1 && cout_pad > cout) || mode == 2) ? cout_pad : cout;
+    TBI_CHECK(mode != 2 || cout_pad >= ksize * ksize * cout, TBI_ERR_BAD_SHAPE, "pack_convt mode 2: cout_pad %d < k*k*cout", cout_pad);
     ConvtTapTable tt{};
     int off = 0;
     for (int ph = 0; ph < 4; ++ph) {
@@ -928,7 +966,7 @@ extern "C" int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, i
         tt.n[ph] = n; tt.off[ph] = off; off += n;
         for (int t = 0; t < n; ++t) { tt.ky[ph][t] = ky[t]; tt.kx[ph][t] = kx[t]; }
     }
-    const unsigned g = grid_for((long long)ksize * ksize * cin * cpad, 256);
+    const unsigned g = grid_for(mode == 2 ? (long long)cin * cpad : (long long)ksize * ksize * cin * cpad, 256);
     if (dtype == TBI_F32) pack_convt_kernel<float><<<g, 256, 0, s>>>(mode, ksize, cin, cout, cpad, tt, w_hwoi, scale, (float*)out);
     else if (dtype == TBI_BF16) pack_convt_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(mode, ksize, cin, cout, cpad, tt, w_hwoi, scale, (__nv_bfloat16*)out);
     else return tbi_set_error(TBI_ERR_UNSUPPORTED, "pack dtype");

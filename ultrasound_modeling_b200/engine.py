@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, BF16, F32, IMPL_AUTO, Epilogue, SplitAtt, TapWgrad, View, check)
+from ._lib import (ACT_ELU, ACT_NONE, ACT_RELU, BF16, F32, IMPL_AUTO, Epilogue, SplitAtt, TapGemm, TapWgrad, View, check)
 
 BN_EPS = 1e-3
 STAGES = (("conv2_1", 64), ("conv2_2", 128), ("conv3_1", 256), ("conv3_2", 512), ("conv4_1", 512))
@@ -332,6 +332,11 @@ class Engine:
         # 16-byte aligned for TMA; the loss kernel writes the real channels only, the padding stays zero
         self.dl_c = 16 if self.dt == BF16 else self.num_class
         self.dlogits = torch.zeros(n, H, W, self.dl_c, dtype=td, device=dev)
+        # bf16: the head's backward runs on the GATHERED gradient G[n,H/2,W/2, 16 taps x num_class (padded to 64 channels)]
+        self.head_gather = self.dt == BF16 and 16 * self.num_class <= 64
+        if self.head_gather:
+            self.head_g = torch.zeros(n, H // 2, W // 2, 64, dtype=td, device=dev)
+            self.head_wg = torch.empty(self.head.cin * 64, dtype=td, device=dev)
         self.loss_map = torch.empty(H, W, dtype=torch.float32, device=dev)
         self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
         # packed compute weights + folded BN
@@ -403,6 +408,8 @@ class Engine:
                 cpad = self.dl_c if Lr is self.head else 0
                 self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 0, Lr.k, Lr.cin, Lr.cout, 0, wp, sc, _ptr(pk["wf"]))))
                 self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 1, Lr.k, Lr.cin, Lr.cout, cpad, wp, sc, _ptr(pk["wb"]))))
+                if Lr is self.head and self.head_gather:
+                    self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 2, Lr.k, Lr.cin, Lr.cout, 64, wp, sc, _ptr(self.head_wg))))
 
         for Lr in self.convs.values():
             prepare(Lr)
@@ -485,8 +492,28 @@ class Engine:
                                                             _ptr(self.loss_map), _ptr(self.correct), _ptr(self.dlogits), self.dl_c)))
         # ---------------- backward ----------------
         # head: d(up4) gets ReLU' of up4 (no dropout on upsample_4); d(pool[0]) plain write
-        conv_bwd(self.head, H // 2, W // 2, view(self.up[4]), view(self.pool[0]), view(self.dlogits),
-                 epi(out=view(self.dup[4]), dact=ACT_RELU, dact_ref=view(self.up[4]), split_c=self.ups[4]["out"], out2=view(self.dpool[0])))
+        head_epi = epi(out=view(self.dup[4]), dact=ACT_RELU, dact_ref=view(self.up[4]), split_c=self.ups[4]["out"], out2=view(self.dpool[0]))
+        if self.head_gather:
+            # gather the 16 strided taps of dlogits once, then dW = X^T G (lands in HWOI order) and dX = G W' are 1-tap GEMMs
+            hh, hw_ = H // 2, W // 2
+            nc = self.num_class
+            self.prog_bwd.append((L.tbi_colsum, (dt, n * H * W, bref(view(self.dlogits, c=nc)), _ptr(self.g("f_tran/b")))))
+            self.prog_bwd.append((L.tbi_convt_gather_dz, (dt, n, hh, hw_, 4, nc, bref(view(self.dlogits)), bref(view(self.head_g)))))
+            wd = keep(TapWgrad())
+            wd.dtype = dt; wd.impl = impl; wd.n = n; wd.gh = hh; wd.gw = hw_; wd.groups = 1
+            wd.cin_g = self.head.cin; wd.cout_g = 16 * nc
+            wd.a_src[0] = view(self.up[4]); wd.a_src[1] = view(self.pool[0]); wd.b_src = view(self.head_g)
+            wd.a_stride = 1; wd.b_stride = 1; wd.ntaps = 1
+            wd.dw = _ptr(self.g("f_tran/w")); wd.tap_stride = 0; wd.ci_stride = 1; wd.co_stride = self.head.cin
+            self.prog_bwd.append((L.tbi_tapwgrad_run, (C.byref(wd),)))
+            mark("f_tran")
+            gd = keep(TapGemm())
+            gd.dtype = dt; gd.impl = impl; gd.n = n; gd.gh = hh; gd.gw = hw_; gd.groups = 1
+            gd.cin_g = 64; gd.cout_g = self.head.cin; gd.src[0] = view(self.head_g); gd.in_stride = 1; gd.ntaps = 1
+            gd.w = _ptr(self.head_wg); gd.epi = head_epi
+            self.prog_bwd.append((L.tbi_tapgemm_run, (C.byref(gd),)))
+        else:
+            conv_bwd(self.head, H // 2, W // 2, view(self.up[4]), view(self.pool[0]), view(self.dlogits), head_epi)
         for i in range(4, -1, -1):
             u = self.ups[i]
             h, w = H >> (6 - i), W >> (6 - i)
