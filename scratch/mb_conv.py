@@ -41,6 +41,16 @@ elif case == "wup3":        # wgrad of upsample_3
     x1 = rnd(64, 32, 32, 512); x2 = rnd(64, 32, 32, 128); dz = rnd(64, 64, 64, 256); w = torch.zeros(4, 4, 256, 640, device="cuda")
     f = lambda: ops.conv2d_transpose_s2_grads(x1, w, dz, x2=x2, need_dx=False)
     flops = 2 * 64 * 32 * 32 * 16 * 640 * 256; bytes_ = (x1.numel() + x2.numel() + dz.numel()) * 2
+elif case in ("dstem", "dc2"):   # dgrad alone: 3x3 C->C with act' fused (stem: 32 ch at 256^2, ELU'; dc2: 128 ch at 64^2 + accumulate)
+    import ctypes as C_
+    from ultrasound_modeling_b200 import _lib
+    L = _lib.lib()
+    ch, hw = (32, 256) if case == "dstem" else (128, 64)
+    dz = rnd(64, hw, hw, ch); ref = rnd(64, hw, hw, ch); w = torch.randn(3, 3, ch, ch, device="cuda") * 0.05
+    wb = ops.pack_conv(w, 1, 1, BF, None); dx = torch.zeros_like(dz)
+    e = ops._epi(dx, dact=ops.ACT_ELU, dact_ref=ref, residual=dx if case == "dc2" else None)
+    f = lambda: _lib.check(L.tbi_conv2d_dgrad(ops._dt(dz), 0, 64, hw, hw, 3, 1, 1, ops._vp(ops.view(dz)), ch, ops._p(wb), C_.byref(e), ops._st()), "dgrad")
+    flops = 2 * 64 * hw * hw * 9 * ch * ch; bytes_ = dz.numel() * 2 * (3 if case == "dstem" else 4)
 for _ in range(3): f()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -8,6 +8,10 @@ if case == "up4":
     x1 = torch.randn(64, 64, 64, 256, device="cuda").to(BF); x2 = torch.randn(64, 64, 64, 64, device="cuda").to(BF)
     w = torch.randn(4, 4, 128, 320, device="cuda") * 0.02; b = torch.zeros(128, device="cuda")
     f = lambda: ops.conv2d_transpose_s2(x1, w, b, act=ops._lib.ACT_RELU, x2=x2)
+elif case == "wide":          # 1x1 conv 64 -> 128 with a residual at 128x128: K tiny, N wide -> epilogue-paced
+    x = torch.randn(64, 128, 128, 64, device="cuda").to(BF); w = torch.randn(1, 1, 64, 128, device="cuda") * 0.05
+    b = torch.zeros(128, device="cuda"); r = torch.randn(64, 128, 128, 128, device="cuda").to(BF)
+    f = lambda: ops.conv2d(x, w, b, residual=r)
 elif case == "headd":
     x1 = torch.randn(64, 128, 128, 128, device="cuda").to(BF); x2 = torch.randn(64, 128, 128, 32, device="cuda").to(BF)
     w = torch.randn(4, 4, 3, 160, device="cuda") * 0.02

@@ -145,7 +145,7 @@ def lib() -> C.CDLL:
     if _lib is None:
         if is_stale():                      # sources changed (or never built): rebuild in-tree; raises if nvcc fails
             build()
-        L = C.CDLL(str(LIB_PATH))
+        L = C.CDLL(os.environ.get("TBI_LIB", str(LIB_PATH)))      # TBI_LIB: load an experimental build (scratch/ only)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError here == header/library mismatch
             fn.restype = res

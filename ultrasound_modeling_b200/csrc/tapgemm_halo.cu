@@ -44,6 +44,7 @@ struct alignas(64) HaloParams {
     int narrow;
     int resident, nslabs;          // weights-resident mode: a CTA keeps one (N tile, group, phase) weight slab in smem
     int sh_x, sh_y;                // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1 (divide)
+    int flat;                      // resident + one halo per chunk + (ntaps, ksteps) has an unrolled issue loop
     int rank4;                     // stride-1 sources: 4-D tensor map (C, W, H, N) instead of the 5-D parity view
     tbi_epilogue epi;
 };
@@ -92,6 +93,50 @@ struct Rings {
     int slab, it_first, it_stride, it_count;
 };
 
+
+// Weights-resident tiles whose taps all live in ONE halo load (stride-1 gathers): the issue stream of a tile is a fixed
+// list of NTAPS*KSTEPS MMAs per K chunk.  Fully unrolled with the tap row offsets in registers it is ~5 instructions per
+// MMA and the descriptor moves of successive MMAs are independent.  (The generic loop below spends ~30 dependent
+// instructions per MMA; for N=32 tiles -- 16 cycles of math per MMA -- the single issuing thread was the bottleneck:
+// ~210 cycles per MMA measured against ~49 for a free-running issue loop, profiles/r1_summary.md.)
+template <int NTAPS, int KSTEPS>
+__device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, const Rings& R, uint32_t tmem_base, uint32_t acc_cols, bool leader,
+                                                       uint32_t idesc, uint32_t a_base, uint32_t a_stage_lo, uint32_t a_hi,
+                                                       uint32_t b_base, uint32_t b_stage_lo, uint32_t b_hi, uint32_t row_lo, int ph) {
+    uint32_t a_off[NTAPS];
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) a_off[t] = ((uint32_t)p.t_row[ph][t] & 0x3FFu) * row_lo;
+    uint32_t sa = 0, a_par = 0, acc_it = 0;
+    for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+        const uint32_t buf = acc_it & 1u;
+        trace(g_halo_trace, 1, acc_it, 0);
+        tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+        tc::tc_fence_after();
+        trace(g_halo_trace, 1, acc_it, 1);
+        const uint32_t tmem_d = tmem_base + buf * acc_cols;
+        uint32_t b_lo = b_base;
+#pragma unroll 1
+        for (int c = 0; c < p.nchunks; ++c) {
+            tc::mbar_wait_bounded(&R.a_full[sa], a_par);
+            tc::tc_fence_after();
+            trace(g_halo_trace, 1, acc_it, 2);
+            const uint32_t a_lo = a_base + sa * a_stage_lo;
+            if (leader) {
+#pragma unroll
+                for (int t = 0; t < NTAPS; ++t)
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k)
+                        tc::umma_bf16_lh(tmem_d, a_lo + a_off[t] + 2 * k, a_hi, b_lo + t * b_stage_lo + 2 * k, b_hi, idesc, (t | k) ? 1u : (c > 0 ? 1u : 0u));
+                tc::umma_commit(&R.a_empty[sa]);
+            }
+            b_lo += NTAPS * b_stage_lo;
+            if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+        }
+        if (leader) tc::umma_commit(&R.t_full[buf]);
+        trace(g_halo_trace, 1, acc_it, 3);
+    }
+}
+
 template <int BN, int ACT, int DACT>
 __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, uint32_t tmem_base, int warp, int lane) {
     // Two groups of four warps (one warp per TMEM lane quadrant).  Group g owns accumulator buffer g, i.e. every
@@ -116,7 +161,9 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
         const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
         const int ox = gx * p.out_stride + (p.nphase > 1 ? p.ph_off_x[t.ph] : p.epi.out_off_x);
         RowCtx rc{};
-        if (valid && !p.narrow) rc = make_row_ctx(p.epi, n, oy, ox);
+        if (valid && !p.narrow) {
+            rc = make_row_ctx(p.epi, n, oy, ox);
+        }
         tc::mbar_wait_bounded<true>(&R.t_full[buf], (acc_it >> 1) & 1u);
         tc::tc_fence_after();
         trace(tr, 2, acc_it, 1);
@@ -155,7 +202,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __grid_constant__ HaloParams p) {
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;            // columns per accumulator buffer
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ uint8_t smem_raw[];
@@ -276,7 +323,27 @@ __global__ void __launch_bounds__(HT_THREADS) tapgemm_halo_kernel(const __grid_c
             }
             cur_ph = ph;
         };
-        if (p.resident) {
+        bool flat_done = false;
+        if (p.resident && p.ngroups == 1 && p.flat) {
+            // ---- weights resident, one halo per chunk: unrolled issue stream ----
+            if (R.it_first < R.it_count) tc::mbar_wait_bounded(R.b_res, 0);
+            const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
+#define TBI_FLAT(NT, KS) resident_flat_mma_loop<NT, KS>(p, R, tmem_base, ACC_COLS, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo, slab_ph)
+            switch (p.ntaps * 8 + ksteps) {
+                case 1 * 8 + 1: TBI_FLAT(1, 1); break;
+                case 1 * 8 + 2: TBI_FLAT(1, 2); break;
+                case 1 * 8 + 4: TBI_FLAT(1, 4); break;
+                case 4 * 8 + 2: TBI_FLAT(4, 2); break;
+                case 4 * 8 + 4: TBI_FLAT(4, 4); break;
+                case 9 * 8 + 1: TBI_FLAT(9, 1); break;
+                case 9 * 8 + 2: TBI_FLAT(9, 2); break;
+                default:        TBI_FLAT(9, 4); break;
+            }
+#undef TBI_FLAT
+            flat_done = true;
+        }
+        if (flat_done) {
+        } else if (p.resident) {
             // ---- weights resident: nothing but halo waits, descriptor adds and MMAs in the steady state ----
             if (R.it_first < R.it_count) { load_taps(slab_ph); tc::mbar_wait_bounded(R.b_res, 0); }
             uint32_t sa = 0, a_par = 0;
@@ -527,6 +594,12 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     static const bool no_resident = getenv("TBI_TC_NO_RESIDENT") != nullptr;
     p.resident = (!no_resident && slab_bytes <= 72 * 1024 && p.nslabs <= max_ctas && slab_bytes + 2 * p.a_stage_bytes <= budget &&
                   p.nchunks * d->ntaps <= 192) ? 1 : 0;
+    {
+        static const bool no_flat = getenv("TBI_TC_NO_FLAT") != nullptr;
+        const int ks = kc / 16, nt = d->ntaps;
+        const bool have = (nt == 1 && (ks == 1 || ks == 2 || ks == 4)) || (nt == 4 && (ks == 2 || ks == 4)) || (nt == 9 && (ks == 1 || ks == 2 || ks == 4));
+        p.flat = (p.resident && p.ngroups == 1 && have && !no_flat) ? 1 : 0;
+    }
     auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
     p.sh_x = lg2(p.tiles_x); p.sh_y = lg2(p.tiles_y);
     if (p.sh_x < 0 || p.sh_y < 0) p.sh_x = p.sh_y = -1;
