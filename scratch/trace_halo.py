@@ -31,10 +31,10 @@ t = tr.cpu().view(3, 64, 8)
 t0 = int(t[t > 0].min())
 rel = lambda v: (int(v) - t0) if int(v) > 0 else -1
 print("cycles relative to first event; producer: [wait_start, got_empty] per halo load")
-for i in range(12): print("P %2d" % i, [rel(v) for v in t[0, i, :2]])
+for i in range(20, 32): print("P %2d" % i, [rel(v) for v in t[0, i, :2]])
 print("MMA: [loop_start, got_t_empty, got_a_full, committed]")
-for i in range(12): print("M %2d" % i, [rel(v) for v in t[1, i, :4]])
+for i in range(20, 32): print("M %2d" % i, [rel(v) for v in t[1, i, :4]])
 print("EPI warp2: [loop_start, got_t_full, ld_done, arrived, stores_issued]")
-for i in range(12): print("E %2d" % i, [rel(v) for v in t[2, i, :5]])
+for i in range(20, 32): print("E %2d" % i, [rel(v) for v in t[2, i, :5]])
 d = [int(t[1, i + 1, 3]) - int(t[1, i, 3]) for i in range(20, 40)]
 print("steady-state cycles per tile (MMA commit to commit):", sum(d) / len(d))

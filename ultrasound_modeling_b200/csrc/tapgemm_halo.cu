@@ -46,14 +46,16 @@ struct alignas(64) HaloParams {
     int sh_x, sh_y;                // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1 (divide)
     int flat;                      // resident + one halo per chunk + (ntaps, ksteps) has an unrolled issue loop
     int rank4;                     // stride-1 sources: 4-D tensor map (C, W, H, N) instead of the 5-D parity view
+    unsigned long long* trace;     // debug timeline buffer or nullptr (a kernel parameter: testing it costs no memory access)
     tbi_epilogue epi;
 };
 
-// optional timeline trace (debug): block 0 writes clock64 stamps, [role][tile][event]; enabled by tbi_debug_set_trace()
-__device__ unsigned long long* g_halo_trace = nullptr;
+// optional timeline trace (debug): block 0 writes clock64 stamps, [role][tile][event]; enabled by tbi_debug_set_halo_trace()
 __device__ __forceinline__ void trace(unsigned long long* tr, int role, int tile, int ev) {
     if (tr && blockIdx.x == 0 && tile < 64) tr[(role * 64 + tile) * 8 + ev] = clock64();
 }
+
+static unsigned long long* g_halo_trace_host = nullptr;
 
 struct TileCoord { int x0, y0, n0, nc0, cg, ph; };
 
@@ -109,17 +111,17 @@ __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, cons
     uint32_t sa = 0, a_par = 0, acc_it = 0;
     for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
         const uint32_t buf = acc_it & 1u;
-        trace(g_halo_trace, 1, acc_it, 0);
+        trace(p.trace, 1, acc_it, 0);
         tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
         tc::tc_fence_after();
-        trace(g_halo_trace, 1, acc_it, 1);
+        trace(p.trace, 1, acc_it, 1);
         const uint32_t tmem_d = tmem_base + buf * acc_cols;
         uint32_t b_lo = b_base;
 #pragma unroll 1
         for (int c = 0; c < p.nchunks; ++c) {
             tc::mbar_wait_bounded(&R.a_full[sa], a_par);
             tc::tc_fence_after();
-            trace(g_halo_trace, 1, acc_it, 2);
+            trace(p.trace, 1, acc_it, 2);
             const uint32_t a_lo = a_base + sa * a_stage_lo;
             if (leader) {
 #pragma unroll
@@ -133,12 +135,12 @@ __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, cons
             if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
         }
         if (leader) tc::umma_commit(&R.t_full[buf]);
-        trace(g_halo_trace, 1, acc_it, 3);
+        trace(p.trace, 1, acc_it, 3);
     }
 }
 
 template <int BN, int ACT, int DACT>
-__device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, uint32_t tmem_base, int warp, int lane) {
+__device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, const float* sbias, uint32_t tmem_base, int warp, int lane) {
     // Two groups of four warps (one warp per TMEM lane quadrant).  Group g owns accumulator buffer g, i.e. every
     // second tile, so the epilogues of consecutive tiles overlap (the per-tile chain wait -> tcgen05.ld -> loads ->
     // math -> stores is latency-bound for small K).
@@ -150,7 +152,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     uint32_t acc_it = 0;
     TileCoord slab_t{};
     if (p.resident) slab_t = decode_tile(p, R.slab, BN);
-    unsigned long long* tr = (warp == 0 && lane == 0) ? g_halo_trace : nullptr;
+    unsigned long long* tr = (warp == 0 && lane == 0) ? p.trace : nullptr;
     for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
         if ((int)(acc_it & 1u) != grp) continue;
         const uint32_t buf = (uint32_t)grp;
@@ -163,6 +165,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
         RowCtx rc{};
         if (valid && !p.narrow) {
             rc = make_row_ctx(p.epi, n, oy, ox);
+            if (rc.bias) rc.bias = sbias;
         }
         tc::mbar_wait_bounded<true>(&R.t_full[buf], (acc_it >> 1) & 1u);
         tc::tc_fence_after();
@@ -219,7 +222,11 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
     R.t_empty = R.t_full + 2;                              // [2]
     R.b_res = R.t_empty + 2;                               // weights-resident slab loaded
     uint32_t* tslot = reinterpret_cast<uint32_t*>(R.b_res + 1);
-    uint4* mma_tab = reinterpret_cast<uint4*>((reinterpret_cast<uintptr_t>(tslot + 4) + 15) & ~static_cast<uintptr_t>(15));  // resident mode: one entry per (chunk, tap): {a row offset>>4, b addr>>4, flags, -}
+    // the folded bias of every output channel, staged once: the epilogue reads it with shared-memory latency and the loads do not
+    // sit behind the (possibly aliasing) global stores of the previous channel group
+    float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tslot + 4) + 15) & ~static_cast<uintptr_t>(15));
+    if (p.epi.bias && !p.narrow)
+        for (int i = threadIdx.x; i < p.cout_total; i += HT_THREADS) sbias[i] = p.epi.bias[i];
     // tile iteration: streaming = round-robin over all tiles; resident = this CTA's slab x a strided set of M tiles
     R.slab = p.resident ? (int)(blockIdx.x % p.nslabs) : 0;
     R.it_first = p.resident ? (int)(blockIdx.x / p.nslabs) : (int)blockIdx.x;
@@ -266,9 +273,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                 if (p.cgroups == 1 && cch >= p.c0) { src = 1; cch -= p.c0; }
                 int tap = 0;
                 for (int grp = 0; grp < p.ngroups; ++grp) {
-                    trace(g_halo_trace, 0, a_it, 0);
+                    trace(p.trace, 0, a_it, 0);
                     tc::mbar_wait_bounded(&R.a_empty[sa], a_par);
-                    trace(g_halo_trace, 0, a_it, 1);
+                    trace(p.trace, 0, a_it, 1);
                     if (leader) {
                         tc::mbar_expect_tx(&R.a_full[sa], p.a_tx);
                         if (p.rank4)
@@ -350,10 +357,10 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
             for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
                 const uint32_t buf = acc_it & 1u;
-                trace(g_halo_trace, 1, acc_it, 0);
+                trace(p.trace, 1, acc_it, 0);
                 tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
                 tc::tc_fence_after();
-                trace(g_halo_trace, 1, acc_it, 1);
+                trace(p.trace, 1, acc_it, 1);
                 const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
                 uint32_t accum = 0, b_lo = b_base, a_lo = 0;
 #pragma unroll 1
@@ -367,7 +374,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                         if (e & 0x400u) {
                             tc::mbar_wait_bounded(&R.a_full[sa], a_par);
                             tc::tc_fence_after();
-                            trace(g_halo_trace, 1, acc_it, 2);
+                            trace(p.trace, 1, acc_it, 2);
                             a_lo = a_base + sa * a_stage_lo;
                         }
                         const uint32_t al = a_lo + (e & 0x3FFu) * row_lo;
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                     }
                 }
                 if (leader) tc::umma_commit(&R.t_full[buf]);
-                trace(g_halo_trace, 1, acc_it, 3);
+                trace(p.trace, 1, acc_it, 3);
             }
         } else {
             // ---- weights streamed: one B stage per (chunk, tap); wrap-around stage counters, nothing but waits + MMAs ----
@@ -393,10 +400,10 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                 const int ph = (p.nphase > 1 ? decode_tile(p, i, BN).ph : 0);
                 if (ph != cur_ph) load_taps(ph);
                 const uint32_t buf = acc_it & 1u;
-                trace(g_halo_trace, 1, acc_it, 0);
+                trace(p.trace, 1, acc_it, 0);
                 tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
                 tc::tc_fence_after();
-                trace(g_halo_trace, 1, acc_it, 1);
+                trace(p.trace, 1, acc_it, 1);
                 const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
                 uint32_t accum = 0, a_lo = 0;
 #pragma unroll 1
@@ -409,7 +416,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                         cur >>= 12;
                         if (e & 0x400u) {
                             tc::mbar_wait_bounded(&R.a_full[sa], a_par);
-                            trace(g_halo_trace, 1, acc_it, 2);
+                            trace(p.trace, 1, acc_it, 2);
                             a_lo = a_base + sa * a_stage_lo;
                         }
                         tc::mbar_wait_bounded(&R.b_full[sb], b_par);
@@ -429,13 +436,13 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                     }
                 }
                 if (leader) tc::umma_commit(&R.t_full[buf]);
-                trace(g_halo_trace, 1, acc_it, 3);
+                trace(p.trace, 1, acc_it, 3);
             }
         }
         __syncwarp();
     } else {
         // ===================== epilogue (warp w owns TMEM lanes [32*(w%4), +32)) =====================
-        TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_role<BN, A_, D_>(p, R, tmem_base, warp, lane)));
+        TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_role<BN, A_, D_>(p, R, sbias, tmem_base, warp, lane)));
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -529,8 +536,8 @@ bool plan_taps(const tbi_tapgemm* d, TapPlan* tp) {
 
 // debug: device buffer of 3*64*8 uint64 (or nullptr to disable); not part of the public header
 extern "C" int tbi_debug_set_halo_trace(void* buf) {
-    unsigned long long* p = (unsigned long long*)buf;
-    return cudaMemcpyToSymbol(g_halo_trace, &p, sizeof(p)) == cudaSuccess ? 0 : -4;
+    g_halo_trace_host = (unsigned long long*)buf;
+    return 0;
 }
 
 bool tbi_tapgemm_halo_supported(const tbi_tapgemm* d) {
@@ -547,7 +554,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     TapPlan tp;
     if (!plan_taps(d, &tp)) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapgemm_halo: tap pattern");
     const int kc = halo_pick_kc(d);
-    p.n = d->n; p.gh = d->gh; p.gw = d->gw;
+    p.n = d->n; p.gh = d->gh; p.gw = d->gw; p.trace = g_halo_trace_host;
     p.tiles_x = (d->gw + TW - 1) / TW; p.tiles_y = (d->gh + TH - 1) / TH; p.m_tiles = d->n * p.tiles_x * p.tiles_y;
     p.cgroups = d->groups; p.nphase = d->nphase > 1 ? d->nphase : 1;
     p.cin_g = d->cin_g; p.cout_g = d->cout_g; p.cout_total = d->cout_g * d->groups;
@@ -625,7 +632,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         if (grid > p.total_tiles) grid = p.total_tiles;
     }
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512 +
-                        (p.resident ? (size_t)p.nchunks * d->ntaps * 16 + 64 : 0) + (size_t)(2 * (p.a_stages + p.b_stages)) * 8;
+                        ((size_t)p.cout_total * 4 + 64) + (size_t)(2 * (p.a_stages + p.b_stages)) * 8;
     switch (bn) {
         case 128: return launch_halo<128>(p, grid, smem, s);
         case 64:  return launch_halo<64>(p, grid, smem, s);

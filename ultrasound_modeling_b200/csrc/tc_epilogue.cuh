@@ -7,8 +7,16 @@
 
 namespace {
 
+// exp(v) for v <= 0 as one FMUL + one MUFU.  (__expf adds a denormal-range rescue around ex2 -- ~10 instructions and a
+// handful of predicates per value -- which made the ELU epilogue issue-bound; below -126*ln2 the answer flushes to 0,
+// i.e. ELU = -1, exactly what bf16 would round to anyway.)
+__device__ __forceinline__ float exp_neg_fast(float v) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v * 1.4426950408889634f));
+    return y;
+}
 template <int ACT> __device__ __forceinline__ float act_fast(float v) {
-    if (ACT == TBI_ACT_ELU)   return v > 0.f ? v : __expf(v) - 1.f;     // SFU exp: abs error ~1e-7 << bf16 resolution
+    if (ACT == TBI_ACT_ELU)   return v > 0.f ? v : exp_neg_fast(v) - 1.f;     // SFU exp: abs error ~1e-7 << bf16 resolution
     if (ACT == TBI_ACT_LRELU) return v > 0.f ? v : 0.3f * v;
     if (ACT == TBI_ACT_RELU)  return fmaxf(v, 0.f);
     return v;
@@ -31,6 +39,24 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
     return q;
+}
+
+// 32 bytes per thread per access when the row is 32-byte aligned (sm_100 256-bit global accesses): every access is then a
+// whole 32-byte sector.  With 16-byte accesses each sector was written in two halves by two instructions (ncu: 2x the
+// sector writes, L1TEX the busiest unit of the stem convolutions).
+__device__ __forceinline__ void st_global_32B(void* p, const uint4& a, const uint4& b) {
+    if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+    } else {
+        reinterpret_cast<uint4*>(p)[0] = a; reinterpret_cast<uint4*>(p)[1] = b;
+    }
+}
+__device__ __forceinline__ void ld_global_32B(const void* p, uint4& a, uint4& b) {
+    if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+        asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p) : "memory");
+    } else {
+        a = reinterpret_cast<const uint4*>(p)[0]; b = reinterpret_cast<const uint4*>(p)[1];
+    }
 }
 
 // per-thread, per-tile pointers to channel 0 of this thread's output pixel in every tensor the epilogue touches
@@ -92,7 +118,7 @@ __device__ __forceinline__ void finish_store8(const RowCtx& r, int co, float (&v
         return;
     }
     if (r.bias) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(r.bias + co)), b1 = __ldg(reinterpret_cast<const float4*>(r.bias + co + 4));
+        const float4 b0 = *reinterpret_cast<const float4*>(r.bias + co), b1 = *reinterpret_cast<const float4*>(r.bias + co + 4);
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
     if (DACT == TBI_ACT_NONE && r.keep) {
@@ -120,53 +146,43 @@ __device__ __forceinline__ void finish_store8(const RowCtx& r, int co, float (&v
     *reinterpret_cast<uint4*>(r.out + co) = pack8(v);
 }
 
-// Fast path: NCOLS in-range channels on one side of the split, as ONE basic block.  Loads and stores go through
-// pointers the compiler must assume alias, and a group's loads issued only after the previous group's store cost one
-// DRAM round trip per group (measured ~3000 cycles each).  So: no data-dependent control flow (an absent residual or
-// bias reads a 32-byte zero block with stride 0; the dropout multiplier is a template flag) and every side input comes
-// through the read-only path, which lets the scheduler lift the loads of all groups above the first store as far as
-// the register budget allows.  (A residual that aliases the output -- in-place accumulation -- is read exactly once,
-// by the thread that then overwrites it, so the read-only path is safe there too.)
-static __device__ __align__(32) unsigned char g_epi_zero[32];
-
-#ifndef TBI_EPI_STAGE
-#define TBI_EPI_STAGE 1          // 1: explicit load-all-then-store-all (measured faster: 14.36 vs 14.86 ms/step); 0: leave the hoisting to the scheduler
-#endif
-template <int ACT, int DACT, bool HAS_K, int NCOLS>
-__device__ __forceinline__ void epilogue_fast(__nv_bfloat16* out, const __nv_bfloat16* __restrict__ res, int res_step,
-                                              const __nv_bfloat16* __restrict__ ref, const uint8_t* __restrict__ k,
-                                              const float* bias, int bias_step, const uint32_t (&r)[NCOLS]) {
+// Fast path: NCOLS in-range channels on one side of the split.  Loads and stores go through pointers the compiler must
+// assume alias, so a load placed after a store waits for nothing in hardware but cannot be hoisted by the compiler, and
+// the epilogue degenerates into one DRAM/L2 round trip per 8-channel group (measured ~800-3000 cycles each).  Hence two
+// phases: (A) every global side input of the chunk into registers, (B) math + stores with no global load in between.
+// The bias comes from `bias` with plain loads inside phase B: the halo kernel points it at a shared-memory copy.
+// Which optional inputs exist is a template parameter (HAS_RES, HAS_K): a variant holds registers only for what it reads.
+template <int ACT, int DACT, bool HAS_RES, bool HAS_K, int NCOLS>
+__device__ __forceinline__ void epilogue_fast(__nv_bfloat16* out, const __nv_bfloat16* res, const __nv_bfloat16* ref, const uint8_t* k,
+                                              const float* bias, const uint32_t (&r)[NCOLS]) {
     constexpr int G = NCOLS / 8;
-#if TBI_EPI_STAGE
-    uint4 qres[G], qref[DACT != TBI_ACT_NONE ? G : 1];
+    uint4 qres[HAS_RES ? G : 1], qref[DACT != TBI_ACT_NONE ? G : 1];
     uint2 qk[HAS_K ? G : 1];
+    static_assert(G % 2 == 0, "channel groups are processed in pairs (32-byte accesses)");
+    if (HAS_RES) {
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
-        qres[j] = *reinterpret_cast<const uint4*>(res + j * res_step);
-        if (DACT != TBI_ACT_NONE) qref[j] = *reinterpret_cast<const uint4*>(ref + 8 * j);
-        if (HAS_K) qk[j] = *reinterpret_cast<const uint2*>(k + 8 * j);
+        for (int j = 0; j < G; j += 2) ld_global_32B(res + 8 * j, qres[j], qres[j + 1]);
     }
-#endif
+    if (DACT != TBI_ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < G; j += 2) ld_global_32B(ref + 8 * j, qref[j], qref[j + 1]);
+    }
+    if (HAS_K) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) qk[j] = *reinterpret_cast<const uint2*>(k + 8 * j);
+    }
+    uint4 held;
 #pragma unroll
     for (int j = 0; j < G; ++j) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[8 * j + i]);
-#if TBI_EPI_STAGE
-        const uint4 q_res = qres[j];
-        const uint4 q_ref = qref[DACT != TBI_ACT_NONE ? j : 0];
-        const uint2 kk = qk[HAS_K ? j : 0];
-#else
-        const uint4 q_res = __ldg(reinterpret_cast<const uint4*>(res + j * res_step));
-        uint4 q_ref; uint2 kk;
-        if (DACT != TBI_ACT_NONE) q_ref = __ldg(reinterpret_cast<const uint4*>(ref + 8 * j));
-        if (HAS_K) kk = __ldg(reinterpret_cast<const uint2*>(k + 8 * j));
-#endif
-        const unsigned char* kb = reinterpret_cast<const unsigned char*>(&kk);
+        const unsigned char* kb = reinterpret_cast<const unsigned char*>(&qk[HAS_K ? j : 0]);
         if (DACT == TBI_ACT_NONE) {
-            // plain loads on purpose: they stay next to their use (an L1 hit) instead of holding 8 registers per group
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + j * bias_step), b1 = *reinterpret_cast<const float4*>(bias + j * bias_step + 4);
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            if (bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + 8 * j), b1 = *reinterpret_cast<const float4*>(bias + 8 * j + 4);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
             if (HAS_K) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) v[i] *= (float)kb[i];
@@ -174,13 +190,13 @@ __device__ __forceinline__ void epilogue_fast(__nv_bfloat16* out, const __nv_bfl
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = act_fast<ACT>(v[i]);
-        {
-            float t[8]; unpack8(q_res, t);
+        if (HAS_RES) {
+            float t[8]; unpack8(qres[HAS_RES ? j : 0], t);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += t[i];
         }
         if (DACT != TBI_ACT_NONE) {
-            float t[8]; unpack8(q_ref, t);
+            float t[8]; unpack8(qref[DACT != TBI_ACT_NONE ? j : 0], t);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= dact_fast<DACT>(t[i]);
             if (HAS_K) {
@@ -188,7 +204,8 @@ __device__ __forceinline__ void epilogue_fast(__nv_bfloat16* out, const __nv_bfl
                 for (int i = 0; i < 8; ++i) v[i] *= (float)kb[i];
             }
         }
-        *reinterpret_cast<uint4*>(out + 8 * j) = pack8(v);
+        if (j & 1) st_global_32B(out + 8 * (j - 1), held, pack8(v));
+        else held = pack8(v);
     }
 }
 
@@ -196,23 +213,23 @@ __device__ __forceinline__ void epilogue_fast(__nv_bfloat16* out, const __nv_bfl
 template <int ACT, int DACT, int NCOLS>
 __device__ __forceinline__ void epilogue_cols(const RowCtx& rc, const uint32_t (&r)[NCOLS], int col0, int cout_g, int cbase) {
     const int co0 = cbase + col0;
-    const __nv_bfloat16* zero16 = reinterpret_cast<const __nv_bfloat16*>(g_epi_zero);
-    const float* zero32 = reinterpret_cast<const float*>(g_epi_zero);
     const bool whole = col0 + NCOLS <= cout_g;
     if (whole && rc.split_c > 0 && co0 >= rc.split_c) {                       // the pass-through half of a split output
         const int c2 = co0 - rc.split_c;
-        epilogue_fast<TBI_ACT_NONE, TBI_ACT_NONE, false, NCOLS>(rc.out2 + c2, rc.res2 ? rc.res2 + c2 : zero16, rc.res2 ? 8 : 0,
-                                                                 nullptr, nullptr, zero32, 0, r);
+        if (rc.res2) epilogue_fast<TBI_ACT_NONE, TBI_ACT_NONE, true, false, NCOLS>(rc.out2 + c2, rc.res2 + c2, nullptr, nullptr, nullptr, r);
+        else         epilogue_fast<TBI_ACT_NONE, TBI_ACT_NONE, false, false, NCOLS>(rc.out2 + c2, nullptr, nullptr, nullptr, nullptr, r);
         return;
     }
     if (whole && (rc.split_c <= 0 || co0 + NCOLS <= rc.split_c) && !(DACT != TBI_ACT_NONE && rc.bias)) {
-        const __nv_bfloat16* res = rc.res ? rc.res + co0 : zero16;
-        const int res_step = rc.res ? 8 : 0;
-        const float* bias = rc.bias ? rc.bias + co0 : zero32;
-        const int bias_step = rc.bias ? 8 : 0;
         const uint8_t* k = DACT != TBI_ACT_NONE ? rc.dkeep : rc.keep;
-        if (k) epilogue_fast<ACT, DACT, true, NCOLS>(rc.out + co0, res, res_step, rc.ref + co0, k + co0, bias, bias_step, r);
-        else   epilogue_fast<ACT, DACT, false, NCOLS>(rc.out + co0, res, res_step, rc.ref + co0, nullptr, bias, bias_step, r);
+        const float* bias = rc.bias ? rc.bias + co0 : nullptr;
+        if (rc.res) {
+            if (k) epilogue_fast<ACT, DACT, true, true, NCOLS>(rc.out + co0, rc.res + co0, rc.ref + co0, k + co0, bias, r);
+            else   epilogue_fast<ACT, DACT, true, false, NCOLS>(rc.out + co0, rc.res + co0, rc.ref + co0, nullptr, bias, r);
+        } else {
+            if (k) epilogue_fast<ACT, DACT, false, true, NCOLS>(rc.out + co0, nullptr, rc.ref + co0, k + co0, bias, r);
+            else   epilogue_fast<ACT, DACT, false, false, NCOLS>(rc.out + co0, nullptr, rc.ref + co0, nullptr, bias, r);
+        }
         return;
     }
 #pragma unroll
