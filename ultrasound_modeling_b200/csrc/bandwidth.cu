@@ -196,11 +196,24 @@ __global__ void colsum_vec_kernel(long long npix, tbi_view x, float* out, int pi
 #pragma unroll
         for (int k = 0; k < V; ++k) s[k] = 0.f;
         if (ch < x.c && lane_p < pl) {
-            const T* base = (const T*)x.ptr + x.coff + ch;
-#pragma unroll 4
-            for (long long p = pbeg + lane_p; p < pend; p += pl) {
+            // U independent 16-byte loads in flight per thread (a single dependent load per iteration left the kernel at ~35 % of HBM peak)
+            constexpr int U = 8;
+            const T* base = (const T*)x.ptr + x.coff + ch + (size_t)(pbeg + lane_p) * x.cstride;
+            const size_t step = (size_t)pl * x.cstride;
+            const int cnt = (int)((pend - pbeg - lane_p + pl - 1) / pl);          // pixels this thread visits
+            int i = 0;
+            for (; i + U <= cnt; i += U) {
+                float a[U][V];
+#pragma unroll
+                for (int u = 0; u < U; ++u) ld_pack<T, V>(base + (size_t)(i + u) * step, a[u]);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int k = 0; k < V; ++k) s[k] += a[u][k];
+            }
+            for (; i < cnt; ++i) {
                 float a[V];
-                ld_pack<T, V>(base + (size_t)p * x.cstride, a);
+                ld_pack<T, V>(base + (size_t)i * step, a);
 #pragma unroll
                 for (int k = 0; k < V; ++k) s[k] += a[k];
             }
@@ -217,6 +230,46 @@ __global__ void colsum_vec_kernel(long long npix, tbi_view x, float* out, int pi
             }
         }
         __syncthreads();
+    }
+}
+
+// Dense tensors (cstride == c, c*sizeof(T) a multiple of 16 B, total thread count a multiple of the chunks per pixel):
+// the tensor is one flat array of 16-byte chunks and a thread striding by the total thread count always lands on the
+// same channel chunk, so it accumulates V channels in registers over perfectly coalesced loads, U of them in flight.
+template <typename T, int V>
+__global__ void __launch_bounds__(256) colsum_flat_kernel(long long nchunks, int cv, const T* __restrict__ x, float* out) {
+    __shared__ float sm[256][V + 1];
+    constexpr int U = 8;
+    const long long T_all = (long long)gridDim.x * blockDim.x;
+    const long long g0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    float s[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) s[k] = 0.f;
+    long long j = g0;
+    for (; j + (U - 1) * T_all < nchunks; j += U * T_all) {
+        Pack<T, V> q[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) q[u] = *reinterpret_cast<const Pack<T, V>*>(x + (size_t)(j + u * T_all) * V);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int k = 0; k < V; ++k) s[k] += ldf(&q[u].v[k]);
+    }
+    for (; j < nchunks; j += T_all) {
+        const Pack<T, V> q = *reinterpret_cast<const Pack<T, V>*>(x + (size_t)j * V);
+#pragma unroll
+        for (int k = 0; k < V; ++k) s[k] += ldf(&q.v[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) sm[threadIdx.x][k] = s[k];
+    __syncthreads();
+    // threads with equal (tid % cv) hold the same channel chunk: one thread per (chunk, k) sums its 256/cv rows
+    const int chunk0 = (int)(((long long)blockIdx.x * blockDim.x) % cv);          // chunk id of thread 0 (T_all % cv == 0 => fixed per block)
+    for (int e = threadIdx.x; e < cv * V; e += blockDim.x) {
+        const int lc = e / V, k = e % V;                                            // lc = tid % cv of the owning threads
+        float tot = 0.f;
+        for (int t = lc; t < (int)blockDim.x; t += cv) tot += sm[t][k];
+        atomicAdd(out + ((chunk0 + lc) % cv) * V + k, tot);
     }
 }
 
@@ -643,6 +696,44 @@ __global__ void bn_param_grad_kernel(int c, long long k_outer, long long inner, 
     }
 }
 
+// HWIO kernels (output channel innermost): 32 consecutive channels per warp row so every access is a full 128-byte line,
+// K split over blockIdx.y; dgamma is linear in the dot product, so the slices combine with one atomic each.
+__global__ void __launch_bounds__(256) bn_param_grad_cols_kernel(int c, long long K, long long row_stride, const float* __restrict__ w, float* dw,
+                                                                 const float* bias, float* dbias, const float* gamma, const float* mean,
+                                                                 const float* var, float eps, float* dgamma, float* dbeta) {
+    __shared__ float red[8][33];
+    const int ch = blockIdx.x * 32 + threadIdx.x, kl = threadIdx.y;
+    const long long per = (K + gridDim.y - 1) / gridDim.y;
+    const long long k0 = (long long)blockIdx.y * per, k1 = min(K, k0 + per);
+    float l = 0.f, istd = 0.f, sc = 0.f;
+    if (ch < c) {
+        istd = rsqrtf(var[ch] + eps);
+        sc = gamma[ch] * istd;
+#pragma unroll 4
+        for (long long k = k0 + kl; k < k1; k += 8) {
+            const size_t a = (size_t)k * row_stride + ch;
+            const float g = dw[a];
+            l = fmaf(w[a], g, l);
+            dw[a] = g * sc;
+        }
+    }
+    red[kl][threadIdx.x] = l;
+    __syncthreads();
+    if (kl == 0 && ch < c) {
+        float dot = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dot += red[q][threadIdx.x];
+        if (blockIdx.y == 0) {
+            const float draw = dbias[ch];
+            const float b = bias ? bias[ch] : 0.f;
+            dot += (b - mean[ch]) * draw;
+            dbeta[ch] += draw;
+            dbias[ch] = draw * sc;
+        }
+        atomicAdd(dgamma + ch, dot * istd);
+    }
+}
+
 __global__ void adam_kernel(long long count, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, const int32_t* step_count, float lr, float b1, float b2, float eps, float gs) {
     const float t = (float)(*step_count + 1);
@@ -780,6 +871,23 @@ extern "C" int tbi_colsum(int dtype, int64_t npix, const tbi_view* x, float* out
     if (blocks < 1) blocks = 1;
     const int ppb = (int)((npix + blocks - 1) / blocks);
     blocks = (npix + ppb - 1) / ppb;
+    {   // dense fast path
+        const int V = dtype == TBI_F32 ? 4 : 8;
+        static const bool no_flat = getenv("TBI_COLSUM_NO_FLAT") != nullptr;
+        if (!no_flat && (dtype == TBI_F32 || dtype == TBI_BF16) && x->cstride == x->c && x->coff == 0 && x->c % V == 0 && 256 % (x->c / V) == 0 &&
+            (((uintptr_t)x->ptr) & 15) == 0) {
+            const int cv = x->c / V;
+            const long long nchunks = npix * cv;
+            long long nb = (nchunks + 256 * 8 - 1) / (256 * 8);
+            const long long capf = (long long)tbi_sm_count() * 4;
+            if (nb > capf) nb = capf;
+            if (nb < 1) nb = 1;
+            if (dtype == TBI_F32) colsum_flat_kernel<float, 4><<<(unsigned)nb, 256, 0, s>>>(nchunks, cv, (const float*)x->ptr, out);
+            else colsum_flat_kernel<__nv_bfloat16, 8><<<(unsigned)nb, 256, 0, s>>>(nchunks, cv, (const __nv_bfloat16*)x->ptr, out);
+            TBI_CUDA_LAUNCH_CHECK("colsum_flat");
+            return TBI_OK;
+        }
+    }
     if (pick_vec(dtype, {x}) > 1) {
         if (dtype == TBI_F32) colsum_vec_kernel<float, 4><<<(unsigned)blocks, 256, 256 * 4 * sizeof(float), s>>>(npix, *x, out, ppb);
         else colsum_vec_kernel<__nv_bfloat16, 8><<<(unsigned)blocks, 256, 256 * 8 * sizeof(float), s>>>(npix, *x, out, ppb);
@@ -984,8 +1092,17 @@ extern "C" int tbi_bn_fold(int c, const float* gamma, const float* beta, const f
 extern "C" int tbi_bn_param_grad(int c, int64_t k_outer, int64_t inner, int64_t outer_stride, int64_t co_stride, const float* w,
                                  float* dw, const float* bias, float* dbias, const float* gamma, const float* mean,
                                  const float* var, float eps, float* dgamma, float* dbeta, void* stream) {
-    bn_param_grad_kernel<<<c, 128, 0, (cudaStream_t)stream>>>(c, k_outer, inner, outer_stride, co_stride, w, dw, bias, dbias,
-                                                              gamma, mean, var, eps, dgamma, dbeta);
+    static const bool rows_only = getenv("TBI_BN_ROWS") != nullptr;
+    if (inner == 1 && co_stride == 1 && !rows_only) {
+        long long ks = k_outer / 64;
+        if (ks < 1) ks = 1;
+        if (ks > 32) ks = 32;
+        bn_param_grad_cols_kernel<<<dim3((unsigned)((c + 31) / 32), (unsigned)ks), dim3(32, 8), 0, (cudaStream_t)stream>>>(
+            c, k_outer, outer_stride, w, dw, bias, dbias, gamma, mean, var, eps, dgamma, dbeta);
+    } else {
+        bn_param_grad_kernel<<<c, 128, 0, (cudaStream_t)stream>>>(c, k_outer, inner, outer_stride, co_stride, w, dw, bias, dbias,
+                                                                  gamma, mean, var, eps, dgamma, dbeta);
+    }
     TBI_CUDA_LAUNCH_CHECK("bn_param_grad");
     return TBI_OK;
 }

@@ -11,12 +11,26 @@ constexpr int MAXK = 36;
 
 template <typename T, int V> struct alignas(sizeof(T) * V) PackD { T v[V]; };
 
-template <typename T, int COUT>
+// exp for v <= 0: one FMUL + MUFU (same helper as the tensor-core epilogue)
+__device__ __forceinline__ float exp_neg_fast_d(float v) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(v * 1.4426950408889634f));
+    return y;
+}
+template <int ACT> __device__ __forceinline__ float act_ct(float v) {
+    if (ACT == TBI_ACT_ELU)   return v > 0.f ? v : exp_neg_fast_d(v) - 1.f;
+    if (ACT == TBI_ACT_LRELU) return v > 0.f ? v : 0.3f * v;
+    if (ACT == TBI_ACT_RELU)  return fmaxf(v, 0.f);
+    return v;
+}
+
+// weights in shared memory as [k][COUT] so one LDS.128 feeds four FMAs; activation is a template parameter
+template <typename T, int COUT, int ACT>
 __global__ void __launch_bounds__(256) smallcin_fwd_kernel(const __grid_constant__ tbi_tapgemm d) {
-    __shared__ float ws[COUT * MAXK];
+    __shared__ __align__(16) float ws[MAXK * COUT];
     __shared__ float bs[COUT];
     const int cin = d.cin_g, Kg = d.ntaps * cin;
-    for (int i = threadIdx.x; i < COUT * Kg; i += blockDim.x) ws[i] = ldf((const T*)d.w + i);
+    for (int i = threadIdx.x; i < COUT * Kg; i += blockDim.x) { const int c = i / Kg, k = i % Kg; ws[k * COUT + c] = ldf((const T*)d.w + i); }
     for (int i = threadIdx.x; i < COUT; i += blockDim.x) bs[i] = d.epi.bias ? d.epi.bias[i] : 0.f;
     __syncthreads();
     const tbi_epilogue& e = d.epi;
@@ -35,9 +49,13 @@ __global__ void __launch_bounds__(256) smallcin_fwd_kernel(const __grid_constant
             const T* px = src + view_off(d.src[0], n, iy, ix, 0);
             for (int ci = 0; ci < cin; ++ci) {
                 const float a = ldf(px + ci);
-                const float* wk = ws + tap * cin + ci;
+                const float4* wk = reinterpret_cast<const float4*>(ws + (tap * cin + ci) * COUT);
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[c] = fmaf(a, wk[c * Kg], acc[c]);
+                for (int c4 = 0; c4 < COUT / 4; ++c4) {
+                    const float4 w4 = wk[c4];
+                    acc[4 * c4] = fmaf(a, w4.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(a, w4.y, acc[4 * c4 + 1]);
+                    acc[4 * c4 + 2] = fmaf(a, w4.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(a, w4.w, acc[4 * c4 + 3]);
+                }
             }
         }
         if (fast) {
@@ -47,7 +65,7 @@ __global__ void __launch_bounds__(256) smallcin_fwd_kernel(const __grid_constant
             for (int c0 = 0; c0 < COUT; c0 += V) {
                 PackD<T, V> q;
 #pragma unroll
-                for (int j = 0; j < V; ++j) stf(&q.v[j], act_apply(e.act, acc[c0 + j] + bs[c0 + j]));
+                for (int j = 0; j < V; ++j) stf(&q.v[j], act_ct<ACT>(acc[c0 + j] + bs[c0 + j]));
                 *reinterpret_cast<PackD<T, V>*>(o + c0) = q;
             }
         } else {
@@ -136,8 +154,15 @@ int tbi_tapgemm_direct(const tbi_tapgemm* d, cudaStream_t s) {
     long long blocks = (M + 255) / 256;
     const long long cap = (long long)tbi_sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    if (d->dtype == TBI_F32) smallcin_fwd_kernel<float, 16><<<(unsigned)blocks, 256, 0, s>>>(*d);
-    else smallcin_fwd_kernel<__nv_bfloat16, 16><<<(unsigned)blocks, 256, 0, s>>>(*d);
+#define TBI_SMALLCIN(ACTV) do { if (d->dtype == TBI_F32) smallcin_fwd_kernel<float, 16, ACTV><<<(unsigned)blocks, 256, 0, s>>>(*d); \
+                                else smallcin_fwd_kernel<__nv_bfloat16, 16, ACTV><<<(unsigned)blocks, 256, 0, s>>>(*d); } while (0)
+    switch (d->epi.act) {
+        case TBI_ACT_ELU:   TBI_SMALLCIN(TBI_ACT_ELU); break;
+        case TBI_ACT_RELU:  TBI_SMALLCIN(TBI_ACT_RELU); break;
+        case TBI_ACT_LRELU: TBI_SMALLCIN(TBI_ACT_LRELU); break;
+        default:            TBI_SMALLCIN(TBI_ACT_NONE); break;
+    }
+#undef TBI_SMALLCIN
     TBI_CUDA_LAUNCH_CHECK("smallcin_fwd");
     return TBI_OK;
 }

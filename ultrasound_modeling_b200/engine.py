@@ -20,6 +20,7 @@ Design (DESIGN.md has the long form):
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -121,6 +122,9 @@ class Engine:
         self.tdtype = torch.bfloat16 if self.dt == BF16 else torch.float32
         self.impl = impl
         self.N = 0
+        self.overlap_prepare = os.environ.get("TBI_NO_PREP_OVERLAP") is None
+        self._side = None
+        self._prep_pending = False
         self._define_layers()
         if not layout_only:
             self._alloc_params(seed)
@@ -411,8 +415,15 @@ class Engine:
                 if Lr is self.head and self.head_gather:
                     self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 2, Lr.k, Lr.cin, Lr.cout, 64, wp, sc, _ptr(self.head_wg))))
 
+        # weight packing of everything behind the full-resolution stem runs on a side stream, overlapped with the stem's
+        # forward (the pack/fold launches are ~85 tiny grids, ~0.6 ms when serialised in front of the step)
+        stem = ("Conv1", "conv2_1_1", "conv2_1_2")
+        for name in stem:
+            prepare(self.convs[name])
+        self.prep_split = len(self.prog_prepare)
         for Lr in self.convs.values():
-            prepare(Lr)
+            if Lr.name not in stem:
+                prepare(Lr)
 
         def conv_fwd(Lr, h, w, src0, src1, e):
             pk = self.packed[Lr.name]
@@ -460,6 +471,7 @@ class Engine:
         conv_fwd(cv["conv2_1_1"], H, W, view(self.t[0]), None, epi(out=view(self.t[1])))
         conv_fwd(cv["conv2_1_2"], H, W, view(self.t[1]), None, epi(out=view(self.t[2])))
         self.prog_fwd.append((L.tbi_avgpool2x2_fwd, (dt, n, H, W, bref(view(self.t[2])), bref(view(self.pool[0])))))
+        self.fwd_split = len(self.prog_fwd)                  # everything after this needs the side-stream packs
         self.att_desc = []
         for si, info in enumerate(self.stage_info):
             h, w = H >> (si + 1), W >> (si + 1)
@@ -565,7 +577,22 @@ class Engine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def prepare(self):
-        self._run(self.prog_prepare, self.stream())
+        """fold BN and pack the compute copies of the weights.  The stem's (tiny) on the current stream; the rest on a side
+        stream that forward() joins after the stem -- fork and join are event waits, so this also captures into a CUDA graph."""
+        self._run(self.prog_prepare[:self.prep_split], self.stream())
+        if not self.overlap_prepare:
+            self._run(self.prog_prepare[self.prep_split:], self.stream())
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        self._side.wait_stream(torch.cuda.current_stream(self.device))
+        self._run(self.prog_prepare[self.prep_split:], self._side.cuda_stream)
+        self._prep_pending = True
+
+    def _join_prepare(self):
+        if self._prep_pending:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
+            self._prep_pending = False
 
     def draw_dropout(self, seed: int = 0x5EED):
         st = self.stream()
@@ -585,7 +612,9 @@ class Engine:
                 k.copy_(torch.as_tensor(masks[i]).to(device=self.device, dtype=torch.uint8) * 2)
 
     def forward(self):
-        self._run(self.prog_fwd, self.stream())
+        self._run(self.prog_fwd[:self.fwd_split], self.stream())
+        self._join_prepare()
+        self._run(self.prog_fwd[self.fwd_split:], self.stream())
 
     def loss(self):
         self.correct.zero_()
