@@ -256,6 +256,28 @@ int tbi_colsum(int dtype, int64_t npix, const tbi_view* x, float* out, void* str
 /* keep-multiplier (0|2) generation for the always-on dropout (counter-based hash RNG); the stream position is
  * (*step_ptr)*count + i so that a CUDA-graph replay draws a fresh mask each step (step_ptr may be NULL) */
 int tbi_dropout_mask(uint8_t* keep, int64_t count, uint64_t seed, const int32_t* step_ptr, void* stream);
+/* ---- Variant B (ResNest.py / Decoder.py) ---------------------------------------------------------
+ * LayerNormalization over the channel axis (Keras axis=-1, biased variance) fused with the activation
+ * that follows it: y = act(gamma*(x-mean_c)/sqrt(var_c+eps)+beta).  x, y: npix pixel records of c channels
+ * (views; may alias).  Replaces tf.keras.layers.LayerNormalization + LeakyReLU at ResNest.py:86-87,99-101,
+ * 126-127,132-133,166-167 and Decoder.py:112-113,130-131.                                          */
+int tbi_layernorm_c_fwd(int dtype, int64_t npix, int c, const tbi_view* x, const float* gamma, const float* beta,
+                        float eps, int act, const tbi_view* y, void* stream);
+/* backward of the above: x = the LayerNorm INPUT, y = its activated output (for act'), dy -> dx;
+ * dgamma/dbeta are ADDED.                                                                          */
+int tbi_layernorm_c_bwd(int dtype, int64_t npix, int c, const tbi_view* x, const tbi_view* y, const tbi_view* dy,
+                        const float* gamma, float eps, int act, const tbi_view* dx, float* dgamma, float* dbeta,
+                        void* stream);
+/* split attention of ResNest.py:171-199: the R inputs are one and the same tensor U (cardinal.forward :136-147
+ * applies the same conv1/conv2 R times) and dense2 is shared, so V = R * U * a with
+ * a = softmax_c | sigmoid (R==1) of dense2(act(LN(dense1(R * mean_hw U)))).
+ * u, v: [n,h,w,K*c]; w1 [K][c][c/2], b1 [K][c/2], LN gamma/beta [K][c/2], w2 [K][c/2][c], b2 [K][c];
+ * att: fp32 scratch [n][K*c] (holds R*a on return).                                                 */
+int tbi_splitatt_shared_fwd(int dtype, int n, int h, int w, int kpaths, int radix, int c, const tbi_view* u,
+                            const tbi_view* v, const float* w1, const float* b1, const float* ln_gamma,
+                            const float* ln_beta, float ln_eps, int act, const float* w2, const float* b2,
+                            float* att, void* stream);
+
 /* x fp32/fp64 host-layout NHWC -> storage dtype (device to device)                               */
 int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void* src, void* dst, void* stream);
 

@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 LIB_PATH = _PKG / "libtbi_sm100.so"
 HASH_PATH = _PKG / "libtbi_sm100.so.hash"
-SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_halo.cu", "tapwgrad_tc.cu", "tapwgrad_small.cu", "direct_small.cu", "splitatt_fused.cu", "bandwidth.cu"]
+SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_halo.cu", "tapwgrad_tc.cu", "tapwgrad_small.cu", "direct_small.cu", "splitatt_fused.cu", "bandwidth.cu", "variant_b.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -126,6 +126,9 @@ SIGNATURES = {
     "tbi_act_bwd": (_I, [_I, _I64, _I, _PV, _PV, _VP, _PV, _VP]),
     "tbi_accumulate": (_I, [_I, _I64, _PV, _PV, _VP]),
     "tbi_colsum": (_I, [_I, _I64, _PV, _VP, _VP]),
+    "tbi_layernorm_c_fwd": (_I, [_I, _I64, _I, _PV, _VP, _VP, _F, _I, _PV, _VP]),
+    "tbi_layernorm_c_bwd": (_I, [_I, _I64, _I, _PV, _PV, _PV, _VP, _F, _I, _PV, _VP, _VP, _VP]),
+    "tbi_splitatt_shared_fwd": (_I, [_I, _I, _I, _I, _I, _I, _I, _PV, _PV, _VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _VP]),
     "tbi_dropout_mask": (_I, [_VP, _I64, C.c_uint64, _VP, _VP]),
     "tbi_cast": (_I, [_I, _I, _I64, _VP, _VP, _VP]),
     "tbi_adam_multi": (_I, [_I64, _VP, _VP, _VP, _VP, _VP, _F, _F, _F, _F, _F, _VP]),

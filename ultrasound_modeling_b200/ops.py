@@ -101,7 +101,7 @@ def _epi(out, bias=None, act=ACT_NONE, residual=None, keep=None, dact=ACT_NONE, 
 
 # ------------------------------------------------------------------------------------------ Conv2D
 def conv2d(x, w_hwio, bias=None, *, dilation=1, groups=1, bn=None, act=ACT_NONE, residual=None, x2=None,
-           impl=IMPL_AUTO, out_f32=False):
+           impl=IMPL_AUTO, out_f32=False, out=None, out_coff=0):
     """Conv2D(strides=1, padding='SAME') [+ BN-inference] [+ act] [+ residual]; x2 = second source of a
     virtual channel concat.  (TBI_ResNest.py:83-91,140-148,162-170)"""
     L = _lib.lib()
@@ -109,8 +109,10 @@ def conv2d(x, w_hwio, bias=None, *, dilation=1, groups=1, bn=None, act=ACT_NONE,
     k, cout = w_hwio.shape[0], w_hwio.shape[3]
     scale, fbias = fold_bn(cout, bias if bias is not None else torch.zeros(cout, device=x.device), bn, x.device)
     wp = pack_conv(w_hwio, groups, 0, x.dtype, scale)
-    y = torch.empty(n, h, w, cout, dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
+    y = out if out is not None else torch.empty(n, h, w, cout, dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
     e = _epi(y, fbias, act, residual, out_f32=int(out_f32))
+    if out is not None:                       # write channels [out_coff, out_coff+cout) of a wider tensor (concat-free)
+        e.out = view(out, c=cout, coff=out_coff)
     check(L.tbi_conv2d_fwd(_dt(x), impl, n, h, w, k, dilation, groups, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
                            cout, _p(wp), C.byref(e), _st()), "conv2d_fwd")
     return y
@@ -285,3 +287,45 @@ def adam_step(p, g, m, v, step_count, lr, b1=0.9, b2=0.999, eps=1e-7, grad_scale
     L = _lib.lib()
     check(L.tbi_adam_multi(p.numel(), _p(p), _p(g), _p(m), _p(v), _p(step_count), lr, b1, b2, eps, grad_scale, _st()), "adam")
     check(L.tbi_adam_advance(_p(step_count), _st()), "adam_advance")
+
+
+# ------------------------------------------------------------------------------------------ Variant B ops
+LN_EPS = 1e-3
+
+
+def layernorm_c(x, gamma, beta, act=ACT_NONE, eps=LN_EPS, inplace=False, coff=0, c=None):
+    """LayerNormalization over channels + activation (ResNest.py:86-87,99-101,126-133; Decoder.py:112-113,130-131).
+    coff/c: normalise only the channel slice [coff, coff+c) of x (each slice of a concat buffer is its own layer)."""
+    L = _lib.lib()
+    n, h, w, ct = x.shape
+    c = ct if c is None else c
+    y = x if inplace else torch.empty_like(x)
+    check(L.tbi_layernorm_c_fwd(_dt(x), n * h * w, c, _vp(view(x, c=c, coff=coff)), _p(_f32(gamma)), _p(_f32(beta)), eps, act,
+                                _vp(view(y, c=c, coff=coff)), _st()), "layernorm_c_fwd")
+    return y
+
+
+def layernorm_c_bwd(x, y, dy, gamma, act=ACT_NONE, eps=LN_EPS):
+    """-> (dx, dgamma, dbeta); x = LayerNorm input, y = its activated output"""
+    L = _lib.lib()
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.zeros(c, dtype=torch.float32, device=x.device)
+    db = torch.zeros(c, dtype=torch.float32, device=x.device)
+    check(L.tbi_layernorm_c_bwd(_dt(x), n * h * w, c, _vp(view(x)), _vp(view(y)), _vp(view(dy)), _p(_f32(gamma)), eps, act,
+                                _vp(view(dx)), _p(dg), _p(db), _st()), "layernorm_c_bwd")
+    return dx, dg, db
+
+
+def splitatt_shared(u, kpaths, radix, w1, b1, ln_gamma, ln_beta, w2, b2, act, eps=LN_EPS):
+    """Variant-B split attention (ResNest.py:171-199): R identical inputs, shared dense2.  u: [n,h,w,K*c];
+    w1 [K,c,c/2], b1 [K,c/2], ln_gamma/ln_beta [K,c/2], w2 [K,c/2,c], b2 [K,c] (fp32)."""
+    L = _lib.lib()
+    n, h, w, C_ = u.shape
+    c = C_ // kpaths
+    v = torch.empty_like(u)
+    att = torch.empty(n, C_, dtype=torch.float32, device=u.device)
+    args = [_f32(t) for t in (w1, b1, ln_gamma, ln_beta, w2, b2)]
+    check(L.tbi_splitatt_shared_fwd(_dt(u), n, h, w, kpaths, radix, c, _vp(view(u)), _vp(view(v)), _p(args[0]), _p(args[1]), _p(args[2]),
+                                    _p(args[3]), eps, act, _p(args[4]), _p(args[5]), _p(att), _st()), "splitatt_shared_fwd")
+    return v
