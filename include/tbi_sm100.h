@@ -256,6 +256,17 @@ int tbi_colsum(int dtype, int64_t npix, const tbi_view* x, float* out, void* str
 /* keep-multiplier (0|2) generation for the always-on dropout (counter-based hash RNG); the stream position is
  * (*step_ptr)*count + i so that a CUDA-graph replay draws a fresh mask each step (step_ptr may be NULL) */
 int tbi_dropout_mask(uint8_t* keep, int64_t count, uint64_t seed, const int32_t* step_ptr, void* stream);
+/* Grouped convolutions whose per-group channel counts are too small for one tensor-core K step (the cardinal 3x3 convs of
+ * the reference defaults radix=4,kpaths=4: 2, 4, 8 input channels per group; TBI_ResNest.py:157-168) are run as DENSE
+ * convolutions over block-diagonal weights: 16x the flops of the grouped form, still ~50x faster than the CUDA-core path.
+ * tbi_conv_dense_expand says whether a (dtype, groups, cin/group, cout/group) layer is treated that way by
+ * tbi_pack_conv_weights / tbi_conv2d_{fwd,dgrad,wgrad}; tbi_conv_packed_elems is the element count of ONE packed copy
+ * (either mode) the caller must allocate; tbi_conv2d_wgrad_workspace the scratch bytes tbi_conv2d_wgrad needs for it
+ * (0 when not expanded; without the scratch the wgrad falls back to the grouped CUDA-core kernel).               */
+int     tbi_conv_dense_expand(int dtype, int groups, int cin_g, int cout_g);
+int64_t tbi_conv_packed_elems(int dtype, int ksize, int groups, int cin_g, int cout_total);
+int64_t tbi_conv2d_wgrad_workspace(int dtype, int ksize, int groups, int cin_total, int cout_total);
+
 /* ---- Variant B (ResNest.py / Decoder.py) ---------------------------------------------------------
  * LayerNormalization over the channel axis (Keras axis=-1, biased variance) fused with the activation
  * that follows it: y = act(gamma*(x-mean_c)/sqrt(var_c+eps)+beta).  x, y: npix pixel records of c channels

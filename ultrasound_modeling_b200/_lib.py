@@ -126,6 +126,9 @@ SIGNATURES = {
     "tbi_act_bwd": (_I, [_I, _I64, _I, _PV, _PV, _VP, _PV, _VP]),
     "tbi_accumulate": (_I, [_I, _I64, _PV, _PV, _VP]),
     "tbi_colsum": (_I, [_I, _I64, _PV, _VP, _VP]),
+    "tbi_conv_dense_expand": (_I, [_I, _I, _I, _I]),
+    "tbi_conv_packed_elems": (_I64, [_I, _I, _I, _I, _I]),
+    "tbi_conv2d_wgrad_workspace": (_I64, [_I, _I, _I, _I, _I]),
     "tbi_layernorm_c_fwd": (_I, [_I, _I64, _I, _PV, _VP, _VP, _F, _I, _PV, _VP]),
     "tbi_layernorm_c_bwd": (_I, [_I, _I64, _I, _PV, _PV, _PV, _VP, _F, _I, _PV, _VP, _VP, _VP]),
     "tbi_splitatt_shared_fwd": (_I, [_I, _I, _I, _I, _I, _I, _I, _PV, _PV, _VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _VP]),

@@ -611,6 +611,40 @@ __global__ void softmax_loss_kernel(int N, int hw, const float* __restrict__ log
 // ---------------------------------------------------------------------------------------------
 // packing, BN fold / param grads, Adam, misc
 // ---------------------------------------------------------------------------------------------
+// block-diagonal dense expansion of a grouped kernel (tbi_conv_dense_expand): same two layouts as below for groups = 1 over
+// cin_total = groups*cin_g input channels, zero where input and output channel belong to different groups
+template <typename T>
+__global__ void pack_conv_expand_kernel(int mode, int ntaps, int groups, int cin_g, int cout_total, const float* __restrict__ w,
+                                        const float* __restrict__ scale, T* __restrict__ out) {
+    const int cout_g = cout_total / groups, cin = groups * cin_g;
+    const long long total = (long long)ntaps * cin * cout_total;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int tap, ci, co;
+        if (mode == 0) {            // out[co][tap][ci]
+            ci = (int)(i % cin); long long t = i / cin; tap = (int)(t % ntaps); co = (int)(t / ntaps);
+        } else {                    // out[ci][tap'][co]
+            co = (int)(i % cout_total); long long t = i / cout_total; const int tp = (int)(t % ntaps); ci = (int)(t / ntaps);
+            tap = ntaps - 1 - tp;
+        }
+        float v = 0.f;
+        if (ci / cin_g == co / cout_g) {
+            v = w[((size_t)tap * cin_g + ci % cin_g) * cout_total + co];
+            if (scale) v *= scale[co];
+        }
+        stf(out + i, v);
+    }
+}
+
+// dw_hwio[tap][ci_g][co] += dense[tap][g(co)*cin_g + ci_g][co]   (the block-diagonal part of a dense weight gradient)
+__global__ void wgrad_gather_blocks_kernel(int ntaps, int groups, int cin_g, int cout_total, const float* __restrict__ dense, float* dw) {
+    const int cout_g = cout_total / groups, cin = groups * cin_g;
+    const long long total = (long long)ntaps * cin_g * cout_total;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i % cout_total); long long t = i / cout_total; const int cig = (int)(t % cin_g); const int tap = (int)(t / cin_g);
+        dw[i] += dense[((size_t)tap * cin + (size_t)(co / cout_g) * cin_g + cig) * cout_total + co];
+    }
+}
+
 template <typename T>
 __global__ void pack_conv_kernel(int mode, int ntaps, int groups, int cin_g, int cout_total, const float* __restrict__ w,
                                  const float* __restrict__ scale, T* __restrict__ out) {
@@ -1052,11 +1086,23 @@ extern "C" int tbi_pack_conv_weights(int dtype, int mode, int ksize, int groups,
     TBI_CHECK(groups >= 1 && cout_total % groups == 0, TBI_ERR_BAD_SHAPE, "pack_conv: groups");
     cudaStream_t s = (cudaStream_t)stream;
     const int ntaps = ksize * ksize;
+    if (tbi_conv_dense_expand(dtype, groups, cin_g, cout_total / groups)) {
+        const unsigned ge = grid_for((long long)ntaps * groups * cin_g * cout_total, 256);
+        pack_conv_expand_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>(mode, ntaps, groups, cin_g, cout_total, w_hwio, scale, (__nv_bfloat16*)out);
+        TBI_CUDA_LAUNCH_CHECK("pack_conv_expand");
+        return TBI_OK;
+    }
     const unsigned g = grid_for((long long)ntaps * cin_g * cout_total, 256);
     if (dtype == TBI_F32) pack_conv_kernel<float><<<g, 256, 0, s>>>(mode, ntaps, groups, cin_g, cout_total, w_hwio, scale, (float*)out);
     else if (dtype == TBI_BF16) pack_conv_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(mode, ntaps, groups, cin_g, cout_total, w_hwio, scale, (__nv_bfloat16*)out);
     else return tbi_set_error(TBI_ERR_UNSUPPORTED, "pack dtype");
     TBI_CUDA_LAUNCH_CHECK("pack_conv");
+    return TBI_OK;
+}
+
+int tbi_wgrad_gather_blocks(int ntaps, int groups, int cin_g, int cout_total, const float* dense, float* dw, cudaStream_t s) {
+    wgrad_gather_blocks_kernel<<<grid_for((long long)ntaps * cin_g * cout_total, 256), 256, 0, s>>>(ntaps, groups, cin_g, cout_total, dense, dw);
+    TBI_CUDA_LAUNCH_CHECK("wgrad_gather_blocks");
     return TBI_OK;
 }
 

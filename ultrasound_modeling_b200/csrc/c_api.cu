@@ -2,6 +2,7 @@
 // convolution entry points (which expand into tap-GEMM descriptors) and implementation dispatch.
 #include "tbi_common.cuh"
 #include <string.h>
+#include <stdlib.h>
 #include <mutex>
 
 static thread_local char g_err[512] = "";
@@ -74,6 +75,24 @@ static int fill_conv_taps(int ksize, int dilation, int* dy, int* dx) {
     return n;
 }
 
+// see include/tbi_sm100.h.  Expanded when the grouped form cannot use the tensor cores in some direction (K per group not a
+// multiple of 16) while the dense form can, and the dense layer stays small.
+extern "C" int tbi_conv_dense_expand(int dtype, int groups, int cin_g, int cout_g) {
+    static const bool off = getenv("TBI_NO_DENSE_EXPAND") != nullptr;
+    if (off || dtype != TBI_BF16 || groups <= 1) return 0;
+    if (cin_g % 16 == 0 && cout_g % 16 == 0) return 0;                       // grouped form is tensor-core eligible both ways
+    const int cin = groups * cin_g, cout = groups * cout_g;
+    return (cin % 16 == 0 && cout % 16 == 0 && cin <= 256 && cout <= 1024) ? 1 : 0;
+}
+extern "C" int64_t tbi_conv_packed_elems(int dtype, int ksize, int groups, int cin_g, int cout_total) {
+    const int64_t grouped = (int64_t)ksize * ksize * cin_g * cout_total;
+    return tbi_conv_dense_expand(dtype, groups, cin_g, cout_total / (groups > 0 ? groups : 1)) ? grouped * groups : grouped;
+}
+extern "C" int64_t tbi_conv2d_wgrad_workspace(int dtype, int ksize, int groups, int cin_total, int cout_total) {
+    if (groups <= 1 || !tbi_conv_dense_expand(dtype, groups, cin_total / groups, cout_total / groups)) return 0;
+    return (int64_t)ksize * ksize * cin_total * cout_total * (int64_t)sizeof(float);
+}
+
 static int check_conv_args(int ksize, int dilation) {
     TBI_CHECK(ksize == 1 || ksize == 3, TBI_ERR_UNSUPPORTED, "conv2d: ksize %d (1 or 3)", ksize);
     TBI_CHECK(dilation == 1 || dilation == 2 || dilation == 4 || dilation == 8, TBI_ERR_UNSUPPORTED, "conv2d: dilation %d", dilation);
@@ -91,6 +110,7 @@ extern "C" int tbi_conv2d_fwd(int dtype, int impl, int n, int h, int w, int ksiz
     const int cin = src0->c + ((src1 && src1->ptr) ? src1->c : 0);
     TBI_CHECK(cin % groups == 0, TBI_ERR_BAD_SHAPE, "conv2d_fwd: cin %d %% groups %d", cin, groups);
     d.cin_g = cin / groups; d.cout_g = cout_total / groups;
+    if (tbi_conv_dense_expand(dtype, groups, d.cin_g, d.cout_g)) { d.groups = 1; d.cin_g = cin; d.cout_g = cout_total; }   // block-diagonal pack
     d.in_stride = 1; d.ntaps = fill_conv_taps(ksize, dilation, d.dy, d.dx);
     d.w = w_packed; d.epi = *epi;
     if (d.epi.out_stride == 0) d.epi.out_stride = 1;
@@ -107,6 +127,7 @@ extern "C" int tbi_conv2d_dgrad(int dtype, int impl, int n, int h, int w, int ks
     d.src[0] = *dz;
     d.cin_g = dz->c / groups;            // K side = forward output channels
     d.cout_g = cin_total / groups;       // produced = forward input channels
+    if (tbi_conv_dense_expand(dtype, groups, d.cout_g, d.cin_g)) { d.groups = 1; d.cin_g = dz->c; d.cout_g = cin_total; }
     d.in_stride = 1; d.ntaps = fill_conv_taps(ksize, dilation, d.dy, d.dx);
     d.w = w_packed_dgrad; d.epi = *epi;
     if (d.epi.out_stride == 0) d.epi.out_stride = 1;
@@ -129,6 +150,18 @@ extern "C" int tbi_conv2d_wgrad(int dtype, int impl, int n, int h, int w, int ks
     d.dw = dw_hwio;
     d.tap_stride = (int64_t)d.cin_g * dz->c; d.ci_stride = dz->c; d.co_stride = 1;
     d.dbias = dbias; d.workspace = workspace; d.workspace_bytes = workspace_bytes;
+    const int64_t need = tbi_conv2d_wgrad_workspace(dtype, ksize, groups, cin, dz->c);
+    if (need > 0 && workspace && workspace_bytes >= need && impl != TBI_IMPL_SIMT) {
+        // dense weight gradient into the scratch, then its block-diagonal part is added to the grouped HWIO gradient
+        cudaStream_t s = (cudaStream_t)stream;
+        if (cudaMemsetAsync(workspace, 0, (size_t)need, s) != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "conv2d_wgrad: memset");
+        tbi_tapwgrad e = d;
+        e.groups = 1; e.cin_g = cin; e.cout_g = dz->c;
+        e.dw = (float*)workspace; e.tap_stride = (int64_t)cin * dz->c; e.ci_stride = dz->c; e.co_stride = 1;
+        e.workspace = nullptr; e.workspace_bytes = 0;
+        rc = tbi_tapwgrad_run(&e, stream); if (rc) return rc;
+        return tbi_wgrad_gather_blocks(d.ntaps, groups, d.cin_g, dz->c, (const float*)workspace, dw_hwio, s);
+    }
     return tbi_tapwgrad_run(&d, stream);
 }
 

@@ -346,12 +346,17 @@ class Engine:
         # packed compute weights + folded BN
         esz = 2 if self.dt == BF16 else 4
         self.packed = {}
+        ws_need = 0
         for L in self.convs.values():
             nel = L.k * L.k * L.cin_g * L.cout
+            if L.kind == "conv":          # small-group convs are packed as block-diagonal dense kernels (tbi_conv_dense_expand)
+                nel = int(self.L.tbi_conv_packed_elems(self.dt, L.k, L.groups, L.cin_g, L.cout))
+                ws_need = max(ws_need, int(self.L.tbi_conv2d_wgrad_workspace(self.dt, L.k, L.groups, L.cin, L.cout)))
             nel_b = L.k * L.k * L.cin * self.dl_c if L is self.head else nel
             self.packed[L.name] = dict(wf=torch.empty(nel, dtype=td, device=dev), wb=torch.empty(nel_b, dtype=td, device=dev),
                                        scale=torch.empty(L.cout, dtype=torch.float32, device=dev),
                                        fbias=torch.empty(L.cout, dtype=torch.float32, device=dev))
+        self.wgrad_ws = torch.empty(ws_need, dtype=torch.uint8, device=dev) if ws_need else None
         self._assemble()
 
     # -- program assembly helpers: each appends (fn, args) ; stream is appended at call time
@@ -441,7 +446,8 @@ class Engine:
             pk = self.packed[Lr.name]
             dw, db = _ptr(self.g(Lr.name + "/w")), _ptr(self.g(Lr.name + "/b"))
             if Lr.kind == "conv":
-                wargs = [dt, impl, n, h, w, Lr.k, 1, Lr.groups, bref(x0), bref(x1) if x1 is not None else None, bref(dz), dw, db, None, 0]
+                wargs = [dt, impl, n, h, w, Lr.k, 1, Lr.groups, bref(x0), bref(x1) if x1 is not None else None, bref(dz), dw, db,
+                         _ptr(self.wgrad_ws) if self.wgrad_ws is not None else None, self.wgrad_ws.numel() if self.wgrad_ws is not None else 0]
                 self.prog_bwd.append((L.tbi_conv2d_wgrad, wargs))
             else:
                 wargs = [dt, impl, n, h, w, Lr.k, bref(x0), bref(x1) if x1 is not None else None, bref(dz), Lr.cout, dw, db, None, 0]
@@ -631,16 +637,20 @@ class Engine:
         check(self.L.tbi_adam_advance(self.step_count.data_ptr(), st), "adam_advance")
 
     def launches_per_step(self, train: bool = True) -> int:
-        """kernel launches of one step (conv entry points expand: convT fwd = 4 phase launches, convT wgrad = wgrad + colsum,
-        split-attention fwd = 3 (+memset), bwd = 4 (+memset))."""
+        """kernel launches of one step as the tensor-core build issues them (checked against the ncu launch list in
+        profiles/): conv / convT wgrad = wgrad kernel + bias column sum (the 1->16 stem wgrad does both in one kernel; a
+        block-diagonal-expanded grouped conv adds the gather), split-attention fwd = 1 fused kernel, bwd = fused kernel +
+        parameter-gradient kernel; everything else is one kernel per entry point.  Memsets are not counted."""
         def count(prog):
             c = 0
-            for fn, _ in prog:
+            for fn, args in prog:
                 nm = fn.__name__
-                c += {"tbi_conv2d_transpose_s2_fwd": 4, "tbi_conv2d_transpose_s2_wgrad": 2, "tbi_split_attention_fwd": 3,
-                      "tbi_split_attention_bwd": 4}.get(nm, 1)
+                k = {"tbi_conv2d_transpose_s2_wgrad": 2, "tbi_conv2d_wgrad": 2, "tbi_split_attention_bwd": 2}.get(nm, 1)
+                if nm == "tbi_conv2d_wgrad" and args[-1] and self.L.tbi_conv2d_wgrad_workspace(args[0], args[5], args[7], args[8]._obj.c, args[10]._obj.c):
+                    k += 1
+                c += k
             return c
         n = count(self.prog_prepare) + count(self.prog_fwd) + count(self.prog_loss)
         if train:
-            n += count(self.prog_bwd) + 2 + sum(1 for k in self.keep if k is not None)
+            n += count(self.prog_bwd) + 2 + sum(1 for k in self.keep if k is not None) - 1     # -1: the stem wgrad needs no separate column sum
         return n

@@ -66,7 +66,8 @@ def pack_conv(w_hwio: torch.Tensor, groups: int, mode: int, dtype: torch.dtype, 
     L = _lib.lib()
     k, _, cin_g, cout = w_hwio.shape
     w32 = _f32(w_hwio)
-    out = torch.empty(w32.numel(), dtype=dtype, device=w32.device)
+    dtc = F32 if dtype == torch.float32 else BF16
+    out = torch.empty(int(L.tbi_conv_packed_elems(dtc, k, groups, cin_g, cout)), dtype=dtype, device=w32.device)
     check(L.tbi_pack_conv_weights(F32 if dtype == torch.float32 else BF16, mode, k, groups, cin_g, cout, _p(w32), _p(scale), _p(out), _st()), "pack_conv")
     return out
 
@@ -128,8 +129,10 @@ def conv2d_grads(x, w_hwio, dz, *, dilation=1, groups=1, scale=None, x2=None, im
     cin = c0 + (x2.shape[3] if x2 is not None else 0)
     dw = torch.zeros(w_hwio.shape, dtype=torch.float32, device=x.device)
     db = torch.zeros(cout, dtype=torch.float32, device=x.device)
+    wsb = int(L.tbi_conv2d_wgrad_workspace(_dt(x), k, groups, cin, cout))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=x.device) if wsb else None
     check(L.tbi_conv2d_wgrad(_dt(x), impl if wgrad_impl is None else wgrad_impl, n, h, w, k, dilation, groups, _vp(view(x)), _vp(view(x2)) if x2 is not None else None,
-                             _vp(view(dz)), _p(dw), _p(db), None, 0, _st()), "conv2d_wgrad")
+                             _vp(view(dz)), _p(dw), _p(db), _p(ws), wsb, _st()), "conv2d_wgrad")
     if not need_dx:
         return None, dw, db
     wb = pack_conv(w_hwio, groups, 1, x.dtype, scale)
