@@ -132,6 +132,29 @@ def test_forward_backward_parity_bf16(ResNest):
     assert not bad, bad[-5:]
 
 
+def test_forward_backward_parity_bf16_r4k4(ResNest):
+    """reference defaults radix=4, kpaths=4 in bf16: the cardinal 3x3 convs have 2/4/8 channels per group and run as
+    block-diagonal dense convolutions on the tensor-core path (tbi_conv_dense_expand); same bars as the r2k1 bf16 test."""
+    from ultrasound_modeling_b200 import _lib
+    assert _lib.lib().tbi_conv_dense_expand(_lib.BF16, 16, 2, 8) == 1 and _lib.lib().tbi_conv_dense_expand(_lib.BF16, 16, 16, 64) == 0
+    o, net = build_pair(ResNest, 64, 4, 4, "bf16")
+    x, y = O.synthetic_batch(2, 64, 64)
+    masks = O.dropout_masks(2, 64, 64)
+    check_step(o, net, x, y, masks, 2e-2, 2e-2, min_agree=0.99)
+    e = net.engine
+    _, inter = o.forward(x.double(), masks, return_intermediates=True)
+    n_units = sum(t.numel() for t in e.up)
+    sync_relu_ties(net, inter, max_flips=int(0.01 * n_units), tie_tol=1e-2)
+    e.backward()
+    got = e.grad_dict()
+    want = o.gradients(x.double(), y.double(), masks)
+    errs2 = sorted((rel2(got[k], want[k]), k) for k in want)
+    errs = sorted((rel(got[k], want[k]), k) for k in want)
+    print("bf16 r4k4 gradient parity: 2-norm worst", errs2[-3:], "| max-norm worst", errs[-3:])
+    assert errs2[-1][0] < 2e-2, errs2[-5:]
+    assert errs[-1][0] < 3e-2, errs[-5:]
+
+
 def test_config1_256x256_batch2_fp32(ResNest):
     """BASELINE.json configs[0]: batch 2, 1x256x256 frames, reference defaults radix=4,kpaths=4."""
     o, net = build_pair(ResNest, 256, 4, 4, "fp32")
