@@ -188,29 +188,35 @@ def run_ours(args):
 
     out = None
     if rank == 0:
-        # ---- dominant kernel, timed live: upsample_1's transposed conv (fwd), 4 phase launches per call
+        # ---- dominant kernel, timed live: the persistent halo tap-GEMM (tapgemm_halo_kernel<128>, ~19 % of the step) on its
+        # longest launch of the step, upsample_4's transposed conv forward (one 4-phase launch).  Algorithmic flops per launch
+        # = 2 * N*h*w * 16 taps * Cin * Cout; `traffic` = dram read+write bytes of that launch from the ncu
+        # --set full capture summarised in profiles/r1_ncu_upsample4_fwd.md (same shape; scaled by batch if --batch differs).
         st = torch.cuda.current_stream().cuda_stream
-        name = "upsample_1"
+        name = "upsample_4"
         calls = [(fn, a) for fn, a in e.prog_fwd if fn.__name__ == "tbi_conv2d_transpose_s2_fwd"]
-        fn, a = calls[1]
-        h, w, cin, cout = args.size >> 5, args.size >> 5, 1024, 512
+        fn, a = calls[4]
+        h, w, cin, cout = args.size >> 2, args.size >> 2, 320, 128
         flops_call = 2.0 * B * h * w * 16 * cin * cout
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         for _ in range(3):
             fn(*a, st)
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 20
-        k0.record()
-        for _ in range(reps):
-            fn(*a, st)
-        k1.record(); torch.cuda.synchronize()
-        kms = k0.elapsed_time(k1) / reps
+        reps, kms = 10, 0.0
+        for _ in range(reps):                                   # L2 flushed between launches: each launch is timed cold, as in the step
+            flush.zero_()
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record(); fn(*a, st); k1.record(); torch.cuda.synchronize()
+            kms += k0.elapsed_time(k1) / reps
+        del flush
         ach = flops_call / (kms / 1e3) / 1e12
-        peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+        peak = pk["bf16_tflops"]                                 # burst figure: this kernel is timed alone (B200_PROFILING.md)
+        peak_sus = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])   # sustained figure: for the whole step
         step_flops = 3.0 * O.forward_flops_per_image(args.size, args.size, 1, 3, 3, args.radix, args.kpaths) * B
-        roof = {"bound": "tensor", "kernel": f"{name} Conv2DTranspose k4 s2 fwd [{B},{h},{w},{cin}]->[{B},{2*h},{2*w},{cout}] (4 phase launches)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": pk_kind + " (sustained bf16)",
-                "ms_per_call": kms, "step_tflops": step_flops * world * args.steps / (ms / 1e3) / 1e12 / world,
-                "step_frac_of_peak": step_flops * args.steps / (ms / 1e3) / 1e12 / peak}
+        traffic = 397.05e6 * (B / 64.0) * (args.size / 256.0) ** 2 if args.dtype == "bf16" else None
+        roof = {"bound": "tensor", "kernel": f"tapgemm_halo_kernel<128>: {name} Conv2DTranspose k4 s2 fwd [{B},{h},{w},{cin}]->[{B},{2*h},{2*w},{cout}] (one 4-phase launch)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": pk_kind + " (burst bf16, kernel timed alone with L2 flushed between launches)",
+                "ms_per_call": kms, "flops_per_call": flops_call, "step_tflops": step_flops * world * args.steps / (ms / 1e3) / 1e12 / world,
+                "step_frac_of_peak_sustained": step_flops * args.steps / (ms / 1e3) / 1e12 / peak_sus}
         cpu_val, cores, sample = cpu_oracle_rate(args.radix, args.kpaths, args.size, seconds=args.cpu_seconds)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

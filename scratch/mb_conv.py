@@ -33,6 +33,14 @@ elif case == "up3":         # upsample_3: convT 640->256 at 32x32
     x1 = rnd(64, 32, 32, 512); x2 = rnd(64, 32, 32, 128); w = torch.randn(4, 4, 256, 640, device="cuda") * 0.02; b = torch.zeros(256, device="cuda")
     f = lambda: ops.conv2d_transpose_s2(x1, w, b, act=ops._lib.ACT_RELU, x2=x2)
     flops = 2 * 64 * 32 * 32 * 16 * 640 * 256; bytes_ = (x1.numel() + x2.numel() + 64 * 64 * 64 * 256) * 2
+elif case == "up4":         # upsample_4: convT 320->128 at 64x64 (the slowest forward launch of the step)
+    x1 = rnd(64, 64, 64, 256); x2 = rnd(64, 64, 64, 64); w = torch.randn(4, 4, 128, 320, device="cuda") * 0.02; b = torch.zeros(128, device="cuda")
+    f = lambda: ops.conv2d_transpose_s2(x1, w, b, act=ops._lib.ACT_RELU, x2=x2)
+    flops = 2 * 64 * 64 * 64 * 16 * 320 * 128; bytes_ = (x1.numel() + x2.numel() + 64 * 128 * 128 * 128) * 2
+elif case == "up2":         # upsample_2: convT 768->512 at 16x16
+    x1 = rnd(64, 16, 16, 512); x2 = rnd(64, 16, 16, 256); w = torch.randn(4, 4, 512, 768, device="cuda") * 0.02; b = torch.zeros(512, device="cuda")
+    f = lambda: ops.conv2d_transpose_s2(x1, w, b, act=ops._lib.ACT_RELU, x2=x2)
+    flops = 2 * 64 * 16 * 16 * 16 * 768 * 512; bytes_ = (x1.numel() + x2.numel() + 64 * 32 * 32 * 512) * 2
 elif case == "wstem":       # wgrad of conv2_1_2
     x = rnd(64, 256, 256, 32); dz = rnd(64, 256, 256, 32); w = torch.zeros(3, 3, 32, 32, device="cuda")
     f = lambda: ops.conv2d_grads(x, w, dz, need_dx=False)
