@@ -45,6 +45,18 @@ elif case == "wstem":       # wgrad of conv2_1_2
     x = rnd(64, 256, 256, 32); dz = rnd(64, 256, 256, 32); w = torch.zeros(3, 3, 32, 32, device="cuda")
     f = lambda: ops.conv2d_grads(x, w, dz, need_dx=False)
     flops = 2 * 64 * 256 * 256 * 9 * 32 * 32; bytes_ = x.numel() * 2 * 2
+elif case == "wup4":        # wgrad of upsample_4
+    x1 = rnd(64, 64, 64, 256); x2 = rnd(64, 64, 64, 64); dz = rnd(64, 128, 128, 128); w = torch.zeros(4, 4, 128, 320, device="cuda")
+    f = lambda: ops.conv2d_transpose_s2_grads(x1, w, dz, x2=x2, need_dx=False)
+    flops = 2 * 64 * 64 * 64 * 16 * 320 * 128; bytes_ = (x1.numel() + x2.numel() + dz.numel()) * 2
+elif case == "wup2":        # wgrad of upsample_2
+    x1 = rnd(64, 16, 16, 512); x2 = rnd(64, 16, 16, 256); dz = rnd(64, 32, 32, 512); w = torch.zeros(4, 4, 512, 768, device="cuda")
+    f = lambda: ops.conv2d_transpose_s2_grads(x1, w, dz, x2=x2, need_dx=False)
+    flops = 2 * 64 * 16 * 16 * 16 * 768 * 512; bytes_ = (x1.numel() + x2.numel() + dz.numel()) * 2
+elif case == "wcc3":        # wgrad of concats_2 stage 3: 3x3 128->256 at 32x32
+    x = rnd(64, 32, 32, 128); dz = rnd(64, 32, 32, 256); w = torch.zeros(3, 3, 128, 256, device="cuda")
+    f = lambda: ops.conv2d_grads(x, w, dz, need_dx=False)
+    flops = 2 * 64 * 32 * 32 * 9 * 128 * 256; bytes_ = (x.numel() + dz.numel()) * 2
 elif case == "wup3":        # wgrad of upsample_3
     x1 = rnd(64, 32, 32, 512); x2 = rnd(64, 32, 32, 128); dz = rnd(64, 64, 64, 256); w = torch.zeros(4, 4, 256, 640, device="cuda")
     f = lambda: ops.conv2d_transpose_s2_grads(x1, w, dz, x2=x2, need_dx=False)

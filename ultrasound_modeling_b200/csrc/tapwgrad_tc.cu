@@ -8,13 +8,17 @@
 // exactly the canonical MN-major SW128 UMMA layout (atom = 64 channels x 8 pixels; SBO = 1024 B between
 // 8-pixel groups; LBO = one box = 8192 B between 64-channel blocks).  Shifted / stride-2 taps are box
 // coordinates, out-of-image pixels are zero-filled by TMA (== they contribute nothing).
-// One CTA owns one (tap, 128-ci, BN-co) tile of dw and a contiguous range of pixel tiles (split-K); the
-// partial result is reduced into the fp32 gradient with red.global.add (caller zeroes dw).
+// One CTA owns T taps x one (128-ci, BN-co) tile of dw -- T accumulators side by side in TMEM -- and a contiguous range of
+// pixel tiles (split-K); the partial results are reduced into the fp32 gradient with red.global.add (caller zeroes dw).
+// T > 1 when the taps of the group read one operand at the same pixels (a transposed conv's taps all read the same input
+// pixels; a stride-1 conv's taps all read the same output-gradient pixels): that operand is loaded once per K-step and the
+// L2->shared-memory stream per MMA drops from 32 KB to ~20 KB (the T = 1 kernel sat on that stream: 64 flop/B).
 // Warp roles as in tapgemm_tc.cu.
 #include "tbi_common.cuh"
 #include "tc_common.cuh"
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -45,13 +49,17 @@ __device__ __forceinline__ void wg_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-template <int NB>
+__host__ __device__ constexpr int wg_pow2(int v) { return v <= 32 ? 32 : v <= 64 ? 64 : v <= 128 ? 128 : v <= 256 ? 256 : 512; }
+
+template <int NB, int T, bool SHARE_A>
 __global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_constant__ TcWgradParams p) {
     constexpr int BN = 64 * NB;
+    constexpr int TCOLS = wg_pow2(T * BN);
+    constexpr int A_BOXES = SHARE_A ? 2 : 2 * T, B_BOXES = SHARE_A ? NB * T : NB;      // boxes per stage (T == 1: 2 and NB)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     const int stages = p.stages;
-    constexpr uint32_t STAGE_BYTES = (2 + NB) * BOX_BYTES;
+    constexpr uint32_t STAGE_BYTES = (A_BOXES + B_BOXES) * BOX_BYTES;
     uint8_t* bar_base = smem + (size_t)stages * STAGE_BYTES;
     uint64_t* full = reinterpret_cast<uint64_t*>(bar_base);
     uint64_t* empty = full + stages;
@@ -65,14 +73,14 @@ __global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_co
         tc::mbar_init(tfull, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc<BN>(tslot);
+    if (warp == 1) tc::tmem_alloc<TCOLS>(tslot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tslot;
 
     int t = blockIdx.x;
-    const int tap = t % p.ntaps; t /= p.ntaps;
+    const int tap = (t % (p.ntaps / T)) * T; t /= (p.ntaps / T);          // first tap of this CTA's group
     const int co_t = t % p.co_tiles; const int ci_t = t / p.co_tiles;
     const int g = blockIdx.z;
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
@@ -102,13 +110,19 @@ __global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_co
                 const int x0 = tix * tw, y0 = tiy * th, n0 = tib * tn;
                 uint8_t* st = smem + (size_t)s * STAGE_BYTES;
                 tc::mbar_expect_tx(&full[s], STAGE_BYTES);
+                // stage layout: [A boxes: (tap,) 64-ci block][B boxes: (tap,) 64-co block]; the shared operand has one copy
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                    tc::tma_load_5d(st + j * BOX_BYTES, &p.a[asrc[j]], &full[s], ach[j], x0 + (int)p.aqx[tap], 0, y0 + (int)p.aqy[tap], n0);
+                for (int tt2 = 0; tt2 < (SHARE_A ? 1 : T); ++tt2)
 #pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    tc::tma_load_5d(st + (2 + j) * BOX_BYTES, &p.b, &full[s], p.b_cbase + g * p.cout_g + co0 + 64 * j + (int)p.bax[tap] * p.b_cpix,
-                                    x0 + (int)p.bqx[tap], (int)p.bay[tap], y0 + (int)p.bqy[tap], n0);
+                    for (int j = 0; j < 2; ++j)
+                        tc::tma_load_5d(st + (tt2 * 2 + j) * BOX_BYTES, &p.a[asrc[j]], &full[s], ach[j], x0 + (int)p.aqx[tap + tt2], 0, y0 + (int)p.aqy[tap + tt2], n0);
+#pragma unroll
+                for (int tt2 = 0; tt2 < (SHARE_A ? T : 1); ++tt2)
+#pragma unroll
+                    for (int j = 0; j < NB; ++j)
+                        tc::tma_load_5d(st + (A_BOXES + tt2 * NB + j) * BOX_BYTES, &p.b, &full[s],
+                                        p.b_cbase + g * p.cout_g + co0 + 64 * j + (int)p.bax[tap + tt2] * p.b_cpix,
+                                        x0 + (int)p.bqx[tap + tt2], (int)p.bay[tap + tt2], y0 + (int)p.bqy[tap + tt2], n0);
             }
         }
         __syncwarp();
@@ -121,13 +135,17 @@ __global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_co
                 wg_wait(&full[s], ((uint32_t)(it / stages)) & 1u);
                 tc::tc_fence_after();
                 const uint32_t a_addr = tc::smem_u32(smem + (size_t)s * STAGE_BYTES);
-                const uint32_t b_addr = a_addr + 2 * BOX_BYTES;
+                const uint32_t b_addr = a_addr + A_BOXES * BOX_BYTES;
 #pragma unroll
-                for (int k = 0; k < KP / 16; ++k) {
-                    // 16 pixels = 2 swizzle atoms along K: +2048 B per step; LBO = box (next 64 channels), SBO = 1024 B
-                    const uint64_t da = tc::make_smem_desc(a_addr + k * 2048, BOX_BYTES, 1024, 2u);
-                    const uint64_t db = tc::make_smem_desc(b_addr + k * 2048, BOX_BYTES, 1024, 2u);
-                    tc::umma_bf16(tmem_base, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                for (int tt2 = 0; tt2 < T; ++tt2) {
+                    const uint32_t a_t = a_addr + (SHARE_A ? 0 : tt2 * 2) * BOX_BYTES, b_t = b_addr + (SHARE_A ? tt2 * NB : 0) * BOX_BYTES;
+#pragma unroll
+                    for (int k = 0; k < KP / 16; ++k) {
+                        // 16 pixels = 2 swizzle atoms along K: +2048 B per step; LBO = box (next 64 channels), SBO = 1024 B
+                        const uint64_t da = tc::make_smem_desc(a_t + k * 2048, BOX_BYTES, 1024, 2u);
+                        const uint64_t db = tc::make_smem_desc(b_t + k * 2048, BOX_BYTES, 1024, 2u);
+                        tc::umma_bf16(tmem_base + tt2 * BN, da, db, idesc, (it | k) != 0 ? 1u : 0u);
+                    }
                 }
                 tc::umma_commit(&empty[s]);
             }
@@ -142,24 +160,27 @@ __global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_co
         wg_wait(tfull, 0);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* base = p.dw + (size_t)tap * p.tap_stride + (size_t)ci * p.ci_stride;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            uint32_t r[32];
-            tc::tmem_ld32(taddr + c, r);
-            tc::tmem_ld_wait();
-            if (row_ok) {
+        for (int tt2 = 0; tt2 < T; ++tt2) {
+            float* base = p.dw + (size_t)(tap + tt2) * p.tap_stride + (size_t)ci * p.ci_stride;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                tc::tmem_ld32(taddr + tt2 * BN + c, r);
+                tc::tmem_ld_wait();
+                if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int co = co0 + c + j;
-                    if (co < p.cout_g) atomicAdd(base + (size_t)(g * p.cout_g + co) * p.co_stride, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; ++j) {
+                        const int co = co0 + c + j;
+                        if (co < p.cout_g) atomicAdd(base + (size_t)(g * p.cout_g + co) * p.co_stride, __uint_as_float(r[j]));
+                    }
                 }
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 1) tc::tmem_dealloc<BN>(tmem_base);
+    if (warp == 1) tc::tmem_dealloc<TCOLS>(tmem_base);
 }
 
 bool wg_aligned_view(const tbi_view& v) {
@@ -187,13 +208,13 @@ int wg_act_tmap(CUtensorMap* out, const tbi_view& v, int n, int stride, int tw, 
     return tbi_make_tmap_bf16(out, base, 5, dims, strides, box, 128);
 }
 
-template <int NB>
+template <int NB, int T, bool SHARE_A>
 int launch_wg(const TcWgradParams& p, dim3 grid, size_t smem, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tapwgrad_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tapwgrad_tc_kernel<NB, T, SHARE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (attr_err != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    tapwgrad_tc_kernel<NB><<<grid, WG_THREADS, smem, s>>>(p);
+    tapwgrad_tc_kernel<NB, T, SHARE_A><<<grid, WG_THREADS, smem, s>>>(p);
     TBI_CUDA_LAUNCH_CHECK("tapwgrad_tc");
     return TBI_OK;
 }
@@ -261,21 +282,51 @@ int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s) {
     rc = wg_act_tmap(&p.b, d->b_src, d->n, d->b_stride, tw, th, tn, &p.b_cbase, &p.b_cpix); if (rc) return rc;
     p.dw = d->dw; p.tap_stride = d->tap_stride; p.ci_stride = d->ci_stride; p.co_stride = d->co_stride;
 
+    // tap groups: T taps per CTA when they share one operand's pixels (see the header comment) and the layer is big enough to
+    // be bound by the operand stream (both channel counts >= 64)
+    static const bool no_multi = getenv("TBI_WGRAD_NO_MULTITAP") != nullptr;
+    int T = 1; bool share_a = true;
+    if (!no_multi && d->cin_g >= 64 && d->cout_g >= 64 && d->ntaps > 1) {
+        bool a_same = true, b_same = true;
+        for (int t = 1; t < d->ntaps; ++t) {
+            a_same = a_same && p.aqy[t] == p.aqy[0] && p.aqx[t] == p.aqx[0];
+            b_same = b_same && p.bqy[t] == p.bqy[0] && p.bqx[t] == p.bqx[0] && p.bay[t] == p.bay[0] && p.bax[t] == p.bax[0];
+        }
+        if ((a_same || b_same) && d->ntaps % 4 == 0) T = 4;
+        else if ((a_same || b_same) && d->ntaps % 3 == 0) T = 3;
+        share_a = a_same;
+    }
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
-    const long long out_tiles = (long long)d->ntaps * p.ci_tiles * p.co_tiles * d->groups;
-    long long ksplit = (4LL * tbi_sm_count() + out_tiles - 1) / out_tiles;      // ~4 CTAs per SM in flight overall
+    const long long out_tiles = (long long)(d->ntaps / T) * p.ci_tiles * p.co_tiles * d->groups;
+    long long ksplit = (4LL * tbi_sm_count() + out_tiles - 1) / out_tiles;      // T = 1: ~4 CTAs per SM in flight overall
+    if (T > 1) {
+        // one CTA per SM (it owns all of TMEM): pick the split-K factor that fills whole waves of SMs best, keeping at least
+        // 8 K-steps per CTA so the 64K-atomic epilogue stays small next to the main loop
+        const long long sms = tbi_sm_count();
+        long long cap = total_tiles / 8; if (cap < 1) cap = 1; if (cap > 16) cap = 16;
+        double best = -1.0; ksplit = 1;
+        for (long long ks = 1; ks <= cap; ++ks) {
+            const long long ctas = out_tiles * ks, waves = (ctas + sms - 1) / sms;
+            const double eff = (double)ctas / (double)(waves * sms);
+            if (eff > best + 0.02) { best = eff; ksplit = ks; }
+        }
+    }
     if (ksplit > total_tiles) ksplit = total_tiles;
     if (ksplit < 1) ksplit = 1;
     p.tiles_per_cta = (int)((total_tiles + ksplit - 1) / ksplit);
     ksplit = (total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
-    const uint32_t stage_bytes = (2 + p.nb) * BOX_BYTES;
-    int stages = (int)(96 * 1024 / stage_bytes);
+    const uint32_t stage_bytes = (T == 1 ? (2 + p.nb) : share_a ? (2 + T * p.nb) : (2 * T + p.nb)) * BOX_BYTES;
+    int stages = (int)((T == 1 ? 96 : 192) * 1024 / stage_bytes);
     if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
     if (stages < 1) stages = 1;
     p.stages = stages;
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
-    dim3 grid((unsigned)(d->ntaps * p.ci_tiles * p.co_tiles), (unsigned)ksplit, (unsigned)d->groups);
-    rc = p.nb == 2 ? launch_wg<2>(p, grid, smem, s) : launch_wg<1>(p, grid, smem, s);
+    dim3 grid((unsigned)((d->ntaps / T) * p.ci_tiles * p.co_tiles), (unsigned)ksplit, (unsigned)d->groups);
+    if (T == 1)      rc = p.nb == 2 ? launch_wg<2, 1, true>(p, grid, smem, s) : launch_wg<1, 1, true>(p, grid, smem, s);
+    else if (T == 4) rc = p.nb == 2 ? (share_a ? launch_wg<2, 4, true>(p, grid, smem, s) : launch_wg<2, 4, false>(p, grid, smem, s))
+                                    : (share_a ? launch_wg<1, 4, true>(p, grid, smem, s) : launch_wg<1, 4, false>(p, grid, smem, s));
+    else             rc = p.nb == 2 ? (share_a ? launch_wg<2, 3, true>(p, grid, smem, s) : launch_wg<2, 3, false>(p, grid, smem, s))
+                                    : (share_a ? launch_wg<1, 3, true>(p, grid, smem, s) : launch_wg<1, 3, false>(p, grid, smem, s));
     if (rc) return rc;
     if (d->dbias)                      // bias gradient = column sum of the (unshifted) output gradient
         return tbi_colsum(d->dtype, (int64_t)d->n * d->b_src.h * d->b_src.w, &d->b_src, d->dbias, (void*)s);
