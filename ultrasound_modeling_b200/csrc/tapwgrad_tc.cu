@@ -300,15 +300,16 @@ int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s) {
     const long long out_tiles = (long long)(d->ntaps / T) * p.ci_tiles * p.co_tiles * d->groups;
     long long ksplit = (4LL * tbi_sm_count() + out_tiles - 1) / out_tiles;      // T = 1: ~4 CTAs per SM in flight overall
     if (T > 1) {
-        // one CTA per SM (it owns all of TMEM): pick the split-K factor that fills whole waves of SMs best, keeping at least
-        // 8 K-steps per CTA so the 64K-atomic epilogue stays small next to the main loop
+        // one CTA per SM (it owns all of TMEM): pick the split-K factor with the shortest modelled time
+        //   waves * (K-steps per CTA + E),  E = the epilogue's T*128*BN reduction atomics expressed in K-steps (~32, measured:
+        //   upsample_1 went 104 -> 210 us when an 8-way split left 8 K-steps per CTA in front of that epilogue)
         const long long sms = tbi_sm_count();
-        long long cap = total_tiles / 8; if (cap < 1) cap = 1; if (cap > 16) cap = 16;
-        double best = -1.0; ksplit = 1;
+        long long cap = total_tiles < 16 ? total_tiles : 16;
+        long long best = -1; ksplit = 1;
         for (long long ks = 1; ks <= cap; ++ks) {
             const long long ctas = out_tiles * ks, waves = (ctas + sms - 1) / sms;
-            const double eff = (double)ctas / (double)(waves * sms);
-            if (eff > best + 0.02) { best = eff; ksplit = ks; }
+            const long long cost = waves * ((total_tiles + ks - 1) / ks + 32);
+            if (best < 0 || cost < best) { best = cost; ksplit = ks; }
         }
     }
     if (ksplit > total_tiles) ksplit = total_tiles;
