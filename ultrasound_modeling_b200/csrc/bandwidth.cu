@@ -139,6 +139,33 @@ __global__ void convt_gather_kernel(int n, int h, int w, int k, int pad, int cou
     }
 }
 
+// bf16, k = 4, cout <= 4, dz records of >= 4 channels (8-byte aligned), G records of exactly 64 channels at a 128-byte pitch:
+// one thread per G pixel gathers its 16 source pixels (8 bytes each) and writes the 128-byte record with eight 16-byte stores
+// (channels 16*cout .. 63 are written as zeros, which the contract allows: the consumers' weights are zero there).
+template <int COUT>
+__global__ void __launch_bounds__(256) convt_gather4_bf16_kernel(int n, int h, int w, tbi_view dz, tbi_view g) {
+    const long long total = (long long)n * h * w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w); long long t = i / w; const int y = (int)(t % h); const int b = (int)(t / h);
+        __align__(16) __nv_bfloat16 rec[64];
+#pragma unroll
+        for (int q = 0; q < 64; ++q) rec[q] = __float2bfloat16_rn(0.f);
+#pragma unroll
+        for (int tap = 0; tap < 16; ++tap) {
+            const int sy = 2 * y - 1 + tap / 4, sx = 2 * x - 1 + tap % 4;
+            if (sy >= 0 && sy < dz.h && sx >= 0 && sx < dz.w) {
+                const uint2 v = *reinterpret_cast<const uint2*>((const __nv_bfloat16*)dz.ptr + view_off(dz, b, sy, sx, 0));
+                const __nv_bfloat16* vv = reinterpret_cast<const __nv_bfloat16*>(&v);
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) rec[tap * COUT + c] = vv[c];
+            }
+        }
+        uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)g.ptr + view_off(g, b, y, x, 0));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = reinterpret_cast<const uint4*>(rec)[q];
+    }
+}
+
 template <typename T, int V>
 __global__ void accumulate_kernel(long long npix, tbi_view src, tbi_view dst) {
     const int cv = dst.c / V;
@@ -526,12 +553,14 @@ __global__ void splitatt_param_grad_kernel(tbi_splitatt p, const float* scratch,
         if (i >= (long long)K * R * c2 * c) return;
         const int ch = (int)(i % c); long long t = i / c; const int j = (int)(t % c2); t /= c2; const int r = (int)(t % R); const int k = (int)(t / R);
         float s = 0.f;
+#pragma unroll 8
         for (int n = 0; n < N; ++n) s = fmaf(p.h1[((size_t)n * K + k) * c2 + j], dz[(((size_t)n * K + k) * R + r) * c + ch], s);
         dw2[i] += s;
     } else if (blockIdx.y == 1) {                            // db2 [K][R][c]
         if (i >= (long long)K * R * c) return;
         const int ch = (int)(i % c); long long t = i / c; const int r = (int)(t % R); const int k = (int)(t / R);
         float s = 0.f;
+#pragma unroll 8
         for (int n = 0; n < N; ++n) s += dz[(((size_t)n * K + k) * R + r) * c + ch];
         db2[i] += s;
     } else if (blockIdx.y == 2) {                            // dw1 [K][c][c2]
@@ -539,6 +568,7 @@ __global__ void splitatt_param_grad_kernel(tbi_splitatt p, const float* scratch,
         const int j = (int)(i % c2); long long t = i / c2; const int ch = (int)(t % c); const int k = (int)(t / c);
         const float sc = p.gamma[k * c2 + j] * rsqrtf(p.var[k * c2 + j] + p.bn_eps);
         float s = 0.f;
+#pragma unroll 8
         for (int n = 0; n < N; ++n) s = fmaf(p.gap[((size_t)n * K + k) * c + ch], dbn[((size_t)n * K + k) * c2 + j], s);
         dw1[i] += s * sc;
     } else {                                                 // db1, dgamma, dbeta [K][c2]
@@ -546,6 +576,7 @@ __global__ void splitatt_param_grad_kernel(tbi_splitatt p, const float* scratch,
         const int j = (int)(i % c2); const int k = (int)(i / c2);
         const float sc = p.gamma[k * c2 + j] * rsqrtf(p.var[k * c2 + j] + p.bn_eps);
         float sb = 0.f, sg = 0.f;
+#pragma unroll 8
         for (int n = 0; n < N; ++n) { const float d = dbn[((size_t)n * K + k) * c2 + j]; sb += d; sg = fmaf(d, xhat[((size_t)n * K + k) * c2 + j], sg); }
         dbeta[i] += sb; dgamma[i] += sg; db1[i] += sb * sc;
     }
@@ -714,11 +745,25 @@ __global__ void bn_param_grad_kernel(int c, long long k_outer, long long inner, 
     const float istd = rsqrtf(var[ch] + eps);
     const float sc = gamma[ch] * istd;
     float l = 0.f;
-    for (long long k = threadIdx.x; k < K; k += blockDim.x) {
-        const size_t a = (size_t)(k / inner) * outer_stride + (size_t)ch * co_stride + (size_t)(k % inner);
-        const float g = dw[a];
-        l = fmaf(w[a], g, l);
-        dw[a] = g * sc;
+    if (inner % 4 == 0 && outer_stride % 4 == 0 && co_stride % 4 == 0 && (((uintptr_t)w | (uintptr_t)dw) & 15) == 0) {
+        // HWOI kernels: runs of `inner` contiguous floats per (tap, channel) -> 16-byte accesses, 4 independent chains
+        const long long K4 = K / 4, inner4 = inner / 4;
+#pragma unroll 4
+        for (long long k = threadIdx.x; k < K4; k += blockDim.x) {
+            const size_t a = (size_t)(k / inner4) * outer_stride + (size_t)ch * co_stride + (size_t)(k % inner4) * 4;
+            float4 g = *reinterpret_cast<const float4*>(dw + a);
+            const float4 ww = *reinterpret_cast<const float4*>(w + a);
+            l = fmaf(ww.x, g.x, l); l = fmaf(ww.y, g.y, l); l = fmaf(ww.z, g.z, l); l = fmaf(ww.w, g.w, l);
+            g.x *= sc; g.y *= sc; g.z *= sc; g.w *= sc;
+            *reinterpret_cast<float4*>(dw + a) = g;
+        }
+    } else {
+        for (long long k = threadIdx.x; k < K; k += blockDim.x) {
+            const size_t a = (size_t)(k / inner) * outer_stride + (size_t)ch * co_stride + (size_t)(k % inner);
+            const float g = dw[a];
+            l = fmaf(w[a], g, l);
+            dw[a] = g * sc;
+        }
     }
     const float dot = block_reduce(l, red, false);
     if (threadIdx.x == 0) {
@@ -796,11 +841,21 @@ __global__ void adam_advance_kernel(int32_t* s) { if (threadIdx.x == 0 && blockI
 
 __global__ void dropout_mask_kernel(uint8_t* keep, long long count, unsigned long long seed, const int32_t* step_ptr) {
     const unsigned long long offset = step_ptr ? (unsigned long long)(*step_ptr) * (unsigned long long)count : 0ull;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+    auto draw = [&](long long i) -> unsigned long long {
         unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + offset + 1);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
-        keep[i] = (uint8_t)(((z >> 33) & 1ull) << 1);      // multiplier: 0 dropped, 2 kept
+        return ((z >> 33) & 1ull) << 1;                      // multiplier: 0 dropped, 2 kept
+    };
+    const bool vec = (reinterpret_cast<uintptr_t>(keep) & 7) == 0;
+    const long long groups = vec ? count / 8 : 0;
+    for (long long gi = blockIdx.x * (long long)blockDim.x + threadIdx.x; gi < groups; gi += (long long)gridDim.x * blockDim.x) {
+        unsigned long long pack = 0;                          // same per-element stream as the scalar form, one 8-byte store
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pack |= draw(gi * 8 + j) << (8 * j);
+        reinterpret_cast<unsigned long long*>(keep)[gi] = pack;
     }
+    for (long long i = groups * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+        keep[i] = (uint8_t)draw(i);
 }
 
 template <typename S, typename D>
@@ -875,6 +930,18 @@ extern "C" int tbi_convt_gather_dz(int dtype, int n, int h, int w, int ksize, in
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned gr = grid_for((long long)n * h * w * ksize * ksize, 256);
     const int pad = ksize == 4 ? 1 : 0;
+    if (dtype == TBI_BF16 && ksize == 4 && cout <= 4 && dz->c >= 4 && dz->cstride % 4 == 0 && dz->coff % 4 == 0 && ((uintptr_t)dz->ptr & 7) == 0 &&
+        g->c == 64 && g->cstride == 64 && g->coff == 0 && ((uintptr_t)g->ptr & 15) == 0) {
+        const unsigned gg = grid_for((long long)n * h * w, 256);
+        switch (cout) {
+            case 1: convt_gather4_bf16_kernel<1><<<gg, 256, 0, s>>>(n, h, w, *dz, *g); break;
+            case 2: convt_gather4_bf16_kernel<2><<<gg, 256, 0, s>>>(n, h, w, *dz, *g); break;
+            case 3: convt_gather4_bf16_kernel<3><<<gg, 256, 0, s>>>(n, h, w, *dz, *g); break;
+            default: convt_gather4_bf16_kernel<4><<<gg, 256, 0, s>>>(n, h, w, *dz, *g); break;
+        }
+        TBI_CUDA_LAUNCH_CHECK("convt_gather4");
+        return TBI_OK;
+    }
     if (dtype == TBI_F32) convt_gather_kernel<float><<<gr, 256, 0, s>>>(n, h, w, ksize, pad, cout, *dz, *g);
     else if (dtype == TBI_BF16) convt_gather_kernel<__nv_bfloat16><<<gr, 256, 0, s>>>(n, h, w, ksize, pad, cout, *dz, *g);
     else return tbi_set_error(TBI_ERR_UNSUPPORTED, "convt_gather dtype");
@@ -1146,7 +1213,7 @@ extern "C" int tbi_bn_param_grad(int c, int64_t k_outer, int64_t inner, int64_t 
         bn_param_grad_cols_kernel<<<dim3((unsigned)((c + 31) / 32), (unsigned)ks), dim3(32, 8), 0, (cudaStream_t)stream>>>(
             c, k_outer, outer_stride, w, dw, bias, dbias, gamma, mean, var, eps, dgamma, dbeta);
     } else {
-        bn_param_grad_kernel<<<c, 128, 0, (cudaStream_t)stream>>>(c, k_outer, inner, outer_stride, co_stride, w, dw, bias, dbias,
+        bn_param_grad_kernel<<<c, 256, 0, (cudaStream_t)stream>>>(c, k_outer, inner, outer_stride, co_stride, w, dw, bias, dbias,
                                                                   gamma, mean, var, eps, dgamma, dbeta);
     }
     TBI_CUDA_LAUNCH_CHECK("bn_param_grad");
@@ -1168,7 +1235,7 @@ extern "C" int tbi_adam_advance(int32_t* step_count, void* stream) {
 }
 
 extern "C" int tbi_dropout_mask(uint8_t* keep, int64_t count, uint64_t seed, const int32_t* step_ptr, void* stream) {
-    dropout_mask_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(keep, count, seed, step_ptr);
+    dropout_mask_kernel<<<grid_for(count / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(keep, count, seed, step_ptr);
     TBI_CUDA_LAUNCH_CHECK("dropout_mask");
     return TBI_OK;
 }
