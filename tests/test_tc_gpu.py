@@ -179,11 +179,12 @@ def test_head_shapes_on_tensor_cores(ops):
     assert rel(res[0][2], gw) < 1e-4 and res[0][2].shape == (4, 4, nc, c1 + c2)
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, BF])
-def test_stem_conv1_direct_kernels(ops, dtype):
-    """Conv1: 1 -> 16 (TBI_ResNest.py:83) runs on the direct few-channel kernels under IMPL_AUTO"""
+@pytest.mark.parametrize("dtype,hw", [(torch.float32, (40, 36)), (BF, (40, 36)), (BF, (24, 64))])
+def test_stem_conv1_direct_kernels(ops, dtype, hw):
+    """Conv1: 1 -> 16 (TBI_ResNest.py:83) runs on the direct few-channel kernels under IMPL_AUTO
+    (width a multiple of 32 in bf16: the row-walking weight-gradient kernel)"""
     torch.manual_seed(6)
-    n, h, w = 2, 40, 36
+    n, (h, w) = 2, hw
     x = torch.randn(n, h, w, 1, device="cuda").to(dtype)
     wt = torch.randn(3, 3, 1, 16, device="cuda") * 0.3
     b = torch.randn(16, device="cuda") * 0.1

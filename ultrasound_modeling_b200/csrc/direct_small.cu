@@ -4,6 +4,7 @@
 // 16-byte stores; the weight gradient is a per-thread register reduction + warp shuffles + one atomic
 // per (block, element).
 #include "tbi_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -141,6 +142,95 @@ __global__ void __launch_bounds__(256) smallcin_wgrad_kernel(const __grid_consta
     }
 }
 
+
+// Row-walking form of the above for the standard 3x3 / pad 1 pattern on dense tensors: a thread owns SEG consecutive pixels
+// of one image row and slides a 3x3 register window of x along it, so a pixel costs 3 scalar loads of x + 32 bytes of dz +
+// the 144 FMAs -- no per-tap address arithmetic or bounds checks (the per-pixel form above spends ~300 instructions per
+// pixel, most of them addressing).  The next pixel's loads are issued before the current pixel's FMAs.
+template <int SEG>
+__global__ void __launch_bounds__(256) smallcin_wgrad_rows_kernel(const __grid_constant__ tbi_tapwgrad d) {
+    constexpr int COUT = 16, NT = 9;
+    typedef __nv_bfloat16 T;
+    __shared__ float red[8][NT * COUT + COUT];
+    float acc[NT][COUT];
+    float bacc[COUT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[t][c] = 0.f;
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) bacc[c] = 0.f;
+    const int W = d.gw, H = d.gh, segs_x = W / SEG;
+    const long long nseg = (long long)d.n * H * segs_x;
+    const T* a = (const T*)d.a_src[0].ptr;
+    const T* b = (const T*)d.b_src.ptr;
+    for (long long sgi = blockIdx.x * (long long)blockDim.x + threadIdx.x; sgi < nseg; sgi += (long long)gridDim.x * blockDim.x) {
+        const int xs = (int)(sgi % segs_x) * SEG; long long t = sgi / segs_x; const int y = (int)(t % H); const int n = (int)(t / H);
+        const T* ar[3]; bool av[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { const int yy = y + r - 1; av[r] = yy >= 0 && yy < H; ar[r] = a + ((size_t)n * H + (av[r] ? yy : y)) * W; }
+        const uint4* bp = reinterpret_cast<const uint4*>(b + (((size_t)n * H + y) * W + xs) * COUT);
+        float win[3][3];                                   // [row][column x-1, x, x+1]
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            win[r][0] = (av[r] && xs > 0) ? ldf(ar[r] + xs - 1) : 0.f;
+            win[r][1] = av[r] ? ldf(ar[r] + xs) : 0.f;
+        }
+        uint4 g0 = bp[0], g1 = bp[1];
+        float nx[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) nx[r] = (av[r] && xs + 1 < W) ? ldf(ar[r] + xs + 1) : 0.f;
+#pragma unroll 2
+        for (int i = 0; i < SEG; ++i) {
+            const uint4 c0 = g0, c1 = g1;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) win[r][2] = nx[r];
+            if (i + 1 < SEG) {                             // prefetch pixel i+1
+                g0 = bp[2 * (i + 1)]; g1 = bp[2 * (i + 1) + 1];
+                const int xn = xs + i + 2;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) nx[r] = (av[r] && xn < W) ? ldf(ar[r] + xn) : 0.f;
+            }
+            float g[COUT];
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&c0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&c1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const float2 f0 = __bfloat1622float2(h0[q]), f1 = __bfloat1622float2(h1[q]); g[2 * q] = f0.x; g[2 * q + 1] = f0.y; g[8 + 2 * q] = f1.x; g[8 + 2 * q + 1] = f1.y; }
+#pragma unroll
+            for (int c = 0; c < COUT; ++c) bacc[c] += g[c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int cx = 0; cx < 3; ++cx) {
+                    const float x = win[r][cx];
+#pragma unroll
+                    for (int c = 0; c < COUT; ++c) acc[r * 3 + cx][c] = fmaf(x, g[c], acc[r * 3 + cx][c]);
+                }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { win[r][0] = win[r][1]; win[r][1] = win[r][2]; }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int tp = 0; tp < NT; ++tp)
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) { const float v = warp_sum(acc[tp][c]); if (lane == 0) red[warp][tp * COUT + c] = v; }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) { const float v = warp_sum(bacc[c]); if (lane == 0) red[warp][NT * COUT + c] = v; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NT * COUT + COUT; i += blockDim.x) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][i];
+        if (i < NT * COUT) {
+            const int tp = i / COUT, co = i % COUT;
+            atomicAdd(d.dw + (size_t)tp * d.tap_stride + (size_t)co * d.co_stride, v);
+        } else if (d.dbias) {
+            atomicAdd(d.dbias + (i - NT * COUT), v);
+        }
+    }
+}
+
 }  // namespace
 
 bool tbi_tapgemm_direct_supported(const tbi_tapgemm* d) {
@@ -181,6 +271,22 @@ int tbi_tapwgrad_direct(const tbi_tapwgrad* d, cudaStream_t s) {
     const long long cap = (long long)tbi_sm_count() * 4;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    {   // row-walking kernel: bf16, dense 1-channel x and 16-channel dz, standard 3x3 taps, width a multiple of 32
+        static const bool off = getenv("TBI_SMALLCIN_NO_ROWS") != nullptr;
+        bool std_taps = d->ntaps == 9;
+        for (int t = 0; t < 9 && std_taps; ++t) std_taps = d->a_dy[t] == t / 3 - 1 && d->a_dx[t] == t % 3 - 1;
+        const tbi_view& A = d->a_src[0]; const tbi_view& B = d->b_src;
+        if (!off && d->dtype == TBI_BF16 && std_taps && A.cstride == 1 && A.coff == 0 && A.h == d->gh && A.w == d->gw &&
+            B.cstride == 16 && B.coff == 0 && B.h == d->gh && B.w == d->gw && d->gw % 32 == 0 && ((uintptr_t)B.ptr & 15) == 0) {
+            const long long nseg = (long long)d->n * d->gh * (d->gw / 32);
+            long long nb = (nseg + 255) / 256;
+            const long long capb = (long long)tbi_sm_count() * 4;
+            if (nb > capb) nb = capb;
+            smallcin_wgrad_rows_kernel<32><<<(unsigned)nb, 256, 0, s>>>(*d);
+            TBI_CUDA_LAUNCH_CHECK("smallcin_wgrad_rows");
+            return TBI_OK;
+        }
+    }
     if (d->dtype == TBI_F32) smallcin_wgrad_kernel<float, 16, 9><<<(unsigned)blocks, 256, 0, s>>>(*d);
     else smallcin_wgrad_kernel<__nv_bfloat16, 16, 9><<<(unsigned)blocks, 256, 0, s>>>(*d);
     TBI_CUDA_LAUNCH_CHECK("smallcin_wgrad");
