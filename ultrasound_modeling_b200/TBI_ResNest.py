@@ -70,6 +70,8 @@ class ResNest:
         self._graphs = {}
         self._pin = {}
         self._warm = set()
+        self._copy_stream = None
+        self._y_event = None
 
     # ------------------------------------------------------------------ inputs
     def _stage(self, name, arr, dst: torch.Tensor):
@@ -88,6 +90,27 @@ class ResNest:
         else:
             dst.copy_(arr.reshape(dst.shape))
 
+    def _stage_labels(self, y, dst: torch.Tensor):
+        """the labels are first needed by the loss, a whole forward pass after the step starts: a pinned fp32 host tensor is
+        copied on a side stream while the forward runs (3/4 of the step's host->device bytes are labels); anything else goes
+        through _stage on the main stream."""
+        if torch.is_tensor(y) and y.device.type == "cpu" and y.dtype == torch.float32 and y.is_contiguous() and y.is_pinned():
+            dev = self.engine.device
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            self._copy_stream.wait_stream(torch.cuda.current_stream(dev))      # the previous step's loss has consumed y_in
+            with torch.cuda.stream(self._copy_stream):
+                dst.copy_(y.reshape(dst.shape), non_blocking=True)
+            self._y_event = self._copy_stream.record_event()
+        else:
+            self._stage("y", y, dst)
+            self._y_event = None
+
+    def _wait_labels(self):
+        if self._y_event is not None:
+            torch.cuda.current_stream(self.engine.device).wait_event(self._y_event)
+            self._y_event = None
+
     # ------------------------------------------------------------------ device step
     def _device_step(self, train: bool, draw: bool):
         e = self.engine
@@ -95,6 +118,7 @@ class ResNest:
         if draw:
             e.draw_dropout()
         e.forward()
+        self._wait_labels()
         e.loss()
         if train:
             if self.grad_sync is not None:
@@ -118,6 +142,7 @@ class ResNest:
         if train and self.grad_sync is not None:
             # data parallel: graph segments + eager NCCL between them (collectives are never captured)
             e = self.engine
+            self._wait_labels()
 
             def pre():
                 e.prepare()
@@ -129,12 +154,26 @@ class ResNest:
             self.grad_sync.step_graphed(e, pre, lambda: e.adam(self.optimizer.learning_rate, 1.0 / self.grad_sync.world_size), key)
             return
         if g is None:
+            # two graphs: [prepare, dropout, forward] | [loss, backward, Adam]; the label copy (side stream) joins between them
+            e = self.engine
+            self._wait_labels()
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._device_step(train, draw)
-            self._graphs[key] = g
-        g.replay()
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                e.prepare()
+                if draw:
+                    e.draw_dropout()
+                e.forward()
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                e.loss()
+                if train:
+                    e.backward()
+                    e.adam(self.optimizer.learning_rate, 1.0)
+            g = self._graphs[key] = (g1, g2)
+        g[0].replay()
+        self._wait_labels()
+        g[1].replay()
 
     def step(self, x, y, train=False, dropout_masks=None):
         """reference: TBI_ResNest.py:35-55.  dropout_masks: None = draw fresh masks (reference behaviour,
@@ -144,7 +183,7 @@ class ResNest:
         n = int(x.shape[0])
         e.build(n)
         self._stage("x", x, e.x_in)
-        self._stage("y", y, e.y_in)
+        self._stage_labels(y, e.y_in)
         draw = dropout_masks is None
         if not draw:
             e.set_dropout(None if dropout_masks is False else dropout_masks)

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) splitatt_fwd_fused_kernel(tbi_splitatt p,
         const int k = i / c2, j = i % c2;
         float q = p.b1[i];
         const float* w1 = (stage_w ? sw1 : p.w1) + (size_t)k * c * c2 + j;
-#pragma unroll 8
+#pragma unroll 32
         for (int ch = 0; ch < c; ++ch) q = fmaf(g[k * c + ch], w1[(size_t)ch * c2], q);
         const float sc = p.gamma[i] * rsqrtf(p.var[i] + p.bn_eps);
         h1[i] = act_apply(p.act, (q - p.mean[i]) * sc + p.beta[i]);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) splitatt_fwd_fused_kernel(tbi_splitatt p,
         const int ch = i % c, kr = i / c, k = kr / R;
         float z = p.b2[i];
         const float* w2 = (stage_w ? sw2 : p.w2) + (size_t)kr * c2 * c + ch;
-#pragma unroll 8
+#pragma unroll 32
         for (int j = 0; j < c2; ++j) z = fmaf(h1[k * c2 + j], w2[(size_t)j * c], z);
         att[i] = z;
     }
@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256) splitatt_bwd_fused_kernel(tbi_splitatt p,
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll 4
     for (int i = wid; i < K * c2; i += nwarp) {              // dh1 = sum_r dz_r W2_r^T : a warp per output, lanes over channels
         const int k = i / c2, j = i % c2;
         float s = 0.f;
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(256) splitatt_bwd_fused_kernel(tbi_splitatt p,
         const int k = i / c2, j = i % c2;
         float q = p.b1[i];
         const float* w1 = W1 + (size_t)k * c * c2 + j;
-#pragma unroll 8
+#pragma unroll 32
         for (int ch = 0; ch < c; ++ch) q = fmaf(gg[k * c + ch], w1[(size_t)ch * c2], q);
         const float istd = rsqrtf(p.var[i] + p.bn_eps);
         const float d = dq[i] * act_grad_from_out(p.act, gh1[i]);
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(256) splitatt_bwd_fused_kernel(tbi_splitatt p,
         dq[i] = d * p.gamma[i] * istd;
     }
     __syncthreads();
+#pragma unroll 4
     for (int i = wid; i < K * c; i += nwarp) {
         const int k = i / c, ch = i % c;
         float s = 0.f;
