@@ -142,16 +142,15 @@ class ResNest:
         if train and self.grad_sync is not None:
             # data parallel: graph segments + eager NCCL between them (collectives are never captured)
             e = self.engine
-            self._wait_labels()
 
             def pre():
                 e.prepare()
                 if draw:
                     e.draw_dropout()
                 e.forward()
-                e.loss()
 
-            self.grad_sync.step_graphed(e, pre, lambda: e.adam(self.optimizer.learning_rate, 1.0 / self.grad_sync.world_size), key)
+            self.grad_sync.step_graphed(e, pre, lambda: e.adam(self.optimizer.learning_rate, 1.0 / self.grad_sync.world_size), key,
+                                        loss_fn=e.loss, before_loss=self._wait_labels)
             return
         if g is None:
             # two graphs: [prepare, dropout, forward] | [loss, backward, Adam]; the label copy (side stream) joins between them

@@ -67,11 +67,12 @@ class GradSync:
         cur.wait_stream(self.comm_stream)
 
     # ------------------------------------------------------------------ CUDA-graph replay with eager collectives
-    def step_graphed(self, engine, pre_fn, post_fn, key):
+    def step_graphed(self, engine, pre_fn, post_fn, key, loss_fn=None, before_loss=None):
         """One training step as CUDA-graph SEGMENTS: [pre_fn = prepare/forward/loss] , one graph per backward slice
         between bucket boundaries, [post_fn = Adam].  The bucket all-reduces are launched eagerly on the side stream
         between segment replays (NCCL calls are never captured), so they overlap the following backward segments
-        exactly as in the eager path."""
+        exactly as in the eager path.  With loss_fn the loss is its own segment and before_loss() runs (eagerly) in front of
+        it: the caller's label copy joins there instead of in front of the forward pass."""
         self._ensure_plan(engine)
         if self.comm_stream is None:
             self.comm_stream = torch.cuda.Stream(device=engine.device)
@@ -88,6 +89,11 @@ class GradSync:
 
             def pre():
                 pre_fn()
+                if loss_fn is None:
+                    engine.grads.zero_()
+
+            def loss_seg():
+                loss_fn()
                 engine.grads.zero_()
 
             segs, pos = [], 0
@@ -96,10 +102,14 @@ class GradSync:
                 segs.append((cap(lambda a=a, b=b: engine._run(engine.prog_bwd[a:b], engine.stream())) if b > a else None, lo, hi))
                 pos = calls
             tail = cap(lambda: engine._run(engine.prog_bwd[pos:], engine.stream())) if pos < len(engine.prog_bwd) else None
-            graphs = dict(pre=cap(pre), segs=segs, tail=tail, post=cap(post_fn))
+            graphs = dict(pre=cap(pre), loss=cap(loss_seg) if loss_fn is not None else None, segs=segs, tail=tail, post=cap(post_fn))
             self._seg_graphs[key] = graphs
             cur = torch.cuda.current_stream(engine.device)
         graphs["pre"].replay()
+        if before_loss is not None:
+            before_loss()
+        if graphs["loss"] is not None:
+            graphs["loss"].replay()
         for g, lo, hi in graphs["segs"]:
             if g is not None:
                 g.replay()
