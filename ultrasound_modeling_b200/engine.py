@@ -123,6 +123,8 @@ class Engine:
         self.impl = impl
         self.N = 0
         self.overlap_prepare = os.environ.get("TBI_NO_PREP_OVERLAP") is None
+        self.overlap_bwd = os.environ.get("TBI_NO_BWD_OVERLAP") is None
+        self._side_bwd = None
         self._side = None
         self._prep_pending = False
         self._define_layers()
@@ -370,6 +372,7 @@ class Engine:
         # (number of prog_bwd calls issued, lowest flat offset above which every gradient is final):
         # lets the data-parallel wrapper all-reduce finished buckets while backward continues
         self.bwd_marks: List[Tuple[int, int]] = []
+        self.bwd_side = set()          # indices of prog_bwd entries that may run beside the data-gradient chain (see run_bwd)
         done = set()
         order = list(self.P.specs.values())
 
@@ -449,9 +452,11 @@ class Engine:
                 wargs = [dt, impl, n, h, w, Lr.k, 1, Lr.groups, bref(x0), bref(x1) if x1 is not None else None, bref(dz), dw, db,
                          _ptr(self.wgrad_ws) if self.wgrad_ws is not None else None, self.wgrad_ws.numel() if self.wgrad_ws is not None else 0]
                 self.prog_bwd.append((L.tbi_conv2d_wgrad, wargs))
+                self.bwd_side.add(len(self.prog_bwd) - 1)
             else:
                 wargs = [dt, impl, n, h, w, Lr.k, bref(x0), bref(x1) if x1 is not None else None, bref(dz), Lr.cout, dw, db, None, 0]
                 self.prog_bwd.append((L.tbi_conv2d_transpose_s2_wgrad, wargs))
+                self.bwd_side.add(len(self.prog_bwd) - 1)
             wgrads.append((Lr, wargs, n, h, w, x0, x1, dz))
             if Lr.bn:
                 if Lr.kind == "conv":
@@ -462,6 +467,7 @@ class Engine:
                                                             _ptr(self.p(Lr.name + "/gamma")), _ptr(self.s(Lr.name + "/mean")),
                                                             _ptr(self.s(Lr.name + "/var")), BN_EPS, _ptr(self.g(Lr.name + "/gamma")),
                                                             _ptr(self.g(Lr.name + "/beta")))))
+                self.bwd_side.add(len(self.prog_bwd) - 1)
             mark(Lr.name)
             if e_dgrad is not None:
                 if Lr.kind == "conv":
@@ -626,9 +632,39 @@ class Engine:
         self.correct.zero_()
         self._run(self.prog_loss, self.stream())
 
+    def run_bwd(self, a: int, b: int):
+        """prog_bwd[a:b] on the current stream, with the weight-gradient side of every conv layer (wgrad + bias sum + BN
+        parameter gradients: needs only the layer's input and its output gradient, writes only parameter gradients) on a
+        second stream beside the data-gradient chain.  Every gradient buffer is written once and never reused, so the only
+        ordering needed is `side waits for whatever main has issued so far` in front of each side entry; the side stream is
+        joined at the end of the slice, i.e. parameter gradients are final at every bucket boundary of parallel.py."""
+        if not self.overlap_bwd or not self.bwd_side:
+            self._run(self.prog_bwd[a:b], self.stream())
+            return
+        main = torch.cuda.current_stream(self.device)
+        if self._side_bwd is None:
+            self._side_bwd = torch.cuda.Stream(self.device)
+        side = self._side_bwd
+        dirty, used = True, False
+        for i in range(a, b):
+            fn, args = self.prog_bwd[i]
+            if i in self.bwd_side:
+                if dirty:
+                    side.wait_stream(main)
+                    dirty = False
+                rc = fn(*args, side.cuda_stream)
+                used = True
+            else:
+                rc = fn(*args, main.cuda_stream)
+                dirty = True
+            if rc != 0:
+                check(rc, fn.__name__)
+        if used:
+            main.wait_stream(side)
+
     def backward(self):
         self.grads.zero_()
-        self._run(self.prog_bwd, self.stream())
+        self.run_bwd(0, len(self.prog_bwd))
 
     def adam(self, lr: float, grad_scale: float = 1.0):
         st = self.stream()

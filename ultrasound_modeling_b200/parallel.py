@@ -56,14 +56,14 @@ class GradSync:
         engine.grads.zero_()
         pos = 0
         for calls, lo, hi in self._plan:
-            engine._run(engine.prog_bwd[pos:calls], cur.cuda_stream)
+            engine.run_bwd(pos, calls)
             pos = calls
             ev = torch.cuda.Event()
             ev.record(cur)
             self.comm_stream.wait_event(ev)
             with torch.cuda.stream(self.comm_stream):
                 self.allreduce(engine.grads[lo:hi])
-        engine._run(engine.prog_bwd[pos:], cur.cuda_stream)
+        engine.run_bwd(pos, len(engine.prog_bwd))
         cur.wait_stream(self.comm_stream)
 
     # ------------------------------------------------------------------ CUDA-graph replay with eager collectives
@@ -99,9 +99,9 @@ class GradSync:
             segs, pos = [], 0
             for calls, lo, hi in self._plan:
                 a, b = pos, calls
-                segs.append((cap(lambda a=a, b=b: engine._run(engine.prog_bwd[a:b], engine.stream())) if b > a else None, lo, hi))
+                segs.append((cap(lambda a=a, b=b: engine.run_bwd(a, b)) if b > a else None, lo, hi))
                 pos = calls
-            tail = cap(lambda: engine._run(engine.prog_bwd[pos:], engine.stream())) if pos < len(engine.prog_bwd) else None
+            tail = cap(lambda: engine.run_bwd(pos, len(engine.prog_bwd))) if pos < len(engine.prog_bwd) else None
             graphs = dict(pre=cap(pre), loss=cap(loss_seg) if loss_fn is not None else None, segs=segs, tail=tail, post=cap(post_fn))
             self._seg_graphs[key] = graphs
             cur = torch.cuda.current_stream(engine.device)
