@@ -522,6 +522,7 @@ class Engine:
             hh, hw_ = H // 2, W // 2
             nc = self.num_class
             self.prog_bwd.append((L.tbi_colsum, (dt, n * H * W, bref(view(self.dlogits, c=nc)), _ptr(self.g("f_tran/b")))))
+            self.bwd_side.add(len(self.prog_bwd) - 1)
             self.prog_bwd.append((L.tbi_convt_gather_dz, (dt, n, hh, hw_, 4, nc, bref(view(self.dlogits)), bref(view(self.head_g)))))
             wd = keep(TapWgrad())
             wd.dtype = dt; wd.impl = impl; wd.n = n; wd.gh = hh; wd.gw = hw_; wd.groups = 1
@@ -530,6 +531,7 @@ class Engine:
             wd.a_stride = 1; wd.b_stride = 1; wd.ntaps = 1
             wd.dw = _ptr(self.g("f_tran/w")); wd.tap_stride = 0; wd.ci_stride = 1; wd.co_stride = self.head.cin
             self.prog_bwd.append((L.tbi_tapwgrad_run, (C.byref(wd),)))
+            self.bwd_side.add(len(self.prog_bwd) - 1)
             mark("f_tran")
             gd = keep(TapGemm())
             gd.dtype = dt; gd.impl = impl; gd.n = n; gd.gh = hh; gd.gw = hw_; gd.groups = 1
