@@ -48,7 +48,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([f.strip() for f in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
@@ -241,8 +241,8 @@ def main():
         faulthandler.dump_traceback_later(int(os.environ["TBI_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--radix", type=int, default=2)
     ap.add_argument("--kpaths", type=int, default=1)

@@ -57,6 +57,10 @@ __device__ __forceinline__ void trace(unsigned long long* tr, int role, int tile
 
 static unsigned long long* g_halo_trace_host = nullptr;
 
+// accumulator buffers in TMEM per CTA: narrow tiles (<= 32 columns) get four so the MMA warp can run three tiles ahead of the
+// epilogue groups (their per-tile times vary; with two buffers the issuing thread waited ~400 cycles per tile for a free one)
+__host__ __device__ constexpr int halo_nbuf(int bn) { return bn <= 32 ? 4 : 2; }
+
 struct TileCoord { int x0, y0, n0, nc0, cg, ph; };
 
 __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile, int BN) {
@@ -104,15 +108,16 @@ struct Rings {
 template <int NTAPS, int KSTEPS>
 __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, const Rings& R, uint32_t tmem_base, uint32_t acc_cols, bool leader,
                                                        uint32_t idesc, uint32_t a_base, uint32_t a_stage_lo, uint32_t a_hi,
-                                                       uint32_t b_base, uint32_t b_stage_lo, uint32_t b_hi, uint32_t row_lo, int ph) {
+                                                       uint32_t b_base, uint32_t b_stage_lo, uint32_t b_hi, uint32_t row_lo, int ph, uint32_t nbuf) {
     uint32_t a_off[NTAPS];
 #pragma unroll
     for (int t = 0; t < NTAPS; ++t) a_off[t] = ((uint32_t)p.t_row[ph][t] & 0x3FFu) * row_lo;
     uint32_t sa = 0, a_par = 0, acc_it = 0;
+    const uint32_t lgb = nbuf == 4 ? 2u : 1u;
     for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
-        const uint32_t buf = acc_it & 1u;
+        const uint32_t buf = acc_it & (nbuf - 1u);
         trace(p.trace, 1, acc_it, 0);
-        tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+        tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> lgb) & 1u) ^ 1u);
         tc::tc_fence_after();
         trace(p.trace, 1, acc_it, 1);
         const uint32_t tmem_d = tmem_base + buf * acc_cols;
@@ -145,6 +150,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     // second tile, so the epilogues of consecutive tiles overlap (the per-tile chain wait -> tcgen05.ld -> loads ->
     // math -> stores is latency-bound for small K).
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t NBUF = halo_nbuf(BN), LGB = NBUF == 4 ? 2 : 1;
     const int q = warp & 3;
     const int grp = warp >> 2;                              // 0 or 1 == accumulator buffer
     const int m = q * 32 + lane;
@@ -155,7 +161,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     unsigned long long* tr = (warp == 0 && lane == 0) ? p.trace : nullptr;
     for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
         if ((int)(acc_it & 1u) != grp) continue;
-        const uint32_t buf = (uint32_t)grp;
+        const uint32_t buf = acc_it & (NBUF - 1u);
         const TileCoord t = decode_tile_warp(p, i, BN, lane, slab_t, i);
         trace(tr, 2, acc_it, 0);
         const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
@@ -167,7 +173,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
             rc = make_row_ctx(p.epi, n, oy, ox);
             if (rc.bias) rc.bias = sbias;
         }
-        tc::mbar_wait_bounded<true>(&R.t_full[buf], (acc_it >> 1) & 1u);
+        tc::mbar_wait_bounded<true>(&R.t_full[buf], (acc_it >> LGB) & 1u);
         tc::tc_fence_after();
         trace(tr, 2, acc_it, 1);
         const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -207,7 +213,8 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
 template <int BN>
 __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __grid_constant__ HaloParams p) {
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;            // columns per accumulator buffer
-    constexpr int TMEM_COLS = 2 * ACC_COLS;
+    constexpr uint32_t NBUF = halo_nbuf(BN), LGB = NBUF == 4 ? 2 : 1;
+    constexpr int TMEM_COLS = NBUF * ACC_COLS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     Rings R;
@@ -218,9 +225,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
     R.a_empty = R.a_full + p.a_stages;
     R.b_full = R.a_empty + p.a_stages;
     R.b_empty = R.b_full + p.b_stages;
-    R.t_full = R.b_empty + p.b_stages;                     // [2]
-    R.t_empty = R.t_full + 2;                              // [2]
-    R.b_res = R.t_empty + 2;                               // weights-resident slab loaded
+    R.t_full = R.b_empty + p.b_stages;                     // [4] (NBUF used)
+    R.t_empty = R.t_full + 4;                              // [4]
+    R.b_res = R.t_empty + 4;                               // weights-resident slab loaded
     uint32_t* tslot = reinterpret_cast<uint32_t*>(R.b_res + 1);
     // the folded bias of every output channel, staged once: the epilogue reads it with shared-memory latency and the loads do not
     // sit behind the (possibly aliasing) global stores of the previous channel group
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         if (p.c0 < p.cin_g * p.cgroups) tc::prefetch_tmap(&p.a[1]);
         for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&R.a_full[s], 1); tc::mbar_init(&R.a_empty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&R.b_full[s], 1); tc::mbar_init(&R.b_empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { tc::mbar_init(&R.t_full[s], 1); tc::mbar_init(&R.t_empty[s], 4); }
+        for (int s = 0; s < (int)NBUF; ++s) { tc::mbar_init(&R.t_full[s], 1); tc::mbar_init(&R.t_empty[s], 4); }
         tc::mbar_init(R.b_res, 1);
         tc::fence_barrier_init();
     }
@@ -335,7 +342,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             // ---- weights resident, one halo per chunk: unrolled issue stream ----
             if (R.it_first < R.it_count) tc::mbar_wait_bounded(R.b_res, 0);
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
-#define TBI_FLAT(NT, KS) resident_flat_mma_loop<NT, KS>(p, R, tmem_base, ACC_COLS, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo, slab_ph)
+#define TBI_FLAT(NT, KS) resident_flat_mma_loop<NT, KS>(p, R, tmem_base, ACC_COLS, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo, slab_ph, NBUF)
             switch (p.ntaps * 8 + ksteps) {
                 case 1 * 8 + 1: TBI_FLAT(1, 1); break;
                 case 1 * 8 + 2: TBI_FLAT(1, 2); break;
@@ -356,9 +363,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             uint32_t sa = 0, a_par = 0;
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
             for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
-                const uint32_t buf = acc_it & 1u;
+                const uint32_t buf = acc_it & (NBUF - 1u);
                 trace(p.trace, 1, acc_it, 0);
-                tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+                tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> LGB) & 1u) ^ 1u);
                 tc::tc_fence_after();
                 trace(p.trace, 1, acc_it, 1);
                 const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
@@ -399,9 +406,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
                 const int ph = (p.nphase > 1 ? decode_tile(p, i, BN).ph : 0);
                 if (ph != cur_ph) load_taps(ph);
-                const uint32_t buf = acc_it & 1u;
+                const uint32_t buf = acc_it & (NBUF - 1u);
                 trace(p.trace, 1, acc_it, 0);
-                tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+                tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> LGB) & 1u) ^ 1u);
                 tc::tc_fence_after();
                 trace(p.trace, 1, acc_it, 1);
                 const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
@@ -632,7 +639,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         if (grid > p.total_tiles) grid = p.total_tiles;
     }
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512 +
-                        ((size_t)p.cout_total * 4 + 64) + (size_t)(2 * (p.a_stages + p.b_stages)) * 8;
+                        ((size_t)p.cout_total * 4 + 64) + (size_t)(2 * (p.a_stages + p.b_stages) + 8) * 8;
     switch (bn) {
         case 128: return launch_halo<128>(p, grid, smem, s);
         case 64:  return launch_halo<64>(p, grid, smem, s);
