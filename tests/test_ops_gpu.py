@@ -173,8 +173,30 @@ def _splitatt_ref(us, P, K, R, c, act=F.elu):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("K,R,c", [(1, 2, 32), (4, 4, 8), (2, 1, 16), (3, 3, 10), (1, 2, 256)])
 def test_split_attention_fwd_bwd(ops, dtype, K, R, c):
+    _check_split_attention(ops, dtype, K, R, c, 3, 6, 5)
+
+
+# the cluster-per-image kernels (csrc/splitatt_fused.cu): cluster sizes 1..16, both thread counts, chunk kept in shared memory
+# or re-read from L2, images whose pixel count does not divide by the cluster size, FC layers redundant per CTA (slice 1) or
+# sliced over the cluster (slice 2) incl. slices that are empty or larger than the thread count, weights staged in shared
+# memory or read from global (stage 0, or too large to stage)
+@pytest.mark.parametrize("K,R,c,h,w,cs,nt,cache_kb,slice_mode,stage", [
+    (1, 2, 32, 16, 16, 8, 256, 100, 0, 1), (1, 2, 32, 40, 33, 8, 512, 0, 2, 1), (4, 4, 8, 9, 7, 2, 256, 100, 2, 0),
+    (1, 2, 64, 24, 20, 16, 256, 100, 0, 1), (2, 1, 16, 12, 12, 4, 256, 0, 1, 0), (1, 3, 16, 20, 20, 8, 512, 100, 2, 1),
+    (1, 2, 256, 8, 8, 4, 256, 100, 0, 1), (1, 2, 256, 5, 3, 1, 256, 0, 0, 1), (1, 2, 128, 32, 32, 0, 0, 100, 0, 1),
+    (4, 3, 16, 16, 16, 0, 0, 0, 0, 1), (1, 1, 8, 16, 16, 8, 256, 100, 2, 1), (1, 2, 256, 16, 16, 8, 256, 100, 0, 1),
+    (4, 4, 64, 16, 16, 8, 256, 0, 0, 1), (1, 2, 64, 64, 64, 0, 0, 100, 0, 1)])
+def test_split_attention_cluster_kernels(ops, monkeypatch, K, R, c, h, w, cs, nt, cache_kb, slice_mode, stage):
+    monkeypatch.setenv("TBI_SA_CS", str(cs))
+    monkeypatch.setenv("TBI_SA_NT", str(nt))
+    monkeypatch.setenv("TBI_SA_CACHE_KB", str(cache_kb))
+    monkeypatch.setenv("TBI_SA_SLICE", str(slice_mode))
+    monkeypatch.setenv("TBI_SA_STAGE", str(stage))
+    _check_split_attention(ops, torch.bfloat16, K, R, c, 5, h, w)
+
+
+def _check_split_attention(ops, dtype, K, R, c, n, h, w):
     torch.manual_seed(5)
-    n, h, w = 3, 6, 5
     u_pre = torch.randn(n, h, w, K * R * c, dtype=torch.float64, requires_grad=True)
     u = F.elu(u_pre)                                          # u is an ELU output in the network
     uq = q(u.detach(), dtype)

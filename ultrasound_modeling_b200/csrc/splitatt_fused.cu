@@ -1,16 +1,24 @@
-// Fused split-attention tail (TBI_ResNest.py:175-207) as ONE cooperative launch per direction.
+// Fused split-attention tail (TBI_ResNest.py:175-207): ONE launch per direction, one thread-block CLUSTER per image.
 //
-// forward : phase 1  every CTA sums its pixel chunk of U (all K*R*c channels) -> atomics into raw[n][K*R*c]
-//           grid.sync
-//           phase 2  every CTA recomputes the (tiny) FC chain of its image in shared memory
-//                    (gap -> dense1 -> BN -> act -> dense2 x R -> softmax over channels / sigmoid) and recombines
-//                    V = sum_r U_r * a_r over the SAME pixel chunk, which is still L2-resident: U crosses HBM once.
-// backward: phase 1  da[n][k][r][c] = sum_pixels dV * U_r   (same chunking) ; grid.sync
-//           phase 2  per-image FC backward in shared memory (softmax/sigmoid bwd, dense2^T, act', BN, dense1^T),
-//                    then dU = (dV * a_r + dgap / HW) * act'(U) over the chunk.  The chunk-0 CTA of each image also
-//                    leaves dz / dbn / xhat in the scratch buffer for the parameter-gradient kernel (reduction over n).
-// A CTA keeps the same chunk in both phases, so the second read of U (and dV) hits L2 (126 MB) for every stage of the
-// network.  Grid size is bounded by co-residency (cooperative launch).
+// The only coupling inside the op is per image (global average pool -> FC chain -> per-channel attention), so an image is
+// given to a cluster of CS CTAs (CS <= 8, portable); each CTA owns a contiguous pixel chunk of that image in both bandwidth
+// passes.  Nothing is exchanged through global memory and no grid-wide barrier exists:
+//
+// forward : pass 1   per-channel sums of U over the chunk -> part[] in this CTA's shared memory
+//           cluster barrier; every CTA pulls the CS partial vectors through distributed shared memory -> gap
+//           FC chain, SPLIT across the cluster: each CTA computes a 1/CS slice of dense1 (+BN+act) and pushes it into every
+//           peer's shared memory, barrier, a 1/CS slice of dense2, push, barrier; softmax over channels (sigmoid for R=1)
+//           is redundant per CTA (a warp per row).
+//           pass 2   V = sum_r U_r * a_r over the SAME chunk with the SAME thread->data mapping as pass 1: the chunk is read
+//           back from shared memory when it was small enough to be kept there, otherwise from L2 (it was read microseconds
+//           earlier by this very CTA, whatever the total size of U: images are independent, so no tensor-wide L2 residency
+//           is needed as it was with a grid-wide barrier).
+// backward: pass 1   da[k][r][c] = sum_pixels dV * U_r ; barrier + pull
+//           softmax/sigmoid backward (redundant), dh1 slice (+ recomputed pre-BN value for xhat) -> dq push, barrier,
+//           dgap slice push, barrier; slice owners write dz / dbn / xhat / dgap of the image to the scratch buffer for the
+//           parameter-gradient kernel (reduction over n).
+//           pass 2   dU_r = (dV * a_r + dgap / HW) * act'(U_r).
+// Images run out of step with each other (no grid barrier), so one cluster's FC chain hides behind other clusters' passes.
 #include "tbi_common.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -18,345 +26,671 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-template <typename T, int V> struct alignas(sizeof(T) * V) PackF { T v[V]; };
-template <typename T, int V> __device__ __forceinline__ void ldp(const T* p, float (&f)[V]) {
-    PackF<T, V> q = *reinterpret_cast<const PackF<T, V>*>(p);
+constexpr int V = 8;                                        // bf16 elements per 16-byte access
+
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[V]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-    for (int i = 0; i < V; ++i) f[i] = ldf(&q.v[i]);
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
-template <typename T, int V> __device__ __forceinline__ void stp(T* p, const float (&f)[V]) {
-    PackF<T, V> q;
+__device__ __forceinline__ uint4 pack8(const float (&f)[V]) {
+    uint4 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
-    for (int i = 0; i < V; ++i) stf(&q.v[i], f[i]);
-    *reinterpret_cast<PackF<T, V>*>(p) = q;
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    return q;
+}
+__device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& q) { *reinterpret_cast<uint4*>(p) = q; }
+
+// Thread -> data mapping shared by both passes: lane_c = tid % cvv owns the 8-channel vector co = lane_c*8 of the K*c
+// attention channels (all R radix copies of it), lane_p = tid / cvv walks the chunk's pixels with stride pl = NT / cvv.
+struct Map {
+    int cvv, pl, lane_c, lane_p, co, kk, cc, nit;
+};
+__device__ __forceinline__ Map make_map(int NT, int KC, int c, int npx) {
+    Map m;
+    m.cvv = KC / V; m.pl = NT / m.cvv;
+    m.lane_c = threadIdx.x % m.cvv; m.lane_p = threadIdx.x / m.cvv;
+    m.co = m.lane_c * V; m.kk = m.co / c; m.cc = m.co % c;
+    m.nit = npx > 0 ? (npx + m.pl - 1) / m.pl : 0;
+    return m;
 }
 
-__device__ __forceinline__ float blk_reduce(float v, float* red, bool is_max) {
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+// pass 1 of both directions.  s[r][k] += U_r (x dV); optionally keeps the raw 16-byte vectors in shared memory
+// (cache_u[(it*R + r)*NT + tid], cache_d[it*NT + tid]: private to the thread, conflict-free, no barrier needed).
+template <int R, bool MUL, int NT>
+__device__ __forceinline__ void pass1(const Map& m, const __nv_bfloat16* up, int ucs, const __nv_bfloat16* dp, int dcs, int c,
+                                      int npx, float (&s)[R][V], uint4* cache_u, uint4* cache_d) {
+    constexpr int UN = MUL ? (R == 1 ? 8 : R == 2 ? 4 : 2) : (R == 1 ? 8 : R == 2 ? 4 : R == 3 ? 2 : 1);   // 5..8 independent 16-byte loads in flight per thread
+    const int tid = threadIdx.x;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { float t = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, t) : v + t; }
-    __syncthreads();
-    if (lane == 0) red[wid] = v;
-    __syncthreads();
-    float r = red[0];
-    for (int i = 1; i < nw; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
-    return r;
-}
-
-// phase 1 of both directions: per-channel sums over this CTA's pixel chunk (optionally times dv)
-template <typename T, int V, bool MUL>
-__device__ __forceinline__ void chunk_reduce(const tbi_splitatt& p, const tbi_view& u, const tbi_view& dv, float* raw, float* sm,
-                                             int n, int pbeg, int pend) {
-    const int hw = p.h * p.w, C = u.c, cv = C / V, R = p.radix, c = p.c;
-    const int cl = min(cv, (int)blockDim.x), pl = blockDim.x / cl;
-    const int lane_c = threadIdx.x % cl, lane_p = threadIdx.x / cl;
-    const T* ub = (const T*)u.ptr + (size_t)n * hw * u.cstride + u.coff;
-    const T* db = MUL ? (const T*)dv.ptr + (size_t)n * hw * dv.cstride + dv.coff : nullptr;
-    for (int cv0 = 0; cv0 < cv; cv0 += cl) {
-        const int ch = (cv0 + lane_c) * V;
-        float s[V];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int k = 0; k < V; ++k) s[k] = 0.f;
-        if (ch < C && lane_p < pl) {
-            const int kk = ch / (R * c), cc = ch % c;
-#pragma unroll 4
-            for (int px = pbeg + lane_p; px < pend; px += pl) {
-                float a[V];
-                ldp<T, V>(ub + (size_t)px * u.cstride + ch, a);
-                if (MUL) {
-                    float g[V];
-                    ldp<T, V>(db + (size_t)px * dv.cstride + kk * c + cc, g);
+        for (int k = 0; k < V; ++k) s[r][k] = 0.f;
+    for (int it = 0; it < m.nit; it += UN) {
+        uint4 q[UN][R], g[UN];
 #pragma unroll
-                    for (int k = 0; k < V; ++k) s[k] = fmaf(a[k], g[k], s[k]);
-                } else {
+        for (int i = 0; i < UN; ++i) {
+            const int px = m.lane_p + (it + i) * m.pl;
+            if (px < npx) {
 #pragma unroll
-                    for (int k = 0; k < V; ++k) s[k] += a[k];
-                }
+                for (int r = 0; r < R; ++r) q[i][r] = ld16(up + (size_t)px * ucs + r * c);
+                if (MUL) g[i] = ld16(dp + (size_t)px * dcs);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; ++r) q[i][r] = make_uint4(0u, 0u, 0u, 0u);
+                if (MUL) g[i] = make_uint4(0u, 0u, 0u, 0u);
             }
         }
 #pragma unroll
-        for (int k = 0; k < V; ++k) sm[(size_t)threadIdx.x * V + k] = s[k];
-        __syncthreads();
-        if (lane_p == 0 && ch < C) {
+        for (int i = 0; i < UN; ++i) {
+            float gv[V];
+            if (MUL) unpack8(g[i], gv);
 #pragma unroll
-            for (int k = 0; k < V; ++k) {
-                float tot = 0.f;
-                for (int q = 0; q < pl; ++q) tot += sm[(size_t)(q * cl + lane_c) * V + k];
-                atomicAdd(raw + (size_t)n * C + ch + k, tot);
+            for (int r = 0; r < R; ++r) {
+                float x[V];
+                unpack8(q[i][r], x);
+#pragma unroll
+                for (int k = 0; k < V; ++k) s[r][k] = MUL ? fmaf(x[k], gv[k], s[r][k]) : s[r][k] + x[k];
             }
+            if (cache_u != nullptr && it + i < m.nit) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) cache_u[((size_t)(it + i) * R + r) * NT + tid] = q[i][r];
+                if (MUL) cache_d[(size_t)(it + i) * NT + tid] = g[i];
+            }
+        }
+    }
+}
+
+// block-level reduction of the per-thread sums over the pixel lanes, PUSHED into every peer's parts[rank][(kk*R + r)*c + cc + k]
+// (distributed shared memory): after cluster barrier A every CTA holds all CS partial vectors locally -- a pull would cost a
+// remote round trip (measured ~1.3 us under load) on the critical path between the two passes
+template <int R, int NT>
+__device__ __forceinline__ void reduce_to_part(const Map& m, int c, float (&s)[R][V], float* tmp, float* parts, cg::cluster_group& cl,
+                                               int CS, int rank, int C) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const bool shfl = m.cvv < 32 && (m.cvv & (m.cvv - 1)) == 0;       // a warp holds 32/cvv pixel lanes of every channel vector
+    const int rows = shfl ? NT / 32 : m.pl;
+    const int row = shfl ? wid : m.lane_p;
+    const int width = m.cvv * V;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (shfl) {
+            for (int o = 16; o >= m.cvv; o >>= 1)
+#pragma unroll
+                for (int k = 0; k < V; ++k) s[r][k] += __shfl_xor_sync(0xffffffffu, s[r][k], o);
+        }
+        if ((!shfl && m.lane_p < m.pl) || (shfl && lane < m.cvv)) {
+            float4* d = reinterpret_cast<float4*>(tmp + (size_t)row * width + m.co);
+            d[0] = make_float4(s[r][0], s[r][1], s[r][2], s[r][3]);
+            d[1] = make_float4(s[r][4], s[r][5], s[r][6], s[r][7]);
+        }
+        __syncthreads();
+        for (int idx = tid; idx < width; idx += NT) {
+            float tot = 0.f;
+            for (int q = 0; q < rows; ++q) tot += tmp[(size_t)q * width + idx];
+            const int e = rank * C + ((idx / c) * R + r) * c + idx % c;
+            for (int rk = 0; rk < CS; ++rk) cl.map_shared_rank(parts, rk)[e] = tot;     // remote stores do not stall the thread
         }
         __syncthreads();
     }
 }
 
-// shared-memory layout of the per-image FC state (floats): g[K*c] | h1[K*c2] | att[K*R*c] | red[32] | tmp[...]
-template <typename T, int V>
-__global__ void __launch_bounds__(256) splitatt_fwd_fused_kernel(tbi_splitatt p, tbi_view u, tbi_view v, float* raw, int bpi, int ppb, int stage_w, int wofs) {
-    extern __shared__ float sm[];
-    cg::grid_group grid = cg::this_grid();
-    const int hw = p.h * p.w, c = p.c, c2 = p.c / 2, R = p.radix, K = p.kpaths, C = u.c;
-    const int n = blockIdx.x / bpi, chunk = blockIdx.x % bpi;
-    const int pbeg = chunk * ppb, pend = min(hw, pbeg + ppb);
-    // FC weights -> shared memory now (the loads overlap phase 1), so the FC chain between the phases never waits on L2
-    float* sw1 = sm + wofs; float* sw2 = sw1 + K * c * c2;
-    if (stage_w) {
-        for (int i = threadIdx.x; i < K * c * c2; i += blockDim.x) sw1[i] = __ldg(p.w1 + i);
-        for (int i = threadIdx.x; i < K * R * c2 * c; i += blockDim.x) sw2[i] = __ldg(p.w2 + i);
+__device__ __forceinline__ void slice_of(int total, int rank, int S, int& lo, int& hi) {
+    lo = (int)((long long)total * rank / S);
+    hi = (int)((long long)total * (rank + 1) / S);
+}
+
+// Every thread of every CTA of the cluster arrives (release: its shared-memory writes, local and remote, are ordered before
+// the barrier) and waits (acquire).  Subsumes __syncthreads().  The cooperative-groups cluster.sync() wraps the same two
+// instructions in two extra CTA barriers.
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// split form
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// out[i] for i in [lo,hi): consecutive threads take consecutive outputs, the input axis is split over `parts` thread groups
+// and summed through tmp.  partial(i, part, parts) returns this thread's partial sum; finish(i, sum) consumes the total.
+// Must be called by the whole CTA; ends with a CTA barrier.
+template <typename F, typename G>
+__device__ __forceinline__ void sliced_matvec(int lo, int hi, int n_in, int NT, float* tmp, F partial, G finish) {
+    const int tid = threadIdx.x;
+    for (int o0 = lo; o0 < hi; o0 += NT) {                  // uniform over the CTA
+        const int no = min(NT, hi - o0);
+        const int parts = min(NT / no, n_in);
+        const int ol = tid % no, part = tid / no;
+        if (part < parts) tmp[part * no + ol] = partial(o0 + ol, part, parts);
+        __syncthreads();
+        if (tid < no) {
+            float s = 0.f;
+            for (int q = 0; q < parts; ++q) s += tmp[q * no + tid];
+            finish(o0 + tid, s);
+        }
+        __syncthreads();
     }
-    chunk_reduce<T, V, false>(p, u, v, raw, sm, n, pbeg, pend);
-    __threadfence();
-    grid.sync();
-    // ---- FC chain for image n (all K cardinals) in shared memory
-    float* g = sm; float* h1 = g + K * c; float* att = h1 + K * c2; float* red = att + K * R * c;
+}
+
+// same with two sums per output
+template <typename F, typename G>
+__device__ __forceinline__ void sliced_matvec2(int lo, int hi, int n_in, int NT, float* tmp, F partial, G finish) {
+    const int tid = threadIdx.x;
+    float2* tmp2 = reinterpret_cast<float2*>(tmp);
+    for (int o0 = lo; o0 < hi; o0 += NT) {                  // uniform over the CTA
+        const int no = min(NT, hi - o0);
+        const int parts = min(NT / no, n_in);
+        const int ol = tid % no, part = tid / no;
+        if (part < parts) tmp2[part * no + ol] = partial(o0 + ol, part, parts);
+        __syncthreads();
+        if (tid < no) {
+            float2 s = make_float2(0.f, 0.f);
+            for (int q = 0; q < parts; ++q) { const float2 t = tmp2[q * no + tid]; s.x += t.x; s.y += t.y; }
+            finish(o0 + tid, s);
+        }
+        __syncthreads();
+    }
+}
+
+// FC layers: a layer whose weights are small is computed REDUNDANTLY by every CTA of the cluster (S = 1: no exchange, no
+// cluster barrier); a large one is SLICED over the cluster (S = CS: each CTA computes 1/CS of the outputs, pushes them into
+// every peer's shared memory, cluster barrier).  When `staged`, the weights (slices) and per-output parameters were copied
+// to shared memory by cp.async at kernel start, behind pass 1, so the chain between the two passes never waits on L2/HBM.
+struct FcPlan { int s1, s2, staged; unsigned long long* trace; };
+
+// debug timeline (scratch/trace_splitatt.py): thread 0 of every CTA stamps clock64 at the phase boundaries
+unsigned long long* g_sa_trace_host = nullptr;
+__device__ __forceinline__ void stamp(unsigned long long* tr, int slot) {
+    if (tr != nullptr && threadIdx.x == 0) {
+        unsigned long long v;
+        if (slot == 0 || slot == 15) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)); else v = (unsigned long long)clock64();
+        tr[(size_t)blockIdx.x * 16 + slot] = v;
+    }
+}
+
+template <int R, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) splitatt_fwd_cluster_kernel(tbi_splitatt p, tbi_view u, tbi_view v, int cache, FcPlan fc) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cl = cg::this_cluster();
+    const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = NT >> 5;
+    const int hw = p.h * p.w, c = p.c, c2 = p.c / 2, K = p.kpaths, C = K * R * c, KC = K * c, KC2 = K * c2;
+    const int n = blockIdx.x / CS;
+    const int ppb = (hw + CS - 1) / CS, pbeg = min(hw, rank * ppb), pend = min(hw, pbeg + ppb), npx = pend - pbeg;
+    const int n1max = (KC2 + fc.s1 - 1) / fc.s1, n2max = (C + fc.s2 - 1) / fc.s2;
+    int lo1, hi1, lo2, hi2;
+    slice_of(KC2, fc.s1 > 1 ? rank : 0, fc.s1, lo1, hi1);   // dense1 outputs of this CTA
+    slice_of(C, fc.s2 > 1 ? rank : 0, fc.s2, lo2, hi2);     // dense2 outputs of this CTA
+    const int no1 = hi1 - lo1, no2 = hi2 - lo2;
+    float* parts = sm;                                      // [CS][C] every CTA's channel sums (pushed by the peers)
+    float* g = parts + CS * C;                              // [KC]
+    float* h1 = g + KC;                                     // [KC2] (slices pushed by the peers when s1 > 1)
+    float* att = h1 + KC2;                                  // [C]   (slices pushed by the peers when s2 > 1)
+    float* tmp = att + C;                                   // [NT*V]
+    float* sw1 = tmp + NT * V;                              // [c][no1]      staged only
+    float* sp1 = sw1 + (size_t)c * n1max;                   // [5][n1max]    b1, gamma, beta, mean, var
+    float* sw2 = sp1 + 5 * n1max;                           // [c2][no2]
+    float* sb2 = sw2 + (size_t)c2 * n2max;                  // [no2]
+    const int staged_floats = fc.staged ? ((n1max * (c + 5) + n2max * (c2 + 1) + 3) & ~3) : 0;
+    uint4* cache_u = cache ? reinterpret_cast<uint4*>(sw1 + staged_floats) : nullptr;
+    if (fc.staged) {
+        for (int idx = tid; idx < c * no1; idx += NT) {
+            const int ch = idx / no1, i = lo1 + idx - ch * no1, k = i / c2, j = i - k * c2;
+            cp_async4(sw1 + idx, p.w1 + ((size_t)k * c + ch) * c2 + j);
+        }
+        for (int idx = tid; idx < no1; idx += NT) {
+            cp_async4(sp1 + idx, p.b1 + lo1 + idx);
+            cp_async4(sp1 + n1max + idx, p.gamma + lo1 + idx);
+            cp_async4(sp1 + 2 * n1max + idx, p.beta + lo1 + idx);
+            cp_async4(sp1 + 3 * n1max + idx, p.mean + lo1 + idx);
+            cp_async4(sp1 + 4 * n1max + idx, p.var + lo1 + idx);
+        }
+        for (int idx = tid; idx < c2 * no2; idx += NT) {
+            const int j = idx / no2, i = lo2 + idx - j * no2, kr = i / c, ch = i - kr * c;
+            cp_async4(sw2 + idx, p.w2 + ((size_t)kr * c2 + j) * c + ch);
+        }
+        for (int idx = tid; idx < no2; idx += NT) cp_async4(sb2 + idx, p.b2 + lo2 + idx);
+    }
+    const Map m = make_map(NT, KC, c, npx);
+    stamp(fc.trace, 0); stamp(fc.trace, 1);
+    cluster_arrive();                                       // "this CTA is running": waited for in front of the first remote store
+    const __nv_bfloat16* up = (const __nv_bfloat16*)u.ptr + ((size_t)n * hw + pbeg) * u.cstride + u.coff + (size_t)m.kk * R * c + m.cc;
+    {
+        float s[R][V];
+        pass1<R, false, NT>(m, up, u.cstride, nullptr, 0, c, npx, s, cache_u, nullptr);
+        stamp(fc.trace, 2);
+        cluster_wait();                                     // every peer has started (they arrived at their first instruction)
+        reduce_to_part<R, NT>(m, c, s, tmp, parts, cl, CS, rank, C);
+    }
+    cp_async_wait_all();
+    stamp(fc.trace, 3);
+    cluster_barrier();                                      // A: every CTA's part[] is complete (and this CTA's staged copies)
+    stamp(fc.trace, 4);
     const float inv_hw = 1.f / (float)hw;
-    const float* rw = raw + (size_t)n * C;
-    for (int i = threadIdx.x; i < K * c; i += blockDim.x) {
-        const int k = i / c, ch = i % c;
+    for (int i = tid; i < KC; i += NT) {
+        const int k = i / c, ch = i - k * c;
         float s = 0.f;
-        for (int r = 0; r < R; ++r) s += __ldcg(rw + (k * R + r) * c + ch);
+        for (int rk = 0; rk < CS; ++rk)
+#pragma unroll
+            for (int r = 0; r < R; ++r) s += parts[rk * C + (k * R + r) * c + ch];
         g[i] = s * inv_hw;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < K * c2; i += blockDim.x) {
-        const int k = i / c2, j = i % c2;
-        float q = p.b1[i];
-        const float* w1 = (stage_w ? sw1 : p.w1) + (size_t)k * c * c2 + j;
-#pragma unroll 32
-        for (int ch = 0; ch < c; ++ch) q = fmaf(g[k * c + ch], w1[(size_t)ch * c2], q);
-        const float sc = p.gamma[i] * rsqrtf(p.var[i] + p.bn_eps);
-        h1[i] = act_apply(p.act, (q - p.mean[i]) * sc + p.beta[i]);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < K * R * c; i += blockDim.x) {
-        const int ch = i % c, kr = i / c, k = kr / R;
-        float z = p.b2[i];
-        const float* w2 = (stage_w ? sw2 : p.w2) + (size_t)kr * c2 * c + ch;
-#pragma unroll 32
-        for (int j = 0; j < c2; ++j) z = fmaf(h1[k * c2 + j], w2[(size_t)j * c], z);
-        att[i] = z;
-    }
-    __syncthreads();
-    for (int kr = 0; kr < K * R; ++kr) {                    // softmax over the channel axis (reference quirk) / sigmoid
+    stamp(fc.trace, 5);
+    sliced_matvec(lo1, hi1, c, NT, tmp,                     // dense1 + BN + act
+        [&](int i, int part_, int parts) {
+            const int k = i / c2, j = i - k * c2;
+            const float* gk = g + k * c;
+            float s = 0.f;
+            if (fc.staged) {
+                const float* w = sw1 + (i - lo1);
+#pragma unroll 8
+                for (int ch = part_; ch < c; ch += parts) s = fmaf(gk[ch], w[ch * no1], s);
+            } else {
+                const float* w = p.w1 + (size_t)k * c * c2 + j;
+#pragma unroll 8
+                for (int ch = part_; ch < c; ch += parts) s = fmaf(gk[ch], __ldg(w + (size_t)ch * c2), s);
+            }
+            return s;
+        },
+        [&](int i, float s) {
+            const int ol = i - lo1;
+            const float b1 = fc.staged ? sp1[ol] : p.b1[i], ga = fc.staged ? sp1[n1max + ol] : p.gamma[i];
+            const float be = fc.staged ? sp1[2 * n1max + ol] : p.beta[i], mu = fc.staged ? sp1[3 * n1max + ol] : p.mean[i];
+            const float va = fc.staged ? sp1[4 * n1max + ol] : p.var[i];
+            const float hv = act_apply(p.act, (s + b1 - mu) * (ga * rsqrtf(va + p.bn_eps)) + be);
+            if (fc.s1 > 1) { for (int rk = 0; rk < CS; ++rk) cl.map_shared_rank(h1, rk)[i] = hv; }
+            else h1[i] = hv;
+        });
+    if (fc.s1 > 1) cluster_barrier();                       // B: h1 complete everywhere
+    stamp(fc.trace, 6);
+    sliced_matvec(lo2, hi2, c2, NT, tmp,                    // dense2
+        [&](int i, int part_, int parts) {
+            const int kr = i / c, ch = i - kr * c, k = kr / R;
+            const float* hk = h1 + k * c2;
+            float s = 0.f;
+            if (fc.staged) {
+                const float* w = sw2 + (i - lo2);
+#pragma unroll 8
+                for (int j = part_; j < c2; j += parts) s = fmaf(hk[j], w[j * no2], s);
+            } else {
+                const float* w = p.w2 + (size_t)kr * c2 * c + ch;
+#pragma unroll 8
+                for (int j = part_; j < c2; j += parts) s = fmaf(hk[j], __ldg(w + (size_t)j * c), s);
+            }
+            return s;
+        },
+        [&](int i, float s) {
+            const float z = s + (fc.staged ? sb2[i - lo2] : p.b2[i]);
+            if (fc.s2 > 1) { for (int rk = 0; rk < CS; ++rk) cl.map_shared_rank(att, rk)[i] = z; }
+            else att[i] = z;
+        });
+    if (fc.s2 > 1) cluster_barrier();                       // C: logits complete everywhere; no remote access after this point
+    stamp(fc.trace, 7);
+    for (int kr = wid; kr < K * R; kr += nwarp) {           // softmax over the channel axis (reference quirk) / sigmoid
         float* a = att + kr * c;
         if (R == 1) {
-            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) a[ch] = 1.f / (1.f + expf(-a[ch]));
+            for (int ch = lane; ch < c; ch += 32) a[ch] = 1.f / (1.f + expf(-a[ch]));
         } else {
-            float lm = -INFINITY;
-            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) lm = fmaxf(lm, a[ch]);
-            const float mx = blk_reduce(lm, red, true);
+            float mx = -INFINITY;
+            for (int ch = lane; ch < c; ch += 32) mx = fmaxf(mx, a[ch]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             float ls = 0.f;
-            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) { const float e = expf(a[ch] - mx); a[ch] = e; ls += e; }
-            const float inv = 1.f / blk_reduce(ls, red, false);
-            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) a[ch] *= inv;
+            for (int ch = lane; ch < c; ch += 32) { const float e = expf(a[ch] - mx); a[ch] = e; ls += e; }
+            const float inv = 1.f / warp_sum(ls);
+            for (int ch = lane; ch < c; ch += 32) a[ch] *= inv;
         }
-        __syncthreads();
     }
-    if (chunk == 0) {                                       // keep the per-image state for the backward pass
-        for (int i = threadIdx.x; i < K * c; i += blockDim.x) p.gap[(size_t)n * K * c + i] = g[i];
-        for (int i = threadIdx.x; i < K * c2; i += blockDim.x) p.h1[(size_t)n * K * c2 + i] = h1[i];
-        for (int i = threadIdx.x; i < K * R * c; i += blockDim.x) p.att[(size_t)n * K * R * c + i] = att[i];
+    __syncthreads();
+    stamp(fc.trace, 8);
+    if (rank == 0) {                                        // keep the per-image state for the backward pass
+        for (int i = tid; i < KC; i += NT) p.gap[(size_t)n * KC + i] = g[i];
+        for (int i = tid; i < KC2; i += NT) p.h1[(size_t)n * KC2 + i] = h1[i];
+        for (int i = tid; i < C; i += NT) p.att[(size_t)n * C + i] = att[i];
     }
-    // ---- recombine over the same chunk (U is L2-resident)
-    const int cvv = (K * c) / V;
-    const T* ub = (const T*)u.ptr + (size_t)n * hw * u.cstride + u.coff;
-    T* vb = (T*)v.ptr + (size_t)n * hw * v.cstride + v.coff;
-    const int npx = pend - pbeg;
-    for (int i = threadIdx.x; i < npx * cvv; i += blockDim.x) {
-        const int co = (i % cvv) * V, px = pbeg + i / cvv;
-        const int k = co / c, cc = co % c;
-        float o[V];
+    // ---- pass 2: recombine over the same chunk, same mapping, LAST pixels first (the most recently read lines are the ones
+    // most likely still in L2 when the tensors in flight exceed it); the chunk's lines are dead after this read (.cs)
+    {
+        float a[R][V];
 #pragma unroll
-        for (int q = 0; q < V; ++q) o[q] = 0.f;
-        const float* a = att + (size_t)k * R * c + cc;
-        const T* up = ub + (size_t)px * u.cstride + (size_t)k * R * c + cc;
-        for (int r = 0; r < R; ++r) {
-            float x[V];
-            ldp<T, V>(up + (size_t)r * c, x);
+        for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int q = 0; q < V; ++q) o[q] = fmaf(x[q], a[r * c + q], o[q]);
+            for (int k = 0; k < V; ++k) a[r][k] = att[(m.kk * R + r) * c + m.cc + k];
+        __nv_bfloat16* vp = (__nv_bfloat16*)v.ptr + ((size_t)n * hw + pbeg) * v.cstride + v.coff + m.co;
+        constexpr int UN = R == 1 ? 8 : R == 2 ? 4 : R == 3 ? 2 : 1;
+        for (int it = ((m.nit - 1) / UN) * UN; it >= 0; it -= UN) {
+            uint4 q[UN][R];
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                const int px = m.lane_p + (it + i) * m.pl;
+                if (px < npx) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        q[i][r] = cache_u ? cache_u[((size_t)(it + i) * R + r) * NT + tid]
+                                          : __ldcs(reinterpret_cast<const uint4*>(up + (size_t)px * u.cstride + r * c));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                const int px = m.lane_p + (it + i) * m.pl;
+                if (px < npx) {
+                    float o[V];
+#pragma unroll
+                    for (int k = 0; k < V; ++k) o[k] = 0.f;
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float x[V];
+                        unpack8(q[i][r], x);
+#pragma unroll
+                        for (int k = 0; k < V; ++k) o[k] = fmaf(x[k], a[r][k], o[k]);
+                    }
+                    st16(vp + (size_t)px * v.cstride, pack8(o));
+                }
+            }
         }
-        stp<T, V>(vb + (size_t)px * v.cstride + co, o);
     }
+    stamp(fc.trace, 9); stamp(fc.trace, 15);
 }
 
 // scratch layout (as tbi_split_attention_bwd): dz [n][K][R][c] | dgap [n][K][c] | dbn [n][K][c2] | xhat [n][K][c2]
-template <typename T, int V>
-__global__ void __launch_bounds__(256) splitatt_bwd_fused_kernel(tbi_splitatt p, tbi_view u, tbi_view dv, tbi_view du, float* scratch, int bpi, int ppb,
-                                                                 int stage_w, int wofs) {
-    extern __shared__ float sm[];
-    cg::grid_group grid = cg::this_grid();
-    const int hw = p.h * p.w, c = p.c, c2 = p.c / 2, R = p.radix, K = p.kpaths, C = u.c, N = p.n;
-    const int n = blockIdx.x / bpi, chunk = blockIdx.x % bpi;
-    const int pbeg = chunk * ppb, pend = min(hw, pbeg + ppb);
-    float* sw1 = sm + wofs; float* sw2 = sw1 + K * c * c2;
-    if (stage_w) {
-        for (int i = threadIdx.x; i < K * c * c2; i += blockDim.x) sw1[i] = __ldg(p.w1 + i);
-        for (int i = threadIdx.x; i < K * R * c2 * c; i += blockDim.x) sw2[i] = __ldg(p.w2 + i);
+template <int R, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) splitatt_bwd_cluster_kernel(tbi_splitatt p, tbi_view u, tbi_view dv, tbi_view du, float* scratch,
+                                                                                      int cache, FcPlan fc) {
+    extern __shared__ __align__(16) float sm[];
+    cg::cluster_group cl = cg::this_cluster();
+    const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = NT >> 5;
+    const int hw = p.h * p.w, c = p.c, c2 = p.c / 2, K = p.kpaths, C = K * R * c, KC = K * c, KC2 = K * c2, N = p.n;
+    const int n = blockIdx.x / CS;
+    const int ppb = (hw + CS - 1) / CS, pbeg = min(hw, rank * ppb), pend = min(hw, pbeg + ppb), npx = pend - pbeg;
+    const int n1max = (KC2 + fc.s1 - 1) / fc.s1, n2max = (KC + fc.s2 - 1) / fc.s2;
+    int lo1, hi1, lo2, hi2;
+    slice_of(KC2, fc.s1 > 1 ? rank : 0, fc.s1, lo1, hi1);   // dh1 / dq outputs of this CTA
+    slice_of(KC, fc.s2 > 1 ? rank : 0, fc.s2, lo2, hi2);    // dgap outputs of this CTA
+    const int no1 = hi1 - lo1, no2 = hi2 - lo2;
+    float* parts = sm;                                      // [CS][C] every CTA's da sums (pushed by the peers)
+    float* att = parts + CS * C;                            // [C]
+    float* dz = att + C;                                    // [C]
+    float* gg = dz + C;                                     // [KC]
+    float* hh = gg + KC;                                    // [KC2]
+    float* dq = hh + KC2;                                   // [KC2] (slices pushed by the peers when s1 > 1)
+    float* dg = dq + KC2;                                   // [KC]  (slices pushed by the peers when s2 > 1)
+    float* tmp = dg + KC;                                   // [NT*V]
+    // staged FC operands, output index fastest with an odd pitch (conflict-free for the copy and for the matvec)
+    const int ld1 = n1max | 1, ld2 = n2max | 1;
+    float* swz = tmp + NT * V;                              // [R*c][ld1]    W2: (r, ch) x output j
+    float* swq = swz + (size_t)R * c * ld1;                 // [c][ld1]      W1: ch x output j
+    float* sp1 = swq + (size_t)c * ld1;                     // [4][n1max]    b1, gamma, mean, var
+    float* swg = sp1 + 4 * n1max;                           // [c2][ld2]     W1: j x output (k, ch)
+    const int staged_floats = fc.staged ? (((R + 1) * c * ld1 + 4 * n1max + c2 * ld2 + 3) & ~3) : 0;
+    const Map m = make_map(NT, KC, c, npx);
+    stamp(fc.trace, 0); stamp(fc.trace, 1);
+    cluster_arrive();                                       // "this CTA is running": waited for in front of the first remote store
+    uint4* cache_u = cache ? reinterpret_cast<uint4*>(swz + staged_floats) : nullptr;
+    uint4* cache_d = cache ? cache_u + (size_t)m.nit * R * NT : nullptr;
+    if (fc.staged) {
+        for (int idx = tid; idx < no1 * R * c; idx += NT) { // global address contiguous in ch
+            const int ol = idx / (R * c), e = idx - ol * R * c, r = e / c, ch = e - r * c, i = lo1 + ol, k = i / c2, j = i - k * c2;
+            cp_async4(swz + (size_t)e * ld1 + ol, p.w2 + (((size_t)k * R + r) * c2 + j) * c + ch);
+        }
+        for (int idx = tid; idx < no1 * c; idx += NT) {     // global address contiguous in j
+            const int ch = idx / no1, ol = idx - ch * no1, i = lo1 + ol, k = i / c2, j = i - k * c2;
+            cp_async4(swq + (size_t)ch * ld1 + ol, p.w1 + ((size_t)k * c + ch) * c2 + j);
+        }
+        for (int idx = tid; idx < no1; idx += NT) {
+            cp_async4(sp1 + idx, p.b1 + lo1 + idx);
+            cp_async4(sp1 + n1max + idx, p.gamma + lo1 + idx);
+            cp_async4(sp1 + 2 * n1max + idx, p.mean + lo1 + idx);
+            cp_async4(sp1 + 3 * n1max + idx, p.var + lo1 + idx);
+        }
+        for (int idx = tid; idx < no2 * c2; idx += NT) {    // rows lo2.. of W1 are contiguous
+            const int ol = idx / c2, j = idx - ol * c2;
+            cp_async4(swg + (size_t)j * ld2 + ol, p.w1 + (size_t)lo2 * c2 + idx);
+        }
     }
-    const float* W1 = stage_w ? sw1 : p.w1; const float* W2 = stage_w ? sw2 : p.w2;
-    chunk_reduce<T, V, true>(p, u, dv, scratch, sm, n, pbeg, pend);          // da accumulates in the dz region
-    __threadfence();
-    grid.sync();
-    float* att = sm; float* dz = att + K * R * c; float* dq = dz + K * R * c; float* dg = dq + K * c2; float* red = dg + K * c;
-    const float* gatt = p.att + (size_t)n * K * R * c;
-    const float* gg = p.gap + (size_t)n * K * c;
-    const float* gh1 = p.h1 + (size_t)n * K * c2;
-    const float* da = scratch + (size_t)n * C;
-    for (int i = threadIdx.x; i < K * R * c; i += blockDim.x) { att[i] = gatt[i]; dz[i] = __ldcg(da + i); }
+    for (int i = tid; i < C; i += NT) att[i] = p.att[(size_t)n * C + i];
+    for (int i = tid; i < KC; i += NT) gg[i] = p.gap[(size_t)n * KC + i];
+    for (int i = tid; i < KC2; i += NT) hh[i] = p.h1[(size_t)n * KC2 + i];
+    const __nv_bfloat16* up = (const __nv_bfloat16*)u.ptr + ((size_t)n * hw + pbeg) * u.cstride + u.coff + (size_t)m.kk * R * c + m.cc;
+    const __nv_bfloat16* dp = (const __nv_bfloat16*)dv.ptr + ((size_t)n * hw + pbeg) * dv.cstride + dv.coff + m.co;
+    {
+        float s[R][V];
+        pass1<R, true, NT>(m, up, u.cstride, dp, dv.cstride, c, npx, s, cache_u, cache_d);
+        stamp(fc.trace, 2);
+        cluster_wait();                                     // every peer has started (they arrived at their first instruction)
+        reduce_to_part<R, NT>(m, c, s, tmp, parts, cl, CS, rank, C);
+    }
+    cp_async_wait_all();
+    stamp(fc.trace, 3);
+    cluster_barrier();                                      // A
+    stamp(fc.trace, 4);
+    for (int i = tid; i < C; i += NT) {
+        float s = 0.f;
+        for (int rk = 0; rk < CS; ++rk) s += parts[rk * C + i];
+        dz[i] = s;                                          // da
+    }
     __syncthreads();
-    for (int kr = 0; kr < K * R; ++kr) {
-        float* a = att + kr * c; float* z = dz + kr * c;
+    stamp(fc.trace, 5);
+    for (int kr = wid; kr < K * R; kr += nwarp) {           // softmax / sigmoid backward: da -> dz
+        const float* a = att + kr * c; float* z = dz + kr * c;
         if (R == 1) {
-            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) z[ch] = a[ch] * (1.f - a[ch]) * z[ch];
+            for (int ch = lane; ch < c; ch += 32) z[ch] = a[ch] * (1.f - a[ch]) * z[ch];
         } else {
             float l = 0.f;
-            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) l += a[ch] * z[ch];
-            const float dot = blk_reduce(l, red, false);
-            for (int ch = threadIdx.x; ch < c; ch += blockDim.x) z[ch] = a[ch] * (z[ch] - dot);
+            for (int ch = lane; ch < c; ch += 32) l = fmaf(a[ch], z[ch], l);
+            const float dot = warp_sum(l);
+            for (int ch = lane; ch < c; ch += 32) z[ch] = a[ch] * (z[ch] - dot);
         }
-        __syncthreads();
     }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    __syncthreads();
+    float* sdz = scratch + (size_t)n * C;
+    float* sdg = scratch + (size_t)N * C + (size_t)n * KC;
+    float* sdbn = scratch + (size_t)N * C + (size_t)N * KC + (size_t)n * KC2;
+    float* sxh = sdbn + (size_t)N * KC2;
+    if (rank == 0) for (int i = tid; i < C; i += NT) sdz[i] = dz[i];
+    const bool own1 = fc.s1 > 1 || rank == 0, own2 = fc.s2 > 1 || rank == 0;      // who writes the image's FC state to scratch
+    sliced_matvec2(lo1, hi1, c, NT, tmp,                    // dh1 = sum_r dz_r W2_r^T and the pre-BN value of dense1
+        [&](int i, int part_, int parts) {
+            const int k = i / c2, j = i - k * c2, ol = i - lo1;
+            const float* z = dz + k * R * c;
+            const float* gk = gg + k * c;
+            float s = 0.f, q = 0.f;
+            if (fc.staged) {
 #pragma unroll 4
-    for (int i = wid; i < K * c2; i += nwarp) {              // dh1 = sum_r dz_r W2_r^T : a warp per output, lanes over channels
-        const int k = i / c2, j = i % c2;
-        float s = 0.f;
-        for (int r = 0; r < R; ++r) {
-            const float* w2 = W2 + (((size_t)k * R + r) * c2 + j) * c;
-            for (int ch = lane; ch < c; ch += 32) s = fmaf(dz[(k * R + r) * c + ch], w2[ch], s);
-        }
-        s = warp_sum(s);
-        if (lane == 0) dq[i] = s;
-    }
-    __syncthreads();
-    float* sdbn = scratch + (size_t)N * K * R * c + (size_t)N * K * c + (size_t)n * K * c2;
-    float* sxh = sdbn + (size_t)N * K * c2;
-    for (int i = threadIdx.x; i < K * c2; i += blockDim.x) {
-        const int k = i / c2, j = i % c2;
-        float q = p.b1[i];
-        const float* w1 = W1 + (size_t)k * c * c2 + j;
-#pragma unroll 32
-        for (int ch = 0; ch < c; ++ch) q = fmaf(gg[k * c + ch], w1[(size_t)ch * c2], q);
-        const float istd = rsqrtf(p.var[i] + p.bn_eps);
-        const float d = dq[i] * act_grad_from_out(p.act, gh1[i]);
-        if (chunk == 0) { sdbn[i] = d; sxh[i] = (q - p.mean[i]) * istd; }
-        dq[i] = d * p.gamma[i] * istd;
-    }
-    __syncthreads();
+                for (int e = part_; e < R * c; e += parts) s = fmaf(z[e], swz[(size_t)e * ld1 + ol], s);
 #pragma unroll 4
-    for (int i = wid; i < K * c; i += nwarp) {
-        const int k = i / c, ch = i % c;
-        float s = 0.f;
-        const float* w1 = W1 + ((size_t)k * c + ch) * c2;
-        for (int j = lane; j < c2; j += 32) s = fmaf(dq[k * c2 + j], w1[j], s);
-        s = warp_sum(s);
-        if (lane == 0) dg[i] = s;
-    }
-    __syncthreads();
-    if (chunk == 0) {
-        float* sdz = scratch + (size_t)n * C;                // overwrite da with dz for the parameter-gradient kernel
-        float* sdg = scratch + (size_t)N * K * R * c + (size_t)n * K * c;
-        // every CTA of the image has already copied da into shared memory: the grid.sync below orders this write after them
-        for (int i = threadIdx.x; i < K * c; i += blockDim.x) sdg[i] = dg[i];
-        (void)sdz;
-    }
-    grid.sync();
-    if (chunk == 0) {
-        float* sdz = scratch + (size_t)n * C;
-        for (int i = threadIdx.x; i < K * R * c; i += blockDim.x) sdz[i] = dz[i];
-    }
-    // ---- dU over the same chunk
-    const float inv_hw = 1.f / (float)hw;
-    const int cvv = (K * c) / V;
-    const T* ub = (const T*)u.ptr + (size_t)n * hw * u.cstride + u.coff;
-    const T* db = (const T*)dv.ptr + (size_t)n * hw * dv.cstride + dv.coff;
-    T* dub = (T*)du.ptr + (size_t)n * hw * du.cstride + du.coff;
-    const int npx = pend - pbeg;
-    for (int i = threadIdx.x; i < npx * cvv; i += blockDim.x) {
-        const int co = (i % cvv) * V, px = pbeg + i / cvv;
-        const int k = co / c, cc = co % c;
-        float gv[V];
-        ldp<T, V>(db + (size_t)px * dv.cstride + co, gv);
-        const float* a = att + (size_t)k * R * c + cc;
-        const float* dgp = dg + k * c + cc;
-        const size_t uo = (size_t)k * R * c + cc;
-        for (int r = 0; r < R; ++r) {
-            float x[V], o[V];
-            ldp<T, V>(ub + (size_t)px * u.cstride + uo + (size_t)r * c, x);
+                for (int ch = part_; ch < c; ch += parts) q = fmaf(gk[ch], swq[(size_t)ch * ld1 + ol], q);
+            } else {
+                for (int e = part_; e < R * c; e += parts) {
+                    const int r = e / c, ch = e - r * c;
+                    s = fmaf(z[e], __ldg(p.w2 + (((size_t)k * R + r) * c2 + j) * c + ch), s);
+                }
+                for (int ch = part_; ch < c; ch += parts) q = fmaf(gk[ch], __ldg(p.w1 + ((size_t)k * c + ch) * c2 + j), q);
+            }
+            return make_float2(s, q);
+        },
+        [&](int i, float2 sq) {
+            const int ol = i - lo1;
+            const float b1 = fc.staged ? sp1[ol] : p.b1[i], ga = fc.staged ? sp1[n1max + ol] : p.gamma[i];
+            const float mu = fc.staged ? sp1[2 * n1max + ol] : p.mean[i], va = fc.staged ? sp1[3 * n1max + ol] : p.var[i];
+            const float istd = rsqrtf(va + p.bn_eps);
+            const float d = sq.x * act_grad_from_out(p.act, hh[i]);
+            if (own1) { sdbn[i] = d; sxh[i] = (sq.y + b1 - mu) * istd; }
+            const float dqv = d * ga * istd;
+            if (fc.s1 > 1) { for (int rk = 0; rk < CS; ++rk) cl.map_shared_rank(dq, rk)[i] = dqv; }
+            else dq[i] = dqv;
+        });
+    if (fc.s1 > 1) cluster_barrier();                       // B: dq complete everywhere
+    stamp(fc.trace, 6);
+    sliced_matvec(lo2, hi2, c2, NT, tmp,                    // dgap = dq W1^T
+        [&](int i, int part_, int parts) {
+            const int k = i / c, ol = i - lo2;
+            const float* dk = dq + k * c2;
+            float s = 0.f;
+            if (fc.staged) {
+#pragma unroll 4
+                for (int j = part_; j < c2; j += parts) s = fmaf(dk[j], swg[(size_t)j * ld2 + ol], s);
+            } else {
+                const float* w1 = p.w1 + (size_t)i * c2;    // row (k*c + ch) of W1
+                for (int j = part_; j < c2; j += parts) s = fmaf(dk[j], __ldg(w1 + j), s);
+            }
+            return s;
+        },
+        [&](int i, float s) {
+            if (own2) sdg[i] = s;
+            if (fc.s2 > 1) { for (int rk = 0; rk < CS; ++rk) cl.map_shared_rank(dg, rk)[i] = s; }
+            else dg[i] = s;
+        });
+    if (fc.s2 > 1) cluster_barrier();                       // C: dgap complete everywhere; no remote access after this point
+    stamp(fc.trace, 7); stamp(fc.trace, 8);
+    // ---- pass 2: dU over the same chunk, same mapping, last pixels first; dead lines read and written with .cs
+    {
+        const float inv_hw = 1.f / (float)hw;
+        float a[R][V], dgs[V];
 #pragma unroll
-            for (int q = 0; q < V; ++q) o[q] = (gv[q] * a[r * c + q] + dgp[q] * inv_hw) * act_grad_from_out(p.act, x[q]);
-            stp<T, V>(dub + (size_t)px * du.cstride + uo + (size_t)r * c, o);
+        for (int k = 0; k < V; ++k) dgs[k] = dg[m.co + k] * inv_hw;
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int k = 0; k < V; ++k) a[r][k] = att[(m.kk * R + r) * c + m.cc + k];
+        __nv_bfloat16* dup = (__nv_bfloat16*)du.ptr + ((size_t)n * hw + pbeg) * du.cstride + du.coff + (size_t)m.kk * R * c + m.cc;
+        constexpr int UN = R == 1 ? 8 : R == 2 ? 4 : 2;
+        for (int it = ((m.nit - 1) / UN) * UN; it >= 0; it -= UN) {
+            uint4 q[UN][R], gq[UN];
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                const int px = m.lane_p + (it + i) * m.pl;
+                if (px < npx) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r)
+                        q[i][r] = cache_u ? cache_u[((size_t)(it + i) * R + r) * NT + tid]
+                                          : __ldcs(reinterpret_cast<const uint4*>(up + (size_t)px * u.cstride + r * c));
+                    gq[i] = cache_u ? cache_d[(size_t)(it + i) * NT + tid] : __ldcs(reinterpret_cast<const uint4*>(dp + (size_t)px * dv.cstride));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < UN; ++i) {
+                const int px = m.lane_p + (it + i) * m.pl;
+                if (px < npx) {
+                    float gv[V];
+                    unpack8(gq[i], gv);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        float x[V], o[V];
+                        unpack8(q[i][r], x);
+#pragma unroll
+                        for (int k = 0; k < V; ++k) o[k] = fmaf(gv[k], a[r][k], dgs[k]) * act_grad_from_out(p.act, x[k]);
+                        __stcs(reinterpret_cast<uint4*>(dup + (size_t)px * du.cstride + r * c), pack8(o));
+                    }
+                }
+            }
         }
     }
+    stamp(fc.trace, 9); stamp(fc.trace, 15);
 }
 
-struct FusedPlan { int bpi, ppb, grid, stage_w, wofs; size_t smem; };
+struct ClusterPlan { int cs, nt, cache; size_t smem; FcPlan fc; };
 
-template <typename KernelT>
-bool plan_fused(const tbi_splitatt* p, KernelT kernel, size_t fc_floats, int V, FusedPlan* fp) {
-    const int hw = p->h * p->w;
-    const size_t base_floats = fc_floats > (size_t)256 * V ? fc_floats : (size_t)256 * V;
-    const size_t w_floats = (size_t)p->kpaths * p->c * (p->c / 2) * (1 + p->radix);
-    fp->stage_w = w_floats * sizeof(float) <= 48 * 1024 ? 1 : 0;
-    fp->wofs = (int)((base_floats + 3) & ~(size_t)3);
-    const size_t smem = sizeof(float) * (fp->wofs + (fp->stage_w ? w_floats : 0)) + 256;
-    if (smem > 160 * 1024) return false;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); return false; }
-    const int cap = per_sm * tbi_sm_count();
-    if (cap < p->n) return false;
-    int bpi = cap / p->n;
-    const int max_bpi = (hw + 63) / 64;
-    if (bpi > max_bpi) bpi = max_bpi;
-    static const int bpi_cap = getenv("TBI_SA_BPI") ? atoi(getenv("TBI_SA_BPI")) : 32;
-    if (bpi > bpi_cap) bpi = bpi_cap;
-    if (bpi < 1) bpi = 1;
-    fp->ppb = (hw + bpi - 1) / bpi;
-    fp->bpi = (hw + fp->ppb - 1) / fp->ppb;
-    fp->grid = fp->bpi * p->n;
-    fp->smem = smem;
-    return true;
+int env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+
+// bwd = 0: forward kernel, 1: backward kernel.  The shared-memory carve-up here must match the kernels'.
+bool make_plan(const tbi_splitatt* p, int bwd, ClusterPlan* pl) {
+    const int K = p->kpaths, R = p->radix, c = p->c, c2 = c / 2;
+    const int hw = p->h * p->w, KC = K * c, KC2 = K * c2, C = K * R * c, cvv = KC / V;
+    int cs = env_int("TBI_SA_CS", 0);
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8 && cs != 16) {
+        cs = 8;
+        while (cs > 1 && (hw + cs - 1) / cs < 32) cs >>= 1;
+    }
+    const int npx = (hw + cs - 1) / cs;
+    int nt = env_int("TBI_SA_NT", 0);
+    if (nt != 256 && nt != 512) nt = (!bwd && (long long)npx * cvv >= 512 * 4) ? 512 : 256;
+    if (cvv < 1 || cvv > nt || nt % cvv != 0) return false;
+    const int nit = (npx + nt / cvv - 1) / (nt / cvv);
+    // FC plan: small layers redundantly per CTA, large ones sliced over the cluster.  Weight floats each step reads over all K:
+    const size_t w_a = bwd ? (size_t)K * (R + 1) * c2 * c : (size_t)K * c * c2;
+    const size_t w_b = bwd ? (size_t)K * c * c2 : (size_t)K * R * c2 * c;
+    const int out_a = KC2, out_b = bwd ? KC : C;
+    const int slice_mode = env_int("TBI_SA_SLICE", 0);      // 0 auto, 1 never slice, 2 always slice (tests)
+    const size_t small = 32 * 1024 / sizeof(float);
+    pl->fc.s1 = (cs > 1 && (slice_mode == 2 || (slice_mode == 0 && w_a > small))) ? cs : 1;
+    pl->fc.s2 = (cs > 1 && (slice_mode == 2 || (slice_mode == 0 && w_b > small))) ? cs : 1;
+    const int n1 = (out_a + pl->fc.s1 - 1) / pl->fc.s1, n2 = (out_b + pl->fc.s2 - 1) / pl->fc.s2;
+    size_t staged_floats = bwd ? (size_t)(R + 1) * c * (n1 | 1) + 4 * (size_t)n1 + (size_t)c2 * (n2 | 1)
+                               : (size_t)n1 * (c + 5) + (size_t)n2 * (c2 + 1);
+    staged_floats = (staged_floats + 3) & ~(size_t)3;
+    pl->fc.staged = (env_int("TBI_SA_STAGE", 1) != 0 && staged_floats * sizeof(float) <= 64 * 1024) ? 1 : 0;
+    const size_t fc_floats = bwd ? (size_t)(cs + 2) * C + 2 * KC + 2 * KC2 : (size_t)(cs + 1) * C + KC + KC2;
+    const size_t base = sizeof(float) * (fc_floats + (size_t)nt * V + (pl->fc.staged ? staged_floats : 0));
+    const size_t cache_bytes = (size_t)nit * (bwd ? R + 1 : R) * nt * 16;
+    const size_t cache_cap = (size_t)env_int("TBI_SA_CACHE_KB", 100) * 1024;
+    pl->cs = cs; pl->nt = nt; pl->fc.trace = g_sa_trace_host;
+    pl->cache = (cache_cap > 0 && base + cache_bytes <= cache_cap) ? 1 : 0;
+    pl->smem = base + (pl->cache ? cache_bytes : 0);
+    return pl->smem <= 200 * 1024;
 }
+
+template <typename... Args>
+int launch_cluster(void (*kernel)(Args...), const ClusterPlan& pl, int n_images, cudaStream_t s, const char* what, Args... args) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess && pl.cs > 8) e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "%s attributes: %s", what, cudaGetErrorString(e));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_images * pl.cs)); cfg.blockDim = dim3((unsigned)pl.nt);
+    cfg.dynamicSmemBytes = pl.smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)pl.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "%s launch (cluster %d, %d threads, %zu B smem): %s", what, pl.cs, pl.nt, pl.smem, cudaGetErrorString(e));
+    return 1;
+}
+
+bool aligned16(const tbi_view* v) { return v->cstride % V == 0 && v->coff % V == 0 && ((uintptr_t)v->ptr & 15) == 0; }
 
 }  // namespace
+
+extern "C" int tbi_debug_set_splitatt_trace(void* dev_buf) { g_sa_trace_host = (unsigned long long*)dev_buf; return 0; }
 
 // returns 1 if launched, 0 if the fused path does not apply (caller falls back to the multi-kernel path), <0 on error
 int tbi_splitatt_fwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, cudaStream_t s) {
     if (p->dtype != TBI_BF16) return 0;
-    static const bool disabled = getenv("TBI_NO_FUSED_SPLITATT") != nullptr;
-    if (disabled) return 0;
-    const int V = 8;
-    if (p->c % V != 0 || u->cstride % V || u->coff % V || v->cstride % V || v->coff % V || ((uintptr_t)u->ptr & 15) || ((uintptr_t)v->ptr & 15)) return 0;
-    const int K = p->kpaths, R = p->radix, c = p->c;
-    FusedPlan fp;
-    auto kernel = splitatt_fwd_fused_kernel<__nv_bfloat16, 8>;
-    if (!plan_fused(p, kernel, (size_t)K * c + K * (c / 2) + (size_t)K * R * c + 32, V, &fp)) return 0;
-    cudaError_t e = cudaMemsetAsync(p->att, 0, sizeof(float) * (size_t)p->n * u->c, s);
-    if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "splitatt fused memset: %s", cudaGetErrorString(e));
-    tbi_splitatt pp = *p; tbi_view uu = *u, vv = *v; float* raw = p->att; int bpi = fp.bpi, ppb = fp.ppb, stw = fp.stage_w, wofs = fp.wofs;
-    void* args[] = {&pp, &uu, &vv, &raw, &bpi, &ppb, &stw, &wofs};
-    e = cudaLaunchCooperativeKernel((void*)kernel, dim3(fp.grid), dim3(256), args, fp.smem, s);
-    if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "splitatt fused fwd launch: %s", cudaGetErrorString(e));
-    return 1;
+    if (getenv("TBI_NO_FUSED_SPLITATT") != nullptr) return 0;
+    if (p->c % V != 0 || !aligned16(u) || !aligned16(v)) return 0;
+    const int R = p->radix;
+    ClusterPlan pl;
+    if (!make_plan(p, 0, &pl)) return 0;
+#define TBI_SA_FWD(RR, NN) launch_cluster(splitatt_fwd_cluster_kernel<RR, NN>, pl, p->n, s, "splitatt fused fwd", *p, *u, *v, pl.cache, pl.fc)
+    if (pl.nt == 512) {
+        switch (R) { case 1: return TBI_SA_FWD(1, 512); case 2: return TBI_SA_FWD(2, 512); case 3: return TBI_SA_FWD(3, 512); case 4: return TBI_SA_FWD(4, 512); }
+    } else {
+        switch (R) { case 1: return TBI_SA_FWD(1, 256); case 2: return TBI_SA_FWD(2, 256); case 3: return TBI_SA_FWD(3, 256); case 4: return TBI_SA_FWD(4, 256); }
+    }
+#undef TBI_SA_FWD
+    return 0;
 }
 
 int tbi_splitatt_bwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* dv, const tbi_view* du, float* scratch, cudaStream_t s) {
     if (p->dtype != TBI_BF16) return 0;
-    static const bool disabled = getenv("TBI_NO_FUSED_SPLITATT") != nullptr;
-    if (disabled) return 0;
-    const int V = 8;
-    if (p->c % V != 0 || u->cstride % V || u->coff % V || dv->cstride % V || dv->coff % V || du->cstride % V || du->coff % V ||
-        ((uintptr_t)u->ptr & 15) || ((uintptr_t)dv->ptr & 15) || ((uintptr_t)du->ptr & 15)) return 0;
-    const int K = p->kpaths, R = p->radix, c = p->c;
-    FusedPlan fp;
-    auto kernel = splitatt_bwd_fused_kernel<__nv_bfloat16, 8>;
-    if (!plan_fused(p, kernel, (size_t)2 * K * R * c + K * (c / 2) + (size_t)K * c + 32, V, &fp)) return 0;
-    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * (size_t)p->n * u->c, s);
-    if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "splitatt fused memset: %s", cudaGetErrorString(e));
-    tbi_splitatt pp = *p; tbi_view uu = *u, dd = *dv, du2 = *du; int bpi = fp.bpi, ppb = fp.ppb, stw = fp.stage_w, wofs = fp.wofs;
-    void* args[] = {&pp, &uu, &dd, &du2, &scratch, &bpi, &ppb, &stw, &wofs};
-    e = cudaLaunchCooperativeKernel((void*)kernel, dim3(fp.grid), dim3(256), args, fp.smem, s);
-    if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "splitatt fused bwd launch: %s", cudaGetErrorString(e));
-    return 1;
+    if (getenv("TBI_NO_FUSED_SPLITATT") != nullptr) return 0;
+    if (p->c % V != 0 || !aligned16(u) || !aligned16(dv) || !aligned16(du)) return 0;
+    const int R = p->radix;
+    ClusterPlan pl;
+    if (!make_plan(p, 1, &pl)) return 0;
+#define TBI_SA_BWD(RR, NN) launch_cluster(splitatt_bwd_cluster_kernel<RR, NN>, pl, p->n, s, "splitatt fused bwd", *p, *u, *dv, *du, scratch, pl.cache, pl.fc)
+    if (pl.nt == 512) {
+        switch (R) { case 1: return TBI_SA_BWD(1, 512); case 2: return TBI_SA_BWD(2, 512); case 3: return TBI_SA_BWD(3, 512); case 4: return TBI_SA_BWD(4, 512); }
+    } else {
+        switch (R) { case 1: return TBI_SA_BWD(1, 256); case 2: return TBI_SA_BWD(2, 256); case 3: return TBI_SA_BWD(3, 256); case 4: return TBI_SA_BWD(4, 256); }
+    }
+#undef TBI_SA_BWD
+    return 0;
 }

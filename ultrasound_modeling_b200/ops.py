@@ -249,24 +249,30 @@ class SplitAttention:
         return SplitAtt(_dt(u), n, h, w, self.K, self.R, self.c, self.act, BN_EPS, *[_p(t) for t in self.params],
                         _p(self.gap), _p(self.h1), _p(self.att))
 
-    def forward(self, u):
+    def forward(self, u, out=None):
         L = _lib.lib()
         n, h, w, _ = u.shape
         self.desc = self._desc(u)
-        v = torch.empty(n, h, w, self.K * self.c, dtype=u.dtype, device=u.device)
+        v = torch.empty(n, h, w, self.K * self.c, dtype=u.dtype, device=u.device) if out is None else out
         check(L.tbi_split_attention_fwd(C.byref(self.desc), _vp(view(u)), _vp(view(v)), _st()), "split_attention_fwd")
         return v
 
-    def backward(self, u, dv):
-        """-> (dz_u = dL/du * act'(u), dict of parameter gradients)"""
+    def new_grads(self, dev):
+        K, R, c = self.K, self.R, self.c
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        return dict(w1=z(K, c, c // 2), b1=z(K, c // 2), gamma=z(K, c // 2), beta=z(K, c // 2), w2=z(K, R, c // 2, c), b2=z(K, R, c))
+
+    def backward(self, u, dv, out=None, grads=None, scratch=None):
+        """-> (dz_u = dL/du * act'(u), dict of parameter gradients).  out / grads / scratch: caller-kept buffers (the parameter
+        gradients are ADDED into grads, as the engine adds them into its flat gradient buffer)."""
         L = _lib.lib()
         n = u.shape[0]
         K, R, c = self.K, self.R, self.c
         dev = u.device
-        du = torch.empty_like(u)
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        g = dict(w1=z(K, c, c // 2), b1=z(K, c // 2), gamma=z(K, c // 2), beta=z(K, c // 2), w2=z(K, R, c // 2, c), b2=z(K, R, c))
-        scratch = torch.empty(n * K * (R * c + 2 * c), dtype=torch.float32, device=dev)
+        du = torch.empty_like(u) if out is None else out
+        g = self.new_grads(dev) if grads is None else grads
+        if scratch is None:
+            scratch = torch.empty(n * K * (R * c + 2 * c), dtype=torch.float32, device=dev)
         check(L.tbi_split_attention_bwd(C.byref(self.desc), _vp(view(u)), _vp(view(dv)), _vp(view(du)), _p(g["w1"]), _p(g["b1"]),
                                         _p(g["gamma"]), _p(g["beta"]), _p(g["w2"]), _p(g["b2"]), _p(scratch), _st()), "split_attention_bwd")
         return du, g
