@@ -289,6 +289,15 @@ int tbi_splitatt_shared_fwd(int dtype, int n, int h, int w, int kpaths, int radi
                             const float* ln_beta, float ln_eps, int act, const float* w2, const float* b2,
                             float* att, void* stream);
 
+/* backward of the above.  att = the forward's att buffer (R*a); scratch: fp32 [2][n][K*c].  dV -> dU; the parameter
+ * gradients (same shapes as the parameters) are ADDED.  One pass over (U, dV) for sum_p U and sum_p dV*U, the FC chain
+ * and its backward per (image, cardinal), one pass dU = dV*att + dgap*R/HW.                            */
+int tbi_splitatt_shared_bwd(int dtype, int n, int h, int w, int kpaths, int radix, int c, const tbi_view* u,
+                            const tbi_view* dv, const tbi_view* du, const float* w1, const float* b1,
+                            const float* ln_gamma, const float* ln_beta, float ln_eps, int act, const float* w2,
+                            const float* att, float* dw1, float* db1, float* dln_gamma, float* dln_beta,
+                            float* dw2, float* db2, float* scratch, void* stream);
+
 /* x fp32/fp64 host-layout NHWC -> storage dtype (device to device)                               */
 int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void* src, void* dst, void* stream);
 

@@ -73,6 +73,37 @@ def test_splitatt_shared(cuda_device, dtype, K, R, c):
     assert rel(v, want) < TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("K,R,c", [(3, 3, 10), (3, 3, 85), (1, 1, 32), (2, 4, 21)])
+def test_splitatt_shared_bwd(cuda_device, dtype, K, R, c):
+    """tbi_splitatt_shared_bwd against autograd of the restated formula (ResNest.py:171-199)"""
+    from ultrasound_modeling_b200 import ops
+    g = torch.Generator().manual_seed(11 * c + R)
+    n, h, w, c2 = 3, 12, 5, c // 2
+    D = lambda *s_, sc=1.0: (torch.randn(*s_, generator=g, dtype=torch.float64) * sc)
+    u = q(D(n, h, w, K * c), dtype).requires_grad_(True)
+    P = dict(w1=D(K, c, c2, sc=0.3), b1=D(K, c2, sc=0.1), lg=1 + D(K, c2, sc=0.1), lb=D(K, c2, sc=0.1), w2=D(K, c2, c, sc=0.3), b2=D(K, c, sc=0.1))
+    P = {k_: t.requires_grad_(True) for k_, t in P.items()}
+    outs = []
+    for k in range(K):
+        uk = u[..., k * c:(k + 1) * c]
+        gap = (R * uk).mean(dim=(1, 2))
+        hh = B.leaky(B.layernorm_c(gap @ P["w1"][k] + P["b1"][k], P["lg"][k], P["lb"][k]))
+        z = hh @ P["w2"][k] + P["b2"][k]
+        a = torch.sigmoid(z) if R == 1 else torch.softmax(z, dim=-1)
+        outs.append(R * uk * a[:, None, None, :])
+    want = torch.cat(outs, dim=3)
+    dv = q(D(n, h, w, K * c), dtype)
+    (want * dv).sum().backward()
+    dev = lambda t: t.detach().float().to(cuda_device)
+    ud = u.detach().to(cuda_device, dtype)
+    v, att = ops.splitatt_shared(ud, K, R, dev(P["w1"]), dev(P["b1"]), dev(P["lg"]), dev(P["lb"]), dev(P["w2"]), dev(P["b2"]), act=2, return_att=True)
+    du, pg = ops.splitatt_shared_bwd(ud, dv.to(cuda_device, dtype), att, K, R, dev(P["w1"]), dev(P["b1"]), dev(P["lg"]), dev(P["lb"]), dev(P["w2"]), act=2)
+    assert rel(du, u.grad) < TOL[dtype]
+    for name, key in (("w1", "w1"), ("b1", "b1"), ("ln_gamma", "lg"), ("ln_beta", "lb"), ("w2", "w2"), ("b2", "b2")):
+        assert rel(pg[name], P[key].grad) < 5e-4, name          # fp32 FC math either way (inputs already quantised)
+
+
 def _pair(dtype, H, W, n, cuda_device):
     from ultrasound_modeling_b200.ResNest import ResNest
     from ultrasound_modeling_b200.Decoder import DecoderCup
@@ -143,3 +174,90 @@ def test_lazy_build_and_golden(cuda_device):
     gz = np.load(GOLDEN)
     p = dec(tok, enc(x)[1])
     assert np.abs(p.cpu().numpy() - gz["probs"]).max() < 1e-4 * np.abs(gz["probs"]).max()
+
+
+class _StoreBf16(torch.autograd.Function):
+    """a tensor stored in bf16 whose gradient is stored in bf16 too (fp64 math on either side)"""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(g.dtype)
+
+
+def _oracle_grads(pe, pd, x, tok, grid, store_bf16=False):
+    """autograd of the oracle for fixed cotangents on the logits and on x_4 -> (name -> gradient, gz, g4).  store_bf16 rounds
+    every stored activation (and its gradient) to bf16 where the product stores a tensor -- still fp64 arithmetic."""
+    trainable = lambda k: not k.endswith(("moving_mean", "moving_variance"))
+    names = ("conv2d_same", "leaky", "avgpool2", "conv2d_transpose_s2_same")
+    orig = {k: getattr(B, k) for k in names}
+    try:
+        if store_bf16:
+            for k, f in orig.items():
+                setattr(B, k, (lambda f: lambda *a, **kw: _StoreBf16.apply(f(*a, **kw)))(f))
+        oe = B.ResNestEncoderOracle(10, 3, 3, 3, pe); od = B.DecoderCupOracle(3, pd, grid=grid)
+        oe.p = {k: v.clone().requires_grad_(trainable(k)) for k, v in oe.p.items()}
+        od.p = {k: v.clone().requires_grad_(trainable(k)) for k, v in od.p.items()}
+        xr = x.clone().requires_grad_(True); tokr = tok.clone().requires_grad_(True)
+        x4w, fw = oe(xr)
+        zw = od(tokr, fw, logits=True)
+        gen = torch.Generator().manual_seed(97)
+        gz = torch.randn(zw.shape, generator=gen, dtype=torch.float64) / zw.numel() ** 0.5
+        g4 = torch.randn(x4w.shape, generator=gen, dtype=torch.float64) / x4w.numel() ** 0.5
+        ((zw * gz).sum() + (x4w * g4).sum()).backward()
+    finally:
+        for k, f in orig.items():
+            setattr(B, k, f)
+    g = {"dx": xr.grad, "dhidden": tokr.grad}
+    g.update({"enc/" + k: v.grad for k, v in oe.p.items() if trainable(k)})
+    g.update({"dec/" + k: v.grad for k, v in od.p.items() if trainable(k)})
+    return g, gz, g4
+
+
+def _cosine(got, ref):
+    keys = [k for k in ref if k not in ("dx", "dhidden")]
+    a = torch.cat([got[k].detach().double().cpu().flatten() / ref[k].abs().max() for k in keys])
+    b = torch.cat([ref[k].flatten() / ref[k].abs().max() for k in keys])
+    return float((a * b).sum() / a.norm() / b.norm())
+
+
+@pytest.mark.parametrize("dtype,H,W,n", [(torch.float32, 64, 32, 2), (torch.bfloat16, 64, 32, 2), (torch.float32, 128, 48, 1)])
+def test_encoder_decoder_backward(cuda_device, dtype, H, W, n):
+    """backward of both Variant B classes against autograd of the oracle: cotangents on the logits and on x_4 flow through the
+    decoder (-> hidden states, skips) and the encoder (-> input frames); every parameter gradient is compared.
+
+    fp32: every gradient within 2 x 1e-4 of its tensor's largest entry (the two classes chained, as in the forward test).
+    bf16: the 2e-2 bar cannot apply to THIS network's gradients -- storing the activations in bf16, with fp64 arithmetic, already
+    moves the oracle's own gradients by a median 5 % and up to ~80 % of a tensor's largest entry (LayerNorm over 3..10 channels,
+    LeakyReLU kinks; scratch/dbg_vb_bf16_sens.py), although the forward outputs stay within 6e-3.  The bf16 run is therefore held
+    to that reference: median and largest error no more than twice what bf16 storage alone does to the oracle, and the
+    direction of the whole gradient (cosine over all parameters) within 0.02 of it.  The bf16 kernels themselves are held to
+    2e-2 one by one (conv / convT / LayerNorm / split-attention gradient tests)."""
+    enc, dec, pe, pd, x, tok, grid = _pair(dtype, H, W, n, cuda_device)
+    ref, gz, g4 = _oracle_grads(pe, pd, x, tok, grid)
+    x4, feats = enc.forward(x.float(), record=True)
+    z = dec.forward(tok.float(), feats, logits=True, record=True)
+    dhid, dfeats = dec.backward(gz.float())
+    assert all(d is not None for d in dfeats)
+    dx = enc.backward(g4.float(), dfeats)
+    got = {"dx": dx, "dhidden": dhid}
+    got.update({"enc/" + k: g for k, g in enc.gradients().items()}); got.update({"dec/" + k: g for k, g in dec.gradients().items()})
+    assert set(got) == set(ref)
+    errs = {k: rel(got[k], ref[k]) for k in ref}
+    worst = sorted(errs.items(), key=lambda kv: -kv[1])[:6]
+    med = float(np.median(list(errs.values())))
+    print("largest relative gradient errors:", worst, "| median", med, "| cosine", _cosine(got, ref))
+    if dtype == torch.float32:
+        assert worst[0][1] < 2 * TOL[dtype], worst
+    else:
+        qref, _, _ = _oracle_grads(pe, pd, x, tok, grid, store_bf16=True)
+        qerrs = {k: rel(qref[k], ref[k]) for k in ref}
+        qmed, qmax, qcos = float(np.median(list(qerrs.values()))), max(qerrs.values()), _cosine(qref, ref)
+        print("bf16 storage alone (oracle, fp64 math): median", qmed, "| max", qmax, "| cosine", qcos)
+        assert med <= 2 * qmed + TOL[dtype] and worst[0][1] <= 2 * qmax + TOL[dtype] and _cosine(got, ref) >= qcos - 0.02
+    # the tape is consumed: a second backward needs a new recorded forward
+    with pytest.raises(RuntimeError):
+        enc.backward(g4.float(), dfeats)

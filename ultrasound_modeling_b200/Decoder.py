@@ -23,6 +23,29 @@ from .ResNest import VariableStore, _Layer
 _DIL = (1, 2, 4, 8)          # conv*_0: 1x1; conv*_1..3: 3x3 dilated 2, 4, 8 (Decoder.py:11-25,35-49)
 
 
+def _convt(layer, x, x2, name, cout, out_f32=False):
+    """Conv2DTranspose k3 s2 'same' over the virtual concat (x, x2), no norm / activation (Decoder.py:57-59,120); recorded for
+    backward when the store is recording"""
+    s = layer._s
+    cin = x.shape[3] + (x2.shape[3] if x2 is not None else 0)
+    w = s.kernel(name + "/kernel", (3, 3, cout, cin))
+    b = s.vector(name + "/bias", cout, 0.0)
+    y = ops.conv2d_transpose_s2(x, w, b, x2=x2, out_f32=out_f32)
+    if s.recording:
+        def bwd():
+            dz = s.gget(y)
+            if dz is None:
+                return
+            dxs, dw, db = ops.conv2d_transpose_s2_grads(x, w, dz.to(x.dtype), x2=x2)
+            s.pacc(name + "/kernel", dw); s.pacc(name + "/bias", db)
+            if x2 is None:
+                s.gacc(x, dxs)
+            else:
+                s.gacc(x, dxs[0]); s.gacc(x2, dxs[1])
+        s.tape.append(bwd)
+    return y
+
+
 class DecoderBlock(_Layer):
     """Decoder.py:7-94: up (Conv2DTranspose k3 s2) -> [concat skip] -> 4 branches + BN -> concat -> LeakyReLU -> again."""
 
@@ -31,10 +54,7 @@ class DecoderBlock(_Layer):
         self.out_channels, self.wDecay = out_channels, wDecay
 
     def _up(self, x, x2):
-        cin = x.shape[3] + (x2.shape[3] if x2 is not None else 0)
-        w = self._s.kernel(self._p + "up/kernel", (3, 3, self.out_channels, cin))
-        b = self._s.vector(self._p + "up/bias", self.out_channels, 0.0)
-        return ops.conv2d_transpose_s2(x, w, b, x2=x2)
+        return _convt(self, x, x2, self._p + "up", self.out_channels)
 
     def _branches(self, half, x, x2):
         n, h, w, _ = x.shape
@@ -74,26 +94,62 @@ class DecoderCup(_Layer):
     def _dev(self, t):
         return torch.as_tensor(np.asarray(t) if not torch.is_tensor(t) else t).to(device=self.device, dtype=self.tdtype).contiguous()
 
-    def forward(self, hidden_states, features=None, logits=False):
+    def forward(self, hidden_states, features=None, logits=False, record=False):
+        """record=True keeps what backward() needs (the tape of this call)"""
         y = self._dev(hidden_states)
         n = y.shape[0]
         gh, gw = self.grid
-        x = y.reshape(n, gh, gw, -1)
+        s = self._s
+        if record:
+            s.start_recording()
+        views = []                                                                  # raw reshapes of the token tensor
+
+        def token_view(*shape):
+            v = y.reshape(*shape)
+            views.append(v)
+            return v
+
+        if record:
+            def gather():                                                           # first on the tape = last to run
+                g = None
+                for v in views:
+                    gv = s.gget(v)
+                    if gv is not None:
+                        g = gv.reshape(y.shape) if g is None else g + gv.reshape(y.shape)
+                self._dhidden = g
+            s.tape.append(gather)
+        x = token_view(n, gh, gw, -1)
         x = self._conv(x, "conv_more", 3, 256)
         x = self._ln(x, "bn1")
         extra = None
+        skips = []
         for i, blk in enumerate(self.blocks):
             skip = self._dev(features[i]) if (features is not None and i < 3) else None
+            skips.append(skip)
             x = blk.forward(x, skip, extra)
-            extra = y.reshape(n, gh * 2 ** (i + 1), gw * 2 ** (i + 1), -1)      # Decoder.py:140-141, consumed by the next layer
-        cin = x.shape[3] + extra.shape[3]
-        w = self._s.kernel("head/kernel", (3, 3, self.num_classes, cin))
-        b = self._s.vector("head/bias", self.num_classes, 0.0)
-        z = ops.conv2d_transpose_s2(x, w, b, x2=extra, out_f32=True)
+            extra = token_view(n, gh * 2 ** (i + 1), gw * 2 ** (i + 1), -1)         # Decoder.py:140-141, consumed by the next layer
+        z = _convt(self, x, extra, "head", self.num_classes, out_f32=True)
+        self._io = (z, skips)
         if logits:
             return z
         probs, _, _, _ = ops.softmax_loss(z, torch.zeros_like(z))
         return probs
+
+    def backward(self, dlogits):
+        """dL/dlogits of the last forward(..., record=True) -> (dL/dhidden_states, [dL/dfeatures]); parameter gradients in
+        gradients().  (The reference's loss is applied to the probabilities by the caller, VisionTransformer.py:205-206,225-254.)"""
+        if not self._s.recording:
+            raise RuntimeError("DecoderCup.backward: call forward(..., record=True) first")
+        z, skips = self._io
+        self._s.gacc(z, torch.as_tensor(dlogits).to(device=self.device, dtype=z.dtype).contiguous())
+        grads_of = [None if t is None else id(t) for t in skips]
+        tg = self._s.tgrads
+        self._s.run_backward()
+        return self._dhidden, [None if k is None else tg.get(k) for k in grads_of]
+
+    def gradients(self):
+        """variable name -> fp32 gradient of the last backward() (trainable variables only: no moving statistics)"""
+        return OrderedDict(self._s.grads)
 
     def __call__(self, hidden_states, features=None, *args, **kwargs):
         return self.forward(hidden_states, features, *args, **kwargs)

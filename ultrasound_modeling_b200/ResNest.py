@@ -1,11 +1,13 @@
 """Variant B encoder: drop-in for the reference's ``ResNest.py`` (classes ResNest, residual_S, cardinal, split_attention)
-on the B200 path.  Forward / inference only this round (the training step of Variant B runs through the ViT bridge of
-``VisionTransformer.py``, scope row 8(f)-1).
+on the B200 path: forward, and backward (``forward(x, record=True)`` then ``backward(dx_4, [dx_3, dx_2, dx_1])`` -> dL/dx, with
+the parameter gradients in ``gradients()``).  The loss of Variant B's training step sits behind the ViT bridge of
+``VisionTransformer.py`` (scope row 8(f)-1, not built): backward therefore takes the gradients of the encoder's four outputs.
 
 Same constructor signatures and call results as the reference:
     ResNest(height, width, channel, ksize, radix=4, kpaths=4, wDecay=None)(x) -> (x_4, [x_3, x_2, x_1])   ResNest.py:7,38-58
 Inputs are NHWC (numpy or torch); outputs are NHWC device tensors in the storage dtype (bf16 default, fp32 for parity runs).
-Every arithmetic step is a libtbi_sm100.so entry point (ops.py); torch only allocates, reshapes and owns the parameters.
+Every arithmetic step is a libtbi_sm100.so entry point (ops.py); torch only allocates, reshapes, owns the parameters and, in
+the backward pass, slices / accumulates gradient buffers (the tape below).
 ``wDecay`` (a Keras kernel regulariser) only adds a term to the training loss and is ignored here.
 
 Keras builds layers lazily on the first call (input channel counts are not constructor arguments); so does this file: a
@@ -33,6 +35,44 @@ class VariableStore:
         self.device = torch.device(device)
         self.vars: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         self.gen = torch.Generator().manual_seed(seed)
+        # backward tape (forward(..., record=True)): closures run in reverse; gradients of activation BUFFERS are kept per buffer
+        # (a conv that writes a channel slice of a concat buffer reads the same slice of that buffer's gradient)
+        self.recording = False
+        self.tape = []
+        self.tgrads: Dict[int, torch.Tensor] = {}
+        self._alive = []
+        self.grads: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+
+    def start_recording(self):
+        self.recording = True
+        self.tape.clear(); self.tgrads.clear(); self._alive.clear(); self.grads.clear()
+
+    def gacc(self, t: torch.Tensor, g: torch.Tensor, coff: int = 0):
+        """add g into channels [coff, coff + g.channels) of the gradient buffer of activation buffer t"""
+        G = self.tgrads.get(id(t))
+        if G is None:
+            G = self.tgrads[id(t)] = torch.zeros_like(t)
+            self._alive.append(t)                              # ids stay unique while the tape lives
+        G[..., coff:coff + g.shape[-1]] += g.to(G.dtype)
+
+    def gset(self, t: torch.Tensor, g: torch.Tensor, coff: int = 0):
+        self.tgrads[id(t)][..., coff:coff + g.shape[-1]] = g.to(self.tgrads[id(t)].dtype)
+
+    def gget(self, t: torch.Tensor, coff: int = 0, c: Optional[int] = None) -> Optional[torch.Tensor]:
+        G = self.tgrads.get(id(t))
+        if G is None:
+            return None
+        c = G.shape[-1] - coff if c is None else c
+        return G if (coff == 0 and c == G.shape[-1]) else G[..., coff:coff + c].contiguous()
+
+    def pacc(self, name: str, g: torch.Tensor):
+        self.grads[name] = self.grads[name] + g if name in self.grads else g.clone()
+
+    def run_backward(self):
+        for fn in reversed(self.tape):
+            fn()
+        self.tape.clear(); self._alive.clear()
+        self.recording = False
 
     def kernel(self, name: str, shape) -> torch.Tensor:
         t = self.vars.get(name)
@@ -64,7 +104,8 @@ class _Layer:
         self._s, self._p = store, prefix
 
     # -- Keras layer equivalents on NHWC device tensors --------------------------------------
-    def _conv(self, x, name, k, cout, *, dilation=1, bn=None, act=ACT_NONE, residual=None, x2=None, out=None, out_coff=0, out_f32=False):
+    def _conv(self, x, name, k, cout, *, dilation=1, bn=None, act=ACT_NONE, residual=None, x2=None, out=None, out_coff=0, out_f32=False,
+              need_dx=True):
         cin = x.shape[3] + (x2.shape[3] if x2 is not None else 0)
         w = self._s.kernel(f"{self._p}{name}/kernel", (k, k, cin, cout))
         b = self._s.vector(f"{self._p}{name}/bias", cout, 0.0)
@@ -73,13 +114,63 @@ class _Layer:
             q = f"{self._p}{bn}/"
             bnp = (self._s.vector(q + "gamma", cout, 1.0), self._s.vector(q + "beta", cout, 0.0),
                    self._s.vector(q + "moving_mean", cout, 0.0), self._s.vector(q + "moving_variance", cout, 1.0))
-        return ops.conv2d(x, w, b, dilation=dilation, bn=bnp, act=act, residual=residual, x2=x2, out=out, out_coff=out_coff, out_f32=out_f32)
+        y = ops.conv2d(x, w, b, dilation=dilation, bn=bnp, act=act, residual=residual, x2=x2, out=out, out_coff=out_coff, out_f32=out_f32)
+        if self._s.recording:
+            s, pre = self._s, f"{self._p}{name}/"
+
+            def bwd():
+                buf, off = (out, out_coff) if out is not None else (y, 0)
+                dy = s.gget(buf, off, cout)
+                if dy is None:
+                    return
+                if residual is not None:
+                    s.gacc(residual, dy)
+                dz = ops.act_bwd(dy, buf if buf.shape[3] == cout else buf[..., off:off + cout].contiguous(), act) if act != ACT_NONE else dy
+                scale = ops.fold_bn(cout, b, bnp, x.device)[0] if bnp is not None else None
+                dxs, dw, db = ops.conv2d_grads(x, w, dz, dilation=dilation, scale=scale, x2=x2, need_dx=need_dx)
+                if bnp is not None:
+                    dgam, dbet = ops.bn_param_grad(w, dw, b, db, bnp)              # dw, db: raw -> true gradients, in place
+                    s.pacc(f"{self._p}{bn}/gamma", dgam); s.pacc(f"{self._p}{bn}/beta", dbet)
+                s.pacc(pre + "kernel", dw); s.pacc(pre + "bias", db)
+                if need_dx:
+                    if x2 is None:
+                        s.gacc(x, dxs)
+                    else:
+                        s.gacc(x, dxs[0]); s.gacc(x2, dxs[1])
+            s.tape.append(bwd)
+        return y
 
     def _ln(self, x, name, act=ACT_LRELU, coff=0, c=None):
+        """LayerNormalization + activation IN PLACE on channels [coff, coff+c) of x"""
         cc = x.shape[3] if c is None else c
         g = self._s.vector(f"{self._p}{name}/gamma", cc, 1.0)
         b = self._s.vector(f"{self._p}{name}/beta", cc, 0.0)
-        return ops.layernorm_c(x, g, b, act=act, inplace=True, coff=coff, c=c)
+        x_in = x[..., coff:coff + cc].clone(memory_format=torch.contiguous_format) if self._s.recording else None    # the LN input
+        y = ops.layernorm_c(x, g, b, act=act, inplace=True, coff=coff, c=c)
+        if self._s.recording:
+            s = self._s
+
+            def bwd():
+                dy = s.gget(x, coff, cc)
+                if dy is None:
+                    return
+                dx, dg, db = ops.layernorm_c_bwd(x_in, x[..., coff:coff + cc].contiguous(), dy, g, act=act)
+                s.pacc(f"{self._p}{name}/gamma", dg); s.pacc(f"{self._p}{name}/beta", db)
+                s.gset(x, dx, coff)        # in-place layer: the slice's gradient becomes the gradient w.r.t. the LN input
+            s.tape.append(bwd)
+        return y
+
+    def _pool(self, x):
+        y = ops.avgpool2x2(x)
+        if self._s.recording:
+            s = self._s
+
+            def bwd():
+                dy = s.gget(y)
+                if dy is not None:
+                    s.gacc(x, ops.avgpool2x2_bwd(dy))
+            s.tape.append(bwd)
+        return y
 
 
 class split_attention(_Layer):
@@ -132,7 +223,23 @@ class residual_S(_Layer):
             blk.features(x, u, k * c)
         per = [blk.split.params() for blk in self.cardinal_blocks]
         stacked = [torch.stack([p[i] for p in per]).contiguous() for i in range(6)]
-        v = ops.splitatt_shared(u, K, self.radix, *stacked, act=ACT_LRELU)
+        v, att = ops.splitatt_shared(u, K, self.radix, *stacked, act=ACT_LRELU, return_att=True)
+        if self._s.recording:
+            s = self._s
+
+            def bwd():
+                dv = s.gget(v)
+                if dv is None:
+                    return
+                du, g = ops.splitatt_shared_bwd(u, dv, att, K, self.radix, *stacked[:5], act=ACT_LRELU)
+                s.gacc(u, du)
+                c2 = c // 2
+                for k_, blk in enumerate(self.cardinal_blocks):
+                    q = blk.split._p
+                    s.pacc(q + "dense1/kernel", g["w1"][k_].reshape(1, 1, c, c2)); s.pacc(q + "dense1/bias", g["b1"][k_])
+                    s.pacc(q + "dense1_bn/gamma", g["ln_gamma"][k_]); s.pacc(q + "dense1_bn/beta", g["ln_beta"][k_])
+                    s.pacc(q + "dense2/kernel", g["w2"][k_].reshape(1, 1, c2, c)); s.pacc(q + "dense2/bias", g["b2"][k_])
+            s.tape.append(bwd)
         sc = self._conv(x, "convtmp_sc", 1, self.outchannel, dilation=self.atrous)
         sc = self._ln(sc, "convtmp_scbn")
         return self._conv(v, "concats_2", self.ksize, self.outchannel, dilation=self.atrous, residual=sc)
@@ -158,16 +265,38 @@ class ResNest(_Layer):
     def variables(self):
         return OrderedDict(self._s.vars)
 
-    def forward(self, x):
+    def forward(self, x, record=False):
+        """record=True keeps what backward() needs (the tape of this call)"""
         x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=self.device, dtype=self.tdtype).contiguous()
+        if record:
+            self._s.start_recording()
+        x0 = x
         x = self._conv(x, "initial_conv", 3, 16, act=ACT_LRELU)
         x = self._conv(x, "convtmp_1", 3, 32, bn="convtmp_1bn", act=ACT_LRELU)
         x = self._conv(x, "convtmp_2", 3, 32, bn="convtmp_2bn", act=ACT_LRELU)
-        x_1 = self.conv_1(ops.avgpool2x2(x))
-        x_2 = self.conv_2(ops.avgpool2x2(x_1))
-        x_3 = self.conv_3(ops.avgpool2x2(x_2))
-        x_4 = self.conv_4(ops.avgpool2x2(x_3))
+        x_1 = self.conv_1(self._pool(x))
+        x_2 = self.conv_2(self._pool(x_1))
+        x_3 = self.conv_3(self._pool(x_2))
+        x_4 = self.conv_4(self._pool(x_3))
+        self._io = (x0, x_4, [x_3, x_2, x_1])
         return x_4, [x_3, x_2, x_1]
+
+    def backward(self, dx_4, dfeatures=None):
+        """gradients of the four outputs of the last forward(x, record=True) -> dL/dx; parameter gradients in gradients()"""
+        if not self._s.recording:
+            raise RuntimeError("ResNest.backward: call forward(x, record=True) first")
+        x0, x_4, feats = self._io
+        dev = lambda t: torch.as_tensor(np.asarray(t) if not torch.is_tensor(t) else t).to(device=self.device, dtype=self.tdtype).contiguous()
+        self._s.gacc(x_4, dev(dx_4))
+        for f, d in zip(feats, dfeatures or []):
+            if d is not None:
+                self._s.gacc(f, dev(d))
+        self._s.run_backward()
+        return self._s.gget(x0)
+
+    def gradients(self):
+        """variable name -> fp32 gradient of the last backward() (trainable variables only: no moving statistics)"""
+        return OrderedDict(self._s.grads)
 
     def __call__(self, x, *args, **kwargs):
         return self.forward(x)

@@ -18,7 +18,10 @@
 //           dgap slice push, barrier; slice owners write dz / dbn / xhat / dgap of the image to the scratch buffer for the
 //           parameter-gradient kernel (reduction over n).
 //           pass 2   dU_r = (dV * a_r + dgap / HW) * act'(U_r).
-// Images run out of step with each other (no grid barrier), so one cluster's FC chain hides behind other clusters' passes.
+// Images run out of step with each other (no grid barrier), so one cluster's FC chain hides behind other clusters' passes once
+// there is more than one wave of clusters.  (Tried and dropped: delaying the odd clusters of the first wave so that one half
+// streams while the other half is in its FC chain -- slower at every delay, scratch/trace_splitatt.py shows why: half the CTAs do
+// not saturate HBM.)
 #include "tbi_common.cuh"
 #include <cooperative_groups.h>
 #include <stdlib.h>
@@ -198,11 +201,12 @@ __device__ __forceinline__ void sliced_matvec2(int lo, int hi, int n_in, int NT,
     }
 }
 
+struct FcPlan { int s1, s2, staged; unsigned long long* trace; };
+
 // FC layers: a layer whose weights are small is computed REDUNDANTLY by every CTA of the cluster (S = 1: no exchange, no
 // cluster barrier); a large one is SLICED over the cluster (S = CS: each CTA computes 1/CS of the outputs, pushes them into
 // every peer's shared memory, cluster barrier).  When `staged`, the weights (slices) and per-output parameters were copied
 // to shared memory by cp.async at kernel start, behind pass 1, so the chain between the two passes never waits on L2/HBM.
-struct FcPlan { int s1, s2, staged; unsigned long long* trace; };
 
 // debug timeline (scratch/trace_splitatt.py): thread 0 of every CTA stamps clock64 at the phase boundaries
 unsigned long long* g_sa_trace_host = nullptr;
@@ -638,7 +642,7 @@ bool make_plan(const tbi_splitatt* p, int bwd, ClusterPlan* pl) {
 }
 
 template <typename... Args>
-int launch_cluster(void (*kernel)(Args...), const ClusterPlan& pl, int n_images, cudaStream_t s, const char* what, Args... args) {
+int launch_cluster(void (*kernel)(Args..., FcPlan), ClusterPlan& pl, int n_images, cudaStream_t s, const char* what, Args... args, FcPlan* fc_arg) {
     cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess && pl.cs > 8) e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "%s attributes: %s", what, cudaGetErrorString(e));
@@ -649,7 +653,7 @@ int launch_cluster(void (*kernel)(Args...), const ClusterPlan& pl, int n_images,
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = (unsigned)pl.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kernel, args...);
+    e = cudaLaunchKernelEx(&cfg, kernel, args..., *fc_arg);
     if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "%s launch (cluster %d, %d threads, %zu B smem): %s", what, pl.cs, pl.nt, pl.smem, cudaGetErrorString(e));
     return 1;
 }
@@ -668,7 +672,7 @@ int tbi_splitatt_fwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_v
     const int R = p->radix;
     ClusterPlan pl;
     if (!make_plan(p, 0, &pl)) return 0;
-#define TBI_SA_FWD(RR, NN) launch_cluster(splitatt_fwd_cluster_kernel<RR, NN>, pl, p->n, s, "splitatt fused fwd", *p, *u, *v, pl.cache, pl.fc)
+#define TBI_SA_FWD(RR, NN) launch_cluster<tbi_splitatt, tbi_view, tbi_view, int>(splitatt_fwd_cluster_kernel<RR, NN>, pl, p->n, s, "splitatt fused fwd", *p, *u, *v, pl.cache, &pl.fc)
     if (pl.nt == 512) {
         switch (R) { case 1: return TBI_SA_FWD(1, 512); case 2: return TBI_SA_FWD(2, 512); case 3: return TBI_SA_FWD(3, 512); case 4: return TBI_SA_FWD(4, 512); }
     } else {
@@ -685,7 +689,7 @@ int tbi_splitatt_bwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_v
     const int R = p->radix;
     ClusterPlan pl;
     if (!make_plan(p, 1, &pl)) return 0;
-#define TBI_SA_BWD(RR, NN) launch_cluster(splitatt_bwd_cluster_kernel<RR, NN>, pl, p->n, s, "splitatt fused bwd", *p, *u, *dv, *du, scratch, pl.cache, pl.fc)
+#define TBI_SA_BWD(RR, NN) launch_cluster<tbi_splitatt, tbi_view, tbi_view, tbi_view, float*, int>(splitatt_bwd_cluster_kernel<RR, NN>, pl, p->n, s, "splitatt fused bwd", *p, *u, *dv, *du, scratch, pl.cache, &pl.fc)
     if (pl.nt == 512) {
         switch (R) { case 1: return TBI_SA_BWD(1, 512); case 2: return TBI_SA_BWD(2, 512); case 3: return TBI_SA_BWD(3, 512); case 4: return TBI_SA_BWD(4, 512); }
     } else {

@@ -166,6 +166,120 @@ __global__ void __launch_bounds__(256) shared_scale_kernel(long long total, int 
     }
 }
 
+// ---- backward of the shared-input split attention --------------------------------------------------------------------
+// su[n][ch] += sum_p u ; sdu[n][ch] += sum_p dv*u   (one pass over u and dv)
+template <typename T>
+__global__ void __launch_bounds__(256) shared_bwd_reduce_kernel(int hw, int C, tbi_view u, tbi_view dv, float* su, float* sdu, int pix_per_block) {
+    const int n = blockIdx.y;
+    const int pbeg = blockIdx.x * pix_per_block, pend = min(hw, pbeg + pix_per_block);
+    const T* ub = (const T*)u.ptr + (size_t)n * hw * u.cstride + u.coff;
+    const T* db = (const T*)dv.ptr + (size_t)n * hw * dv.cstride + dv.coff;
+    const int cl = min(C, (int)blockDim.x), pl = blockDim.x / cl;
+    const int lc = threadIdx.x % cl, lp = threadIdx.x / cl;
+    if (lp >= pl) return;
+    for (int ch = lc; ch < C; ch += cl) {
+        float s = 0.f, sd = 0.f;
+        for (int p = pbeg + lp; p < pend; p += pl) {
+            const float x = ldf(ub + (size_t)p * u.cstride + ch);
+            s += x; sd = fmaf(ldf(db + (size_t)p * dv.cstride + ch), x, sd);
+        }
+        atomicAdd(su + (size_t)n * C + ch, s);
+        atomicAdd(sdu + (size_t)n * C + ch, sd);
+    }
+}
+
+// one block per (n, k): recompute the FC chain from su, then its backward.  V = U * att with att = R * a, so
+// dL/da = R * sum_p dV*U.  Parameter gradients are ADDED with atomics (reduction over n and k blocks).
+// On return su[n][k*c + ch] holds dgap * R / hw, the per-image constant of dU.
+__global__ void __launch_bounds__(128) shared_fc_bwd_kernel(int hw, int K, int R, int c, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                            const float* __restrict__ lng, const float* __restrict__ lnb, float eps, int act,
+                                                            const float* __restrict__ w2, const float* __restrict__ att, float* su,
+                                                            const float* __restrict__ sdu, float* dw1, float* db1, float* dlng, float* dlnb,
+                                                            float* dw2, float* db2) {
+    extern __shared__ float sm[];
+    const int c2 = c / 2;
+    float* g = sm; float* xh = g + c; float* h1 = xh + c2; float* dz = h1 + c2; float* dq = dz + c; float* red = dq + c2;
+    const int n = blockIdx.x, k = blockIdx.y;
+    float* sun = su + ((size_t)n * K + k) * c;
+    const float* sdn = sdu + ((size_t)n * K + k) * c;
+    const float* an = att + ((size_t)n * K + k) * c;
+    const float rs = (float)R / (float)hw;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) g[ch] = sun[ch] * rs;
+    __syncthreads();
+    float ls = 0.f, lss = 0.f;
+    for (int j = threadIdx.x; j < c2; j += blockDim.x) {
+        float q = b1[k * c2 + j];
+        const float* w = w1 + (size_t)k * c * c2 + j;
+        for (int ch = 0; ch < c; ++ch) q = fmaf(g[ch], w[(size_t)ch * c2], q);
+        xh[j] = q; ls += q; lss = fmaf(q, q, lss);
+    }
+    const float mean = block_sum(ls, red) / (float)c2;
+    const float var = fmaxf(block_sum(lss, red) / (float)c2 - mean * mean, 0.f);
+    const float istd = rsqrtf(var + eps);
+    __syncthreads();
+    for (int j = threadIdx.x; j < c2; j += blockDim.x) {
+        const float x = (xh[j] - mean) * istd;
+        xh[j] = x;
+        h1[j] = act_apply(act, x * lng[k * c2 + j] + lnb[k * c2 + j]);
+    }
+    // softmax / sigmoid backward
+    float ldot = 0.f;
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) ldot = fmaf(an[ch] / (float)R, (float)R * sdn[ch], ldot);
+    const float dot = block_sum(ldot, red);                  // (also orders the h1 / xh writes above)
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        const float a = an[ch] / (float)R, da = (float)R * sdn[ch];
+        const float z = R == 1 ? a * (1.f - a) * da : a * (da - dot);
+        dz[ch] = z;
+        atomicAdd(db2 + k * c + ch, z);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c2 * c; i += blockDim.x) {
+        const int j = i / c, ch = i - j * c;
+        atomicAdd(dw2 + (size_t)k * c2 * c + i, h1[j] * dz[ch]);
+    }
+    float lh = 0.f, lhx = 0.f;
+    for (int j = threadIdx.x; j < c2; j += blockDim.x) {
+        const float* w = w2 + ((size_t)k * c2 + j) * c;
+        float d = 0.f;
+        for (int ch = 0; ch < c; ++ch) d = fmaf(dz[ch], w[ch], d);
+        const float dy = d * act_grad_from_out(act, h1[j]);
+        atomicAdd(dlng + k * c2 + j, dy * xh[j]);
+        atomicAdd(dlnb + k * c2 + j, dy);
+        const float hh = dy * lng[k * c2 + j];
+        dq[j] = hh; lh += hh; lhx = fmaf(hh, xh[j], lhx);
+    }
+    const float m1 = block_sum(lh, red) / (float)c2;
+    const float m2 = block_sum(lhx, red) / (float)c2;
+    __syncthreads();
+    for (int j = threadIdx.x; j < c2; j += blockDim.x) {
+        const float d = istd * (dq[j] - m1 - xh[j] * m2);
+        dq[j] = d;
+        atomicAdd(db1 + k * c2 + j, d);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c * c2; i += blockDim.x) {
+        const int ch = i / c2, j = i - ch * c2;
+        atomicAdd(dw1 + (size_t)k * c * c2 + i, g[ch] * dq[j]);
+    }
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        const float* w = w1 + ((size_t)k * c + ch) * c2;
+        float d = 0.f;
+        for (int j = 0; j < c2; ++j) d = fmaf(dq[j], w[j], d);
+        sun[ch] = d * rs;
+    }
+}
+
+// du[n,p,ch] = dv[n,p,ch] * att[n][ch] + dgs[n][ch]
+template <typename T>
+__global__ void __launch_bounds__(256) shared_du_kernel(long long total, int hw, int C, tbi_view dv, tbi_view du, const float* __restrict__ att,
+                                                        const float* __restrict__ dgs) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % C); const long long pg = i / C; const int n = (int)(pg / hw);
+        const float g = ldf((const T*)dv.ptr + (size_t)pg * dv.cstride + dv.coff + ch);
+        stf((T*)du.ptr + (size_t)pg * du.cstride + du.coff + ch, fmaf(g, att[(size_t)n * C + ch], dgs[(size_t)n * C + ch]));
+    }
+}
+
 unsigned grid_cap(long long work, int per_block, int waves) {
     long long b = (work + per_block - 1) / per_block;
     const long long cap = (long long)tbi_sm_count() * waves;
@@ -230,5 +344,36 @@ extern "C" int tbi_splitatt_shared_fwd(int dtype, int n, int h, int w, int kpath
         shared_scale_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, *u, *v, att);
     } else return tbi_set_error(TBI_ERR_UNSUPPORTED, "splitatt_shared_fwd dtype");
     TBI_CUDA_LAUNCH_CHECK("splitatt_shared_fwd");
+    return TBI_OK;
+}
+
+extern "C" int tbi_splitatt_shared_bwd(int dtype, int n, int h, int w, int kpaths, int radix, int c, const tbi_view* u, const tbi_view* dv,
+                                       const tbi_view* du, const float* w1, const float* b1, const float* ln_gamma, const float* ln_beta,
+                                       float ln_eps, int act, const float* w2, const float* att, float* dw1, float* db1, float* dln_gamma,
+                                       float* dln_beta, float* dw2, float* db2, float* scratch, void* stream) {
+    TBI_CHECK(u && dv && du && w1 && b1 && ln_gamma && ln_beta && w2 && att && dw1 && db1 && dln_gamma && dln_beta && dw2 && db2 && scratch,
+              TBI_ERR_BAD_SHAPE, "splitatt_shared_bwd: null argument");
+    TBI_CHECK(c >= 2 && kpaths >= 1 && radix >= 1 && u->c == kpaths * c && dv->c == kpaths * c && du->c == kpaths * c, TBI_ERR_BAD_SHAPE,
+              "splitatt_shared_bwd: u/dv/du must have kpaths*c = %d channels", kpaths * c);
+    TBI_CHECK(c <= 2048, TBI_ERR_UNSUPPORTED, "splitatt_shared_bwd: c = %d > 2048", c);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int hw = h * w, C = kpaths * c;
+    float* su = scratch; float* sdu = scratch + (size_t)n * C;
+    if (cudaMemsetAsync(scratch, 0, 2 * (size_t)n * C * sizeof(float), s) != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "splitatt_shared_bwd: memset");
+    int chunks = (tbi_sm_count() * 4 + n - 1) / n;
+    if (chunks > (hw + 63) / 64) chunks = (hw + 63) / 64;
+    if (chunks < 1) chunks = 1;
+    const int ppb = (hw + chunks - 1) / chunks;
+    const dim3 gg((unsigned)((hw + ppb - 1) / ppb), (unsigned)n);
+    const unsigned ge = grid_cap((long long)n * hw * C, 256 * 4, 16);
+    const size_t fsm = (size_t)(2 * c + 3 * (c / 2) + 32) * sizeof(float);
+    if (dtype == TBI_F32) shared_bwd_reduce_kernel<float><<<gg, 256, 0, s>>>(hw, C, *u, *dv, su, sdu, ppb);
+    else if (dtype == TBI_BF16) shared_bwd_reduce_kernel<__nv_bfloat16><<<gg, 256, 0, s>>>(hw, C, *u, *dv, su, sdu, ppb);
+    else return tbi_set_error(TBI_ERR_UNSUPPORTED, "splitatt_shared_bwd dtype");
+    shared_fc_bwd_kernel<<<dim3((unsigned)n, (unsigned)kpaths), 128, fsm, s>>>(hw, kpaths, radix, c, w1, b1, ln_gamma, ln_beta, ln_eps, act, w2, att, su, sdu,
+                                                                               dw1, db1, dln_gamma, dln_beta, dw2, db2);
+    if (dtype == TBI_F32) shared_du_kernel<float><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, *dv, *du, att, su);
+    else shared_du_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, *dv, *du, att, su);
+    TBI_CUDA_LAUNCH_CHECK("splitatt_shared_bwd");
     return TBI_OK;
 }
