@@ -1,6 +1,7 @@
 """Variant B decoder: drop-in for the reference's ``Decoder.py`` (DecoderBlock :7-94, DecoderCup :98-146) on the B200 path.
-Forward / inference only this round (see ResNest.py in this package for the conventions: lazy variables, Keras names and
-layouts, NHWC in and out, every arithmetic step a libtbi_sm100.so entry point).
+Forward, and backward through the tape of ResNest.py in this package (``forward(..., record=True)`` then
+``backward(dlogits)`` -> (dL/dhidden_states, [dL/dskips]); parameter gradients in ``gradients()``).  Conventions as in
+ResNest.py: lazy variables, Keras names and layouts, NHWC in and out, every arithmetic step a libtbi_sm100.so entry point.
 
     DecoderCup(num_classes, wDecay=None)(hidden_states [N,T,hidden], features=[x_3,x_2,x_1]) -> probs [N,16*gh,16*gw,num_classes]
 
