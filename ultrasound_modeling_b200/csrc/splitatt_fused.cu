@@ -623,14 +623,20 @@ bool make_plan(const tbi_splitatt* p, int bwd, ClusterPlan* pl) {
     const size_t w_b = bwd ? (size_t)K * c * c2 : (size_t)K * R * c2 * c;
     const int out_a = KC2, out_b = bwd ? KC : C;
     const int slice_mode = env_int("TBI_SA_SLICE", 0);      // 0 auto, 1 never slice, 2 always slice (tests)
-    const size_t small = 32 * 1024 / sizeof(float);
+    // slicing costs remote stores + a cluster barrier on the critical path, redundant computation costs L2 reads of the whole
+    // layer by every CTA (measured at c = 128, dense2 = 64 KB: sliced 20.1 us, redundant 21.5 us per forward launch)
+    const size_t small = (size_t)env_int("TBI_SA_SMALL_KB", 32) * 1024 / sizeof(float);
     pl->fc.s1 = (cs > 1 && (slice_mode == 2 || (slice_mode == 0 && w_a > small))) ? cs : 1;
     pl->fc.s2 = (cs > 1 && (slice_mode == 2 || (slice_mode == 0 && w_b > small))) ? cs : 1;
     const int n1 = (out_a + pl->fc.s1 - 1) / pl->fc.s1, n2 = (out_b + pl->fc.s2 - 1) / pl->fc.s2;
     size_t staged_floats = bwd ? (size_t)(R + 1) * c * (n1 | 1) + 4 * (size_t)n1 + (size_t)c2 * (n2 | 1)
                                : (size_t)n1 * (c + 5) + (size_t)n2 * (c2 + 1);
     staged_floats = (staged_floats + 3) & ~(size_t)3;
-    pl->fc.staged = (env_int("TBI_SA_STAGE", 1) != 0 && staged_floats * sizeof(float) <= 64 * 1024) ? 1 : 0;
+    // shared memory is not free: the CTAs of a launch start over a window that grows with their shared-memory size (measured
+    // with scratch/trace_splitatt.py: 0.6 us at 12 KB, 2.3 us at 24 KB, 5.3 us at 61 KB per CTA), so the forward kernel stages
+    // only small parameter sets; the backward matvecs need the transposed staged copies to read shared memory conflict-free
+    const size_t stage_cap = (size_t)env_int("TBI_SA_STAGE_KB", bwd ? 64 : 16) * 1024;
+    pl->fc.staged = (env_int("TBI_SA_STAGE", 1) != 0 && staged_floats * sizeof(float) <= stage_cap) ? 1 : 0;
     const size_t fc_floats = bwd ? (size_t)(cs + 2) * C + 2 * KC + 2 * KC2 : (size_t)(cs + 1) * C + KC + KC2;
     const size_t base = sizeof(float) * (fc_floats + (size_t)nt * V + (pl->fc.staged ? staged_floats : 0));
     const size_t cache_bytes = (size_t)nit * (bwd ? R + 1 : R) * nt * 16;
