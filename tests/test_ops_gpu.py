@@ -195,6 +195,36 @@ def test_split_attention_cluster_kernels(ops, monkeypatch, K, R, c, h, w, cs, nt
     _check_split_attention(ops, torch.bfloat16, K, R, c, 5, h, w)
 
 
+@pytest.mark.parametrize("h,c", [(128, 32), (32, 128)])
+def test_split_attention_full_size_properties(ops, h, c):
+    """BASELINE config 2 sizes (batch 32, radix 2, bf16), where the oracle is too slow: size-independent properties.
+    Images are independent and the cluster kernels use no atomics, so (i) running the batch in two halves gives BIT-identical
+    V and dU, (ii) parameter gradients of the halves add up, (iii) V is a convex combination per (pixel, channel) when R > 1
+    only through the per-image attention: sum_r a_r over radix is NOT 1 (softmax is over channels, the reference's quirk) but
+    sum_c a_r[c] is 1 for every r -- checked through V of an all-ones U."""
+    torch.manual_seed(2000 + c)
+    K, R, N = 1, 2, 32
+    D = lambda *s_: torch.randn(*s_, device="cuda")
+    mk = lambda: ops.SplitAttention(K, R, c, D(K, c, c // 2) * 0.2, D(K, c // 2) * 0.1, 1 + 0.1 * D(K, c // 2), 0.1 * D(K, c // 2), 0.1 * D(K, c // 2),
+                                    0.5 + torch.rand(K, c // 2, device="cuda"), D(K, R, c // 2, c) * 0.2, D(K, R, c) * 0.1)
+    sa = mk()
+    u = torch.randn(N, h, h, K * R * c, device="cuda").to(torch.bfloat16)
+    dv = torch.randn(N, h, h, K * c, device="cuda").to(torch.bfloat16)
+    v = sa.forward(u)
+    du, pg = sa.backward(u, dv)
+    halves, grads = [], []
+    for sl in (slice(0, N // 2), slice(N // 2, N)):
+        vh = sa.forward(u[sl].contiguous())
+        duh, pgh = sa.backward(u[sl].contiguous(), dv[sl].contiguous())
+        halves.append((vh, duh)); grads.append(pgh)
+    assert torch.equal(torch.cat([a for a, _ in halves]), v) and torch.equal(torch.cat([b for _, b in halves]), du)
+    for k_ in pg:
+        assert rel(grads[0][k_] + grads[1][k_], pg[k_]) < 1e-5, k_
+    ones = torch.ones(2, 8, 8, K * R * c, device="cuda", dtype=torch.bfloat16)
+    vo = sa.forward(ones).float()                       # V[c] = sum_r a_r[c]  ->  sum_c V[c] = R
+    assert float((vo.sum(-1) - R).abs().max()) < 2e-2 * R
+
+
 def _check_split_attention(ops, dtype, K, R, c, n, h, w):
     torch.manual_seed(5)
     u_pre = torch.randn(n, h, w, K * R * c, dtype=torch.float64, requires_grad=True)

@@ -65,7 +65,7 @@ __device__ __forceinline__ Map make_map(int NT, int KC, int c, int npx) {
 template <int R, bool MUL, int NT>
 __device__ __forceinline__ void pass1(const Map& m, const __nv_bfloat16* up, int ucs, const __nv_bfloat16* dp, int dcs, int c,
                                       int npx, float (&s)[R][V], uint4* cache_u, uint4* cache_d) {
-    constexpr int UN = MUL ? (R == 1 ? 8 : R == 2 ? 4 : 2) : (R == 1 ? 8 : R == 2 ? 4 : R == 3 ? 2 : 1);   // 5..8 independent 16-byte loads in flight per thread
+    constexpr int UN = MUL ? (NT == 512 ? (R == 1 ? 4 : R == 2 ? 2 : 1) : (R == 1 ? 8 : R == 2 ? 4 : 2)) : (R == 1 ? 8 : R == 2 ? 4 : R == 3 ? 2 : 1);   // 5..8 independent 16-byte loads in flight per thread
     const int tid = threadIdx.x;
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) splitatt_fwd_cluster_kernel(tbi
 
 // scratch layout (as tbi_split_attention_bwd): dz [n][K][R][c] | dgap [n][K][c] | dbn [n][K][c2] | xhat [n][K][c2]
 template <int R, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) splitatt_bwd_cluster_kernel(tbi_splitatt p, tbi_view u, tbi_view dv, tbi_view du, float* scratch,
+__global__ void __launch_bounds__(NT, 2) splitatt_bwd_cluster_kernel(tbi_splitatt p, tbi_view u, tbi_view dv, tbi_view du, float* scratch,
                                                                                       int cache, FcPlan fc) {
     extern __shared__ __align__(16) float sm[];
     cg::cluster_group cl = cg::this_cluster();
@@ -557,15 +557,20 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) splitatt_bwd_cluster_ke
     // ---- pass 2: dU over the same chunk, same mapping, last pixels first; dead lines read and written with .cs
     {
         const float inv_hw = 1.f / (float)hw;
-        float a[R][V], dgs[V];
+        // 512-thread CTAs run at 64 registers (two CTAs per SM): the attention values stay in shared memory there
+        constexpr bool A_REGS = NT == 256;
+        float a[A_REGS ? R : 1][V], dgs[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) dgs[k] = dg[m.co + k] * inv_hw;
+        if (A_REGS) {
 #pragma unroll
-        for (int r = 0; r < R; ++r)
+            for (int r = 0; r < R; ++r)
 #pragma unroll
-            for (int k = 0; k < V; ++k) a[r][k] = att[(m.kk * R + r) * c + m.cc + k];
+                for (int k = 0; k < V; ++k) a[r][k] = att[(m.kk * R + r) * c + m.cc + k];
+        }
+        const float* arow = att + m.kk * R * c + m.cc;
         __nv_bfloat16* dup = (__nv_bfloat16*)du.ptr + ((size_t)n * hw + pbeg) * du.cstride + du.coff + (size_t)m.kk * R * c + m.cc;
-        constexpr int UN = R == 1 ? 8 : R == 2 ? 4 : 2;
+        constexpr int UN = NT == 512 ? (R == 1 ? 4 : R == 2 ? 2 : 1) : (R == 1 ? 8 : R == 2 ? 4 : 2);
         for (int it = ((m.nit - 1) / UN) * UN; it >= 0; it -= UN) {
             uint4 q[UN][R], gq[UN];
 #pragma unroll
@@ -590,7 +595,7 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 1) splitatt_bwd_cluster_ke
                         float x[V], o[V];
                         unpack8(q[i][r], x);
 #pragma unroll
-                        for (int k = 0; k < V; ++k) o[k] = fmaf(gv[k], a[r][k], dgs[k]) * act_grad_from_out(p.act, x[k]);
+                        for (int k = 0; k < V; ++k) o[k] = fmaf(gv[k], A_REGS ? a[r][k] : arow[r * c + k], dgs[k]) * act_grad_from_out(p.act, x[k]);
                         __stcs(reinterpret_cast<uint4*>(dup + (size_t)px * du.cstride + r * c), pack8(o));
                     }
                 }
@@ -615,6 +620,8 @@ bool make_plan(const tbi_splitatt* p, int bwd, ClusterPlan* pl) {
     }
     const int npx = (hw + cs - 1) / cs;
     int nt = env_int("TBI_SA_NT", 0);
+    // backward: 512-thread CTAs (64 registers, attention values in shared memory) measured slower than 256-thread ones
+    // (66.1 / 42.5 / 36.1 us against 61.4 / 40.9 / 30.4 us on the three config-2 shapes)
     if (nt != 256 && nt != 512) nt = (!bwd && (long long)npx * cvv >= 512 * 4) ? 512 : 256;
     if (cvv < 1 || cvv > nt || nt % cvv != 0) return false;
     const int nit = (npx + nt / cvv - 1) / (nt / cvv);

@@ -9,6 +9,7 @@ Adam then applies grad_scale = 1/world (average).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -33,7 +34,9 @@ def plan_buckets(marks: Sequence[Tuple[int, int]], total: int, bucket_elems: int
 
 
 class GradSync:
-    def __init__(self, process_group=None, bucket_bytes: int = 25 << 20):
+    def __init__(self, process_group=None, bucket_bytes: Optional[int] = None):
+        if bucket_bytes is None:                             # TBI_BUCKET_MB: sweep knob for bench runs
+            bucket_bytes = int(os.environ.get("TBI_BUCKET_MB", "25")) << 20
         if not dist.is_initialized():
             raise RuntimeError("GradSync needs torch.distributed to be initialised (backend nccl on GPUs)")
         self.pg = process_group
