@@ -166,6 +166,38 @@ __global__ void __launch_bounds__(256) convt_gather4_bf16_kernel(int n, int h, i
     }
 }
 
+// The inverse direction (forward of a k = 4, stride-2 transposed conv computed as a plain GEMM per INPUT pixel):
+// Y[n,i,j,(ky*4+kx)*COUT+co] = sum_ci X[n,i,j,ci] * W[ky][kx][co][ci]  (fp32 records of y.cstride channels), and
+// out[n,oy,ox,co] = bias[co] + sum over the 2 x 2 (ky,kx) with 2i - 1 + ky = oy, 2j - 1 + kx = ox of Y[n,i,j,..].
+// One thread per OUTPUT pixel; the four records it reads are shared with its neighbours (L1/L2).
+template <int COUT>
+__global__ void __launch_bounds__(256) convt_scatter4_f32_kernel(int n, int h, int w, tbi_view y, const float* __restrict__ bias, tbi_view out) {
+    const int H = 2 * h, W = 2 * w;
+    const long long total = (long long)n * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % W); long long t = i / W; const int oy = (int)(t % H); const int b = (int)(t / H);
+        float acc[COUT];
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int ky = ((oy + 1) & 1) + 2 * a, iy = (oy + 1 - ky) >> 1;
+            if (iy < 0 || iy >= h) continue;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int kx = ((ox + 1) & 1) + 2 * e, ix = (ox + 1 - kx) >> 1;
+                if (ix < 0 || ix >= w) continue;
+                const float* src = (const float*)y.ptr + view_off(y, b, iy, ix, (ky * 4 + kx) * COUT);
+#pragma unroll
+                for (int c = 0; c < COUT; ++c) acc[c] += src[c];
+            }
+        }
+        float* dst = (float*)out.ptr + view_off(out, b, oy, ox, 0);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) dst[c] = acc[c];
+    }
+}
+
 template <typename T, int V>
 __global__ void accumulate_kernel(long long npix, tbi_view src, tbi_view dst) {
     const int cv = dst.c / V;
@@ -700,9 +732,14 @@ struct ConvtTapTable { int n[4]; int off[4]; int ky[4][4]; int kx[4][4]; };
 template <typename T>
 __global__ void pack_convt_kernel(int mode, int k, int cin, int cout, int cpad, ConvtTapTable tt, const float* __restrict__ w,
                                   const float* __restrict__ scale, T* __restrict__ out) {
-    const long long total = mode == 2 ? (long long)cin * cpad : (long long)k * k * cin * (mode == 1 ? cpad : cout);
+    const long long total = mode >= 2 ? (long long)cin * cpad : (long long)k * k * cin * (mode == 1 ? cpad : cout);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int ky, kx, ci, co;
+        if (mode == 3) {            // out[q][ci]: the transposed-conv forward as a plain GEMM per INPUT pixel (K = cin, N = q)
+            ci = (int)(i % cin); const int q = (int)(i / cin);
+            if (q >= k * k * cout) { stf(out + i, 0.f); continue; }
+            co = q % cout; const int tap = q / cout; ky = tap / k; kx = tap % k;
+        } else
         if (mode == 2) {            // out[ci][q], q = (ky*k+kx)*cout + co, zero-padded to cpad
             const int q = (int)(i % cpad); ci = (int)(i / cpad);
             if (q >= k * k * cout) { stf(out + i, 0.f); continue; }
@@ -949,6 +986,22 @@ extern "C" int tbi_convt_gather_dz(int dtype, int n, int h, int w, int ksize, in
     return TBI_OK;
 }
 
+extern "C" int tbi_convt_scatter_y(int n, int h, int w, int ksize, int cout, const tbi_view* y, const float* bias, const tbi_view* out, void* stream) {
+    TBI_CHECK(ksize == 4 && cout >= 1 && cout <= 4, TBI_ERR_UNSUPPORTED, "convt_scatter: ksize %d, cout %d (k = 4, cout <= 4 only)", ksize, cout);
+    TBI_CHECK(y && out && y->h == h && y->w == w && y->c >= 16 * cout && out->h == 2 * h && out->w == 2 * w && out->c >= cout, TBI_ERR_BAD_SHAPE,
+              "convt_scatter: shapes");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned g = grid_for((long long)n * 4 * h * w, 256);
+    switch (cout) {
+        case 1: convt_scatter4_f32_kernel<1><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
+        case 2: convt_scatter4_f32_kernel<2><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
+        case 3: convt_scatter4_f32_kernel<3><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
+        default: convt_scatter4_f32_kernel<4><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
+    }
+    TBI_CUDA_LAUNCH_CHECK("convt_scatter");
+    return TBI_OK;
+}
+
 extern "C" int tbi_accumulate(int dtype, int64_t npix, const tbi_view* src, const tbi_view* dst, void* stream) {
     TBI_CHECK(src->c == dst->c, TBI_ERR_BAD_SHAPE, "accumulate: channel mismatch");
     cudaStream_t s = (cudaStream_t)stream;
@@ -1176,8 +1229,8 @@ int tbi_wgrad_gather_blocks(int ntaps, int groups, int cin_g, int cout_total, co
 extern "C" int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout, int cout_pad, const float* w_hwoi,
                                       const float* scale, void* out, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
-    const int cpad = ((mode == 1 && cout_pad > cout) || mode == 2) ? cout_pad : cout;
-    TBI_CHECK(mode != 2 || cout_pad >= ksize * ksize * cout, TBI_ERR_BAD_SHAPE, "pack_convt mode 2: cout_pad %d < k*k*cout", cout_pad);
+    const int cpad = ((mode == 1 && cout_pad > cout) || mode >= 2) ? cout_pad : cout;
+    TBI_CHECK(mode < 2 || cout_pad >= ksize * ksize * cout, TBI_ERR_BAD_SHAPE, "pack_convt mode %d: cout_pad %d < k*k*cout", mode, cout_pad);
     ConvtTapTable tt{};
     int off = 0;
     for (int ph = 0; ph < 4; ++ph) {
@@ -1187,7 +1240,7 @@ extern "C" int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, i
         tt.n[ph] = n; tt.off[ph] = off; off += n;
         for (int t = 0; t < n; ++t) { tt.ky[ph][t] = ky[t]; tt.kx[ph][t] = kx[t]; }
     }
-    const unsigned g = grid_for(mode == 2 ? (long long)cin * cpad : (long long)ksize * ksize * cin * cpad, 256);
+    const unsigned g = grid_for(mode >= 2 ? (long long)cin * cpad : (long long)ksize * ksize * cin * cpad, 256);
     if (dtype == TBI_F32) pack_convt_kernel<float><<<g, 256, 0, s>>>(mode, ksize, cin, cout, cpad, tt, w_hwoi, scale, (float*)out);
     else if (dtype == TBI_BF16) pack_convt_kernel<__nv_bfloat16><<<g, 256, 0, s>>>(mode, ksize, cin, cout, cpad, tt, w_hwoi, scale, (__nv_bfloat16*)out);
     else return tbi_set_error(TBI_ERR_UNSUPPORTED, "pack dtype");
