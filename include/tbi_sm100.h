@@ -188,11 +188,12 @@ int tbi_pack_convt_weights(int dtype, int mode, int ksize, int cin, int cout, in
  * after which dW_hwoi (flattened [k*k*cout][cin]) = G^T X  and  dX = G W' are plain (1-tap) tap-GEMMs.
  * tbi_pack_convt_weights mode 2 writes W'[ci][q], q = (ky*k+kx)*cout+co, rows zero-padded to cout_pad.       */
 int tbi_convt_gather_dz(int dtype, int n, int h, int w, int ksize, int cout, const tbi_view* dz, const tbi_view* g, void* stream);
-/* forward counterpart: Y fp32 [n,h,w,>=16*cout] = the k=4 stride-2 transposed conv evaluated as ONE plain GEMM per input pixel
+/* forward counterpart: Y (fp32 or bf16: y_dtype) [n,h,w,>=16*cout] = the k=4 stride-2 transposed conv evaluated as ONE plain GEMM per input pixel
  * (weights packed with tbi_pack_convt_weights mode 3: [q = tap*cout + co][cin]); out fp32 [n,2h,2w,cout] = bias + the four
  * (tap, input pixel) contributions of every output pixel.  Used for the head f_tran (TBI_ResNest.py:124): with cout = 3 the
  * per-output-phase form issues 160 N=16 MMAs per 128 outputs and is MMA-dispatch-bound.                            */
-int tbi_convt_scatter_y(int n, int h, int w, int ksize, int cout, const tbi_view* y, const float* bias, const tbi_view* out, void* stream);
+int tbi_convt_scatter_y(int y_dtype, int n, int h, int w, int ksize, int cout, const tbi_view* y, const float* bias,
+                        const tbi_view* out, void* stream);
 /* taps of output-parity phase (a,b): returns count; ky/kx = kernel index, dy/dx = input offset.  */
 int tbi_convt_phase_taps(int ksize, int a, int b, int* ky, int* kx, int* dy, int* dx);
 

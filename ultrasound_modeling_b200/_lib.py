@@ -113,7 +113,7 @@ SIGNATURES = {
     "tbi_pack_conv_weights": (_I, [_I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "tbi_pack_convt_weights": (_I, [_I, _I, _I, _I, _I, _I, _VP, _VP, _VP, _VP]),
     "tbi_convt_gather_dz": (_I, [_I, _I, _I, _I, _I, _I, _PV, _PV, _VP]),
-    "tbi_convt_scatter_y": (_I, [_I, _I, _I, _I, _I, _PV, _VP, _PV, _VP]),
+    "tbi_convt_scatter_y": (_I, [_I, _I, _I, _I, _I, _I, _PV, _VP, _PV, _VP]),
     "tbi_convt_phase_taps": (_I, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
     "tbi_bn_fold": (_I, [_I, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP]),
     "tbi_bn_param_grad": (_I, [_I, _I64, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP]),

@@ -167,11 +167,11 @@ __global__ void __launch_bounds__(256) convt_gather4_bf16_kernel(int n, int h, i
 }
 
 // The inverse direction (forward of a k = 4, stride-2 transposed conv computed as a plain GEMM per INPUT pixel):
-// Y[n,i,j,(ky*4+kx)*COUT+co] = sum_ci X[n,i,j,ci] * W[ky][kx][co][ci]  (fp32 records of y.cstride channels), and
+// Y[n,i,j,(ky*4+kx)*COUT+co] = sum_ci X[n,i,j,ci] * W[ky][kx][co][ci]  (records of y.cstride channels, fp32 or bf16), and
 // out[n,oy,ox,co] = bias[co] + sum over the 2 x 2 (ky,kx) with 2i - 1 + ky = oy, 2j - 1 + kx = ox of Y[n,i,j,..].
 // One thread per OUTPUT pixel; the four records it reads are shared with its neighbours (L1/L2).
-template <int COUT>
-__global__ void __launch_bounds__(256) convt_scatter4_f32_kernel(int n, int h, int w, tbi_view y, const float* __restrict__ bias, tbi_view out) {
+template <typename TY, int COUT>
+__global__ void __launch_bounds__(256) convt_scatter4_kernel(int n, int h, int w, tbi_view y, const float* __restrict__ bias, tbi_view out) {
     const int H = 2 * h, W = 2 * w;
     const long long total = (long long)n * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -187,9 +187,9 @@ __global__ void __launch_bounds__(256) convt_scatter4_f32_kernel(int n, int h, i
             for (int e = 0; e < 2; ++e) {
                 const int kx = ((ox + 1) & 1) + 2 * e, ix = (ox + 1 - kx) >> 1;
                 if (ix < 0 || ix >= w) continue;
-                const float* src = (const float*)y.ptr + view_off(y, b, iy, ix, (ky * 4 + kx) * COUT);
+                const TY* src = (const TY*)y.ptr + view_off(y, b, iy, ix, (ky * 4 + kx) * COUT);
 #pragma unroll
-                for (int c = 0; c < COUT; ++c) acc[c] += src[c];
+                for (int c = 0; c < COUT; ++c) acc[c] += ldf(src + c);
             }
         }
         float* dst = (float*)out.ptr + view_off(out, b, oy, ox, 0);
@@ -986,18 +986,23 @@ extern "C" int tbi_convt_gather_dz(int dtype, int n, int h, int w, int ksize, in
     return TBI_OK;
 }
 
-extern "C" int tbi_convt_scatter_y(int n, int h, int w, int ksize, int cout, const tbi_view* y, const float* bias, const tbi_view* out, void* stream) {
+extern "C" int tbi_convt_scatter_y(int y_dtype, int n, int h, int w, int ksize, int cout, const tbi_view* y, const float* bias, const tbi_view* out,
+                                   void* stream) {
     TBI_CHECK(ksize == 4 && cout >= 1 && cout <= 4, TBI_ERR_UNSUPPORTED, "convt_scatter: ksize %d, cout %d (k = 4, cout <= 4 only)", ksize, cout);
     TBI_CHECK(y && out && y->h == h && y->w == w && y->c >= 16 * cout && out->h == 2 * h && out->w == 2 * w && out->c >= cout, TBI_ERR_BAD_SHAPE,
               "convt_scatter: shapes");
+    TBI_CHECK(y_dtype == TBI_F32 || y_dtype == TBI_BF16, TBI_ERR_UNSUPPORTED, "convt_scatter: y dtype");
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned g = grid_for((long long)n * 4 * h * w, 256);
+#define TBI_SCATTER(CO) do { if (y_dtype == TBI_F32) convt_scatter4_kernel<float, CO><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); \
+                             else convt_scatter4_kernel<__nv_bfloat16, CO><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); } while (0)
     switch (cout) {
-        case 1: convt_scatter4_f32_kernel<1><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
-        case 2: convt_scatter4_f32_kernel<2><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
-        case 3: convt_scatter4_f32_kernel<3><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
-        default: convt_scatter4_f32_kernel<4><<<g, 256, 0, s>>>(n, h, w, *y, bias, *out); break;
+        case 1: TBI_SCATTER(1); break;
+        case 2: TBI_SCATTER(2); break;
+        case 3: TBI_SCATTER(3); break;
+        default: TBI_SCATTER(4); break;
     }
+#undef TBI_SCATTER
     TBI_CUDA_LAUNCH_CHECK("convt_scatter");
     return TBI_OK;
 }
