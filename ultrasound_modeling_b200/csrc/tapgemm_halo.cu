@@ -568,7 +568,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     p.c0 = d->groups > 1 ? d->cin_g * d->groups : d->src[0].c;
     p.kc = kc; p.nchunks = d->cin_g / kc; p.row_bytes = kc * 2;
     p.ngroups = tp.ngroups; p.ntaps = d->ntaps; p.pitch = TW + tp.ex;
-    p.narrow = (d->cout_g < 8 && d->groups == 1) ? 1 : 0;
+    p.narrow = tbi_tc_narrow(d) ? 1 : 0;
     p.epi = d->epi;
     p.out_stride = d->nphase > 1 ? 2 : (d->epi.out_stride ? d->epi.out_stride : 1);
     for (int gi = 0; gi < tp.ngroups; ++gi) { p.g_ox[gi] = tp.ox[gi]; p.g_oy[gi] = tp.oy[gi]; p.g_ax[gi] = tp.ax[gi]; p.g_ay[gi] = tp.ay[gi]; }
@@ -587,6 +587,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     else p.a[1] = p.a[0];
     int bn = 128;
     while (bn > 16 && bn / 2 >= d->cout_g) bn >>= 1;
+    if (p.narrow) bn = 16;                                   // the element-wise epilogue exists for 16-column tiles only
     {
         const uint64_t K = (uint64_t)d->ntaps * d->cin_g;
         uint64_t dims[2] = {K, (uint64_t)p.cout_total * p.nphase};

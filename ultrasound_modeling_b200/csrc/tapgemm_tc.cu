@@ -243,7 +243,7 @@ bool tbi_tapgemm_tc_supported(const tbi_tapgemm* d, const char** why) {
     if (d->in_stride != 1 && d->in_stride != 2) NO("in_stride");
     if (d->groups > 1 && d->src[1].ptr) NO("groups with two sources");
     if (pick_kc(d) == 0) NO("input channels per source are not a multiple of 16");
-    const bool narrow = d->cout_g < 8 && d->groups == 1;
+    const bool narrow = tbi_tc_narrow(d);
     if (d->cout_g % 8 != 0 && !narrow) NO("output channels per group are not a multiple of 8");
     if (!aligned_view(d->src[0]) || !aligned_view(d->src[1])) NO("source view not 16-byte aligned");
     if (d->in_stride == 2 && ((d->src[0].h | d->src[0].w) & 1)) NO("stride-2 gather needs even source dims");
@@ -289,7 +289,7 @@ int tbi_tapgemm_tc(const tbi_tapgemm* d, cudaStream_t s) {
     p.cin_g = d->cin_g; p.cout_g = d->cout_g; p.groups = d->groups; p.cout_total = d->cout_g * d->groups;
     p.c0 = d->groups > 1 ? d->cin_g * d->groups : d->src[0].c;
     p.kc = kc; p.nphase = d->nphase > 1 ? d->nphase : 1; p.ntaps = d->ntaps;
-    p.narrow = (d->cout_g < 8 && d->groups == 1) ? 1 : 0;
+    p.narrow = tbi_tc_narrow(d) ? 1 : 0;
     p.epi = d->epi;
     p.out_stride = d->nphase > 1 ? 2 : (d->epi.out_stride ? d->epi.out_stride : 1);
     for (int ph = 0; ph < p.nphase; ++ph) {
@@ -312,6 +312,7 @@ int tbi_tapgemm_tc(const tbi_tapgemm* d, cudaStream_t s) {
     } else p.a[1] = p.a[0];
     int bn = 128;
     while (bn > 16 && bn / 2 >= d->cout_g) bn >>= 1;
+    if (p.narrow) bn = 16;                                   // the element-wise epilogue exists for 16-column tiles only
     {
         const uint64_t K = (uint64_t)d->ntaps * d->cin_g;
         uint64_t dims[2] = {K, (uint64_t)p.cout_total * p.nphase};

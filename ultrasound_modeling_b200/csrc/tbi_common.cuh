@@ -79,6 +79,13 @@ __device__ __forceinline__ void epilogue_store(const tbi_epilogue& e, int n, int
     else stf((T*)e.out.ptr + view_off(e.out, n, oy, ox, co), v);
 }
 
+// "narrow" tensor-core epilogue: 16-column accumulator tiles written element by element through epilogue_store() (any output
+// dtype).  Used when there are fewer than 8 output channels (the 3-class head) and for fp32 outputs of up to 64 columns (the
+// head's forward as a per-input-pixel GEMM, engine.py) -- the vectorised epilogue writes bf16 only.
+static inline bool tbi_tc_narrow(const tbi_tapgemm* d) {
+    return d->groups == 1 && (d->cout_g < 8 || (d->epi.out_f32 && d->cout_g <= 64));
+}
+
 // entry points implemented per translation unit
 int tbi_tapgemm_simt(const tbi_tapgemm* d, cudaStream_t s);
 int tbi_tapwgrad_simt(const tbi_tapwgrad* d, cudaStream_t s);

@@ -347,13 +347,15 @@ class Engine:
         # Y[n,H/2,W/2, 16 taps x num_class (padded to 64)], followed by the 4-tap scatter into the logits.  With 3 output channels
         # the per-phase transposed conv is MMA-dispatch-bound (160 N=16 MMAs per 128 outputs: 267 us against a 60 us HBM floor).
         # Measured: Y in bf16 -> step 9.61 -> 9.52 ms but the bf16 r4k4 gradient test leaves the 2e-2 bar (each logit becomes a
-        # sum of four bf16-rounded terms); Y in fp32 -> correct, but a 64-column fp32 output is not on the tcgen05 epilogue's
-        # fast path yet (10.55 ms).  Needs the fp32 epilogue for 64-column tiles: round-2 item.
+        # sum of four bf16-rounded terms); Y in fp32 (48 columns through the element-wise "narrow" tcgen05 epilogue,
+        # tbi_tc_narrow) -> exact, but that epilogue costs more than the MMAs save (9.85 ms; 10.55 ms on the CUDA-core path).
+        # Needs a vectorised fp32 epilogue, or the scatter fused into the GEMM epilogue: round-2 item.
         mode = os.environ.get("TBI_HEAD_FWD_GEMM", "0")
         self.head_fwd_gemm = self.head_gather and mode in ("1", "bf16")
         if self.head_fwd_gemm:
-            self.head_y = torch.empty(n, H // 2, W // 2, 64, dtype=td if mode == "bf16" else torch.float32, device=dev)
-            self.head_wf = torch.empty(64 * self.head.cin, dtype=td, device=dev)
+            self.head_yc = 64 if mode == "bf16" else 16 * self.num_class          # fp32: exactly the real columns (narrow epilogue)
+            self.head_y = torch.empty(n, H // 2, W // 2, self.head_yc, dtype=td if mode == "bf16" else torch.float32, device=dev)
+            self.head_wf = torch.empty(self.head_yc * self.head.cin, dtype=td, device=dev)
         self.loss_map = torch.empty(H, W, dtype=torch.float32, device=dev)
         self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
         # packed compute weights + folded BN
@@ -434,7 +436,7 @@ class Engine:
                 if Lr is self.head and self.head_gather:
                     self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 2, Lr.k, Lr.cin, Lr.cout, 64, wp, sc, _ptr(self.head_wg))))
                 if Lr is self.head and self.head_fwd_gemm:
-                    self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 3, Lr.k, Lr.cin, Lr.cout, 64, wp, sc, _ptr(self.head_wf))))
+                    self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 3, Lr.k, Lr.cin, Lr.cout, self.head_yc, wp, sc, _ptr(self.head_wf))))
 
         # weight packing of everything behind the full-resolution stem runs on a side stream, overlapped with the stem's
         # forward (the pack/fold launches are ~85 tiny grids, ~0.6 ms when serialised in front of the step)
@@ -526,7 +528,7 @@ class Engine:
         if self.head_fwd_gemm:
             gf = keep(TapGemm())
             gf.dtype = dt; gf.impl = impl; gf.n = n; gf.gh = H // 2; gf.gw = W // 2; gf.groups = 1
-            gf.cin_g = self.head.cin; gf.cout_g = 64; gf.src[0] = view(self.up[4]); gf.src[1] = view(self.pool[0]); gf.in_stride = 1; gf.ntaps = 1
+            gf.cin_g = self.head.cin; gf.cout_g = self.head_yc; gf.src[0] = view(self.up[4]); gf.src[1] = view(self.pool[0]); gf.in_stride = 1; gf.ntaps = 1
             gf.w = _ptr(self.head_wf); gf.epi = epi(out=view(self.head_y), out_f32=int(self.head_y.dtype == torch.float32))
             self.prog_fwd.append((L.tbi_tapgemm_run, (C.byref(gf),)))
             self.prog_fwd.append((L.tbi_convt_scatter_y, (F32 if self.head_y.dtype == torch.float32 else BF16, n, H // 2, W // 2, 4, self.num_class, bref(view(self.head_y)),
