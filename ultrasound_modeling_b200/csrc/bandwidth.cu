@@ -617,33 +617,52 @@ __global__ void splitatt_param_grad_kernel(tbi_splitatt p, const float* scratch,
 // ---------------------------------------------------------------------------------------------
 // softmax + my_loss_cat + accuracy (+ gradient w.r.t. logits)
 // ---------------------------------------------------------------------------------------------
+// The loss couples the batch through the per-pixel class counts, so a pixel is owned by one CTA -- but by SL_J threads of it:
+// thread (pixel lane, j) takes the images n = j, j + SL_J, ...; the counts and the pixel's loss are reduced over j through shared
+// memory in a fixed order (deterministic).  A warp is 32 consecutive pixels of one image: 384-byte contiguous accesses.
+// (One thread per pixel looping over the whole batch left only 65 536 threads for 285 MB of traffic: 118 us.)
+constexpr int SL_J = 8;
 template <int NC, typename TD>
-__global__ void softmax_loss_kernel(int N, int hw, const float* __restrict__ logits, const float* __restrict__ y,
-                                    float* __restrict__ probs, float* __restrict__ loss_map, int32_t* correct,
-                                    TD* __restrict__ dlogits, int dl_cs) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int ok = 0;
-    if (p < hw) {
-        float cnt[3] = {0.f, 0.f, 0.f};
-        for (int n = 0; n < N; ++n) {
+__global__ void __launch_bounds__(32 * SL_J) softmax_loss_kernel(int N, int hw, const float* __restrict__ logits, const float* __restrict__ y,
+                                                                float* __restrict__ probs, float* __restrict__ loss_map, int32_t* correct,
+                                                                TD* __restrict__ dlogits, int dl_cs) {
+    __shared__ float red[SL_J][32][3];
+    const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const bool live = p < hw;
+    float cnt[3] = {0.f, 0.f, 0.f};
+    if (live) {
+        for (int n = j; n < N; n += SL_J) {
             const float* yy = y + ((size_t)n * hw + p) * NC;
 #pragma unroll
             for (int c = 0; c < 3; ++c) cnt[c] += yy[c];
         }
-        float sf[3];
+    }
 #pragma unroll
-        for (int c = 0; c < 3; ++c) sf[c] = (1.f / (cnt[c] + 1.f)) / (float)hw;
-        float ce = 0.f;
-        for (int n = 0; n < N; ++n) {
+    for (int c = 0; c < 3; ++c) red[j][lane][c] = cnt[c];
+    __syncthreads();
+    float sf[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < SL_J; ++q) t += red[q][lane][c];
+        sf[c] = (1.f / (t + 1.f)) / (float)hw;
+    }
+    __syncthreads();
+    int ok = 0;
+    float ce = 0.f;
+    if (live) {
+        for (int n = j; n < N; n += SL_J) {
             const size_t o = ((size_t)n * hw + p) * NC;
             float z[NC], yy[NC];
             float m = -INFINITY;
 #pragma unroll
             for (int c = 0; c < NC; ++c) { z[c] = logits[o + c]; yy[c] = y[o + c]; m = fmaxf(m, z[c]); }
-            float s = 0.f;
+            float sm = 0.f;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) { z[c] = expf(z[c] - m); s += z[c]; }
-            const float inv = 1.f / s;
+            for (int c = 0; c < NC; ++c) { z[c] = expf(z[c] - m); sm += z[c]; }
+            const float inv = 1.f / sm;
             int am = 0, ay = 0;
 #pragma unroll
             for (int c = 0; c < NC; ++c) { z[c] *= inv; if (z[c] > z[am]) am = c; if (yy[c] > yy[ay]) ay = c; }
@@ -665,10 +684,17 @@ __global__ void softmax_loss_kernel(int N, int hw, const float* __restrict__ log
                 if (dlogits) stf(dlogits + ((size_t)n * hw + p) * dl_cs + c, z[c] * (dldp[c] - dot));
             }
         }
-        loss_map[p] = -ce;
+    }
+    red[j][lane][0] = ce;
+    __syncthreads();
+    if (j == 0 && live) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < SL_J; ++q) t += red[q][lane][0];
+        loss_map[p] = -t;
     }
     ok = (int)warp_sum((float)ok);
-    if ((threadIdx.x & 31) == 0 && ok) atomicAdd(correct, ok);
+    if (lane == 0 && ok) atomicAdd(correct, ok);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1180,13 +1206,13 @@ extern "C" int tbi_softmax_loss_fwd_bwd(int dlogits_dtype, int n, int h, int w, 
     TBI_CHECK(nc >= 3 && nc <= 4, TBI_ERR_UNSUPPORTED, "softmax_loss: num_class %d (my_loss_cat hard-codes 3 classes; 3..4 supported)", nc);
     cudaStream_t s = (cudaStream_t)stream;
     const int hw = h * w;
-    const unsigned g = (hw + 127) / 128;
+    const unsigned g = (hw + 31) / 32;
     if (dlogits_dtype == TBI_F32) {
-        if (nc == 3) softmax_loss_kernel<3, float><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
-        else         softmax_loss_kernel<4, float><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
+        if (nc == 3) softmax_loss_kernel<3, float><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
+        else         softmax_loss_kernel<4, float><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
     } else if (dlogits_dtype == TBI_BF16) {
-        if (nc == 3) softmax_loss_kernel<3, __nv_bfloat16><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
-        else         softmax_loss_kernel<4, __nv_bfloat16><<<g, 128, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
+        if (nc == 3) softmax_loss_kernel<3, __nv_bfloat16><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
+        else         softmax_loss_kernel<4, __nv_bfloat16><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
     } else return tbi_set_error(TBI_ERR_UNSUPPORTED, "softmax_loss: dlogits dtype");
     TBI_CUDA_LAUNCH_CHECK("softmax_loss");
     return TBI_OK;
