@@ -128,6 +128,11 @@ const char* tbi_last_error(void);
 /* 1 if the running device is sm_100 and the tcgen05 kernels can launch; 0 otherwise */
 int         tbi_device_ok(void);
 
+/* How many bf16 tap-GEMM / weight-gradient launches issued with TBI_IMPL_AUTO ran on the CUDA-core kernel because the tcgen05
+ * path refused their shape (cumulative per process; reset != 0 zeroes the counters), and the reason of the last one.     */
+int         tbi_fallback_stats(int64_t* tapgemm_simt, int64_t* tapwgrad_simt, int reset);
+const char* tbi_last_fallback(void);
+
 /* ---- convolutions ------------------------------------------------------------------------
  * tbi_tapgemm_run / tbi_tapwgrad_run are the single execution entry points; the named conv
  * entry points below fill the descriptors for the shapes the reference uses and call them.
@@ -313,6 +318,14 @@ int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void* src, void
 int tbi_adam_multi(int64_t count, float* p, const float* g, float* m, float* v, const int32_t* step_count,
                    float lr, float b1, float b2, float eps, float grad_scale, void* stream);
 int tbi_adam_advance(int32_t* step_count, void* stream);
+/* Same update with the hyper-parameters read from DEVICE memory: hyper = {lr, grad_scale, clip_norm} (fp32[3]).  A captured
+ * CUDA graph then follows learning-rate changes (the reference assigns schedules to .learning_rate, MainParallel.py:74-79).
+ * clip_norm > 0 with gnorm_sq != NULL applies tf.clip_by_global_norm (VisionTransformer.py:244):
+ *   g *= clip_norm / max(sqrt(*gnorm_sq) * |grad_scale|, clip_norm),  *gnorm_sq = sum of squares of the UNSCALED gradient
+ * which tbi_sumsq accumulates (out += sum x^2; the caller zeroes out).                                       */
+int tbi_adam_multi_dev(int64_t count, float* p, const float* g, float* m, float* v, const int32_t* step_count,
+                       const float* hyper, const float* gnorm_sq, float b1, float b2, float eps, void* stream);
+int tbi_sumsq(int64_t count, const float* x, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -49,7 +49,13 @@ def test_parameter_inventory_matches_reference_variables(radix, kpaths):
     for k, shp in want.items():
         assert got[k] == tuple(shp), (k, got[k], shp)
     n_train = sum(torch.Size(s).numel() for n, s in want.items() if O.is_trainable(n))
-    assert sum(s.numel for s in e.P.specs.values()) == n_train
+    mapped = sum(torch.Size(got[kn]).numel() for kn, store, _, _ in e._keras_items() if store == "P")
+    assert mapped == n_train
+    # what the flat buffer holds beyond the Keras variables: the zero pad channels of the fused 1x1 cardinal convs whose
+    # width G*cv11 is not a multiple of 16 (radix 3), each with a kernel column, a bias, gamma and beta
+    pad = sum((i["c1w"] - i["G"] * i["cv11"]) * (i["cin"] + 3) for i in e.stage_info)
+    assert sum(s.numel for s in e.P.specs.values()) == n_train + pad
+    assert (pad > 0) == (radix == 3)
 
 
 def test_plan_buckets_tiles_the_buffer():

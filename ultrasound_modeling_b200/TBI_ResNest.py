@@ -45,8 +45,15 @@ class _ResModel:
         return [v for k, v in named.items() if not (k.endswith("/moving_mean") or k.endswith("/moving_variance"))]
 
     def save(self, path):
+        """reference: self.resModel.save(path) (TBI_ResNest.py:472).  Writes <path>/variables.npz: Keras variable name ->
+        array in Keras layout (HWIO / HWOI); `load(path)` reads it back."""
         os.makedirs(path, exist_ok=True)
-        torch.save({k: v.cpu() for k, v in self._o.engine.state_dict().items()}, os.path.join(path, "variables.pt"))
+        np.savez(os.path.join(path, "variables.npz"), **{k: v.cpu().numpy() for k, v in self._o.engine.state_dict().items()})
+
+    def load(self, path):
+        with np.load(os.path.join(path, "variables.npz")) as z:
+            self._o.engine.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files})
+
 
 
 class ResNest:
@@ -67,6 +74,8 @@ class ResNest:
         self.loss = self.my_loss_cat
         self.use_cuda_graph = use_cuda_graph
         self.grad_sync = grad_sync                           # parallel.GradSync or None
+        if grad_sync is not None:
+            grad_sync.attach(self.engine)
         self._graphs = {}
         self._pin = {}
         self._warm = set()
@@ -74,33 +83,51 @@ class ResNest:
         self._y_event = None
 
     # ------------------------------------------------------------------ inputs
-    def _stage(self, name, arr, dst: torch.Tensor):
+    PIN_RING = 2
+
+    def _pinned(self, name, shape):
+        """a ring of pinned staging buffers per input; each slot remembers the event of the async copy that last read it, and
+        the host waits for that event before overwriting the slot (a step never synchronises, so without this the host could
+        rewrite the buffer while the previous step's DMA is still queued behind ~10 ms of GPU work)."""
+        ring = self._pin.get(name)
+        if ring is None or ring["shape"] != tuple(shape):
+            ring = self._pin[name] = dict(shape=tuple(shape), i=0,
+                                          bufs=[torch.empty(shape, dtype=torch.float32, pin_memory=True) for _ in range(self.PIN_RING)],
+                                          events=[None] * self.PIN_RING)
+        i = ring["i"]
+        ring["i"] = (i + 1) % self.PIN_RING
+        if ring["events"][i] is not None:
+            ring["events"][i].synchronize()
+        return ring, i
+
+    def _stage(self, name, arr, dst: torch.Tensor, stream=None):
         """host (numpy/torch, fp64/fp32) or device tensor -> the engine's static fp32 input buffer"""
         if isinstance(arr, np.ndarray):
             arr = torch.from_numpy(np.ascontiguousarray(arr))
         if arr.device.type == "cpu" and arr.dtype == torch.float32 and arr.is_contiguous() and arr.is_pinned():
             dst.copy_(arr.reshape(dst.shape), non_blocking=True)      # caller's pinned fp32 buffer: DMA straight from it
         elif arr.device.type == "cpu":
-            pin = self._pin.get(name)
-            if pin is None or pin.shape != dst.shape:
-                pin = torch.empty(dst.shape, dtype=torch.float32, pin_memory=True)
-                self._pin[name] = pin
+            ring, i = self._pinned(name, dst.shape)
+            pin = ring["bufs"][i]
             pin.copy_(arr.reshape(dst.shape))                # casts fp64 -> fp32 on the host, like Keras' autocast
             dst.copy_(pin, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.engine.device))
+            ring["events"][i] = ev
         else:
             dst.copy_(arr.reshape(dst.shape))
 
     def _stage_labels(self, y, dst: torch.Tensor):
-        """the labels are first needed by the loss, a whole forward pass after the step starts: a pinned fp32 host tensor is
-        copied on a side stream while the forward runs (3/4 of the step's host->device bytes are labels); anything else goes
-        through _stage on the main stream."""
-        if torch.is_tensor(y) and y.device.type == "cpu" and y.dtype == torch.float32 and y.is_contiguous() and y.is_pinned():
+        """the labels are first needed by the loss, a whole forward pass after the step starts: host labels are copied on a
+        side stream while the forward runs (3/4 of the step's host->device bytes are labels); a device tensor goes through
+        _stage on the main stream."""
+        if isinstance(y, np.ndarray) or (torch.is_tensor(y) and y.device.type == "cpu"):
             dev = self.engine.device
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(dev)
             self._copy_stream.wait_stream(torch.cuda.current_stream(dev))      # the previous step's loss has consumed y_in
             with torch.cuda.stream(self._copy_stream):
-                dst.copy_(y.reshape(dst.shape), non_blocking=True)
+                self._stage("y", y, dst)
             self._y_event = self._copy_stream.record_event()
         else:
             self._stage("y", y, dst)
@@ -123,13 +150,30 @@ class ResNest:
         if train:
             if self.grad_sync is not None:
                 self.grad_sync.backward_and_sync(e)
-                e.adam(self.optimizer.learning_rate, 1.0 / self.grad_sync.world_size)
             else:
                 e.backward()
-                e.adam(self.optimizer.learning_rate, 1.0)
+            e.adam()                                        # hyper-parameters come from the device buffer (set_hyper in _run)
+
+    def _purge_graphs(self):
+        """drop CUDA graphs captured against builds whose buffers the engine has released"""
+        e = self.engine
+        if e.evicted:
+            dead = set(e.evicted)
+            e.evicted.clear()
+            for cache in (self._graphs, self.grad_sync._seg_graphs if self.grad_sync is not None else {}):
+                for k in [k for k in cache if k[0] in dead]:
+                    del cache[k]
+            self._warm = {k for k in self._warm if k[0] not in dead}
 
     def _run(self, train: bool, draw: bool):
-        key = (self.engine.N, train, draw)
+        e = self.engine
+        # the learning rate the caller sees (self.optimizer.learning_rate, TBI_ResNest.py:28) reaches the device before the step,
+        # eager or replayed: a schedule assigned between steps is honoured by a captured graph too
+        world = self.grad_sync.world_size if self.grad_sync is not None else 1
+        scale = 1.0 / world if (self.grad_sync is None or self.grad_sync.average) else 1.0
+        e.set_hyper(self.optimizer.learning_rate, scale)
+        self._purge_graphs()
+        key = (e.gen, train, draw)                           # e.gen: a graph is only valid for the build (buffers) it captured
         if not self.use_cuda_graph:
             self._device_step(train, draw)
             return
@@ -141,20 +185,16 @@ class ResNest:
                 return
         if train and self.grad_sync is not None:
             # data parallel: graph segments + eager NCCL between them (collectives are never captured)
-            e = self.engine
-
             def pre():
                 e.prepare()
                 if draw:
                     e.draw_dropout()
                 e.forward()
 
-            self.grad_sync.step_graphed(e, pre, lambda: e.adam(self.optimizer.learning_rate, 1.0 / self.grad_sync.world_size), key,
-                                        loss_fn=e.loss, before_loss=self._wait_labels)
+            self.grad_sync.step_graphed(e, pre, e.adam, key, loss_fn=e.loss, before_loss=self._wait_labels)
             return
         if g is None:
             # two graphs: [prepare, dropout, forward] | [loss, backward, Adam]; the label copy (side stream) joins between them
-            e = self.engine
             self._wait_labels()
             torch.cuda.synchronize()
             g1 = torch.cuda.CUDAGraph()
@@ -168,7 +208,7 @@ class ResNest:
                 e.loss()
                 if train:
                     e.backward()
-                    e.adam(self.optimizer.learning_rate, 1.0)
+                    e.adam()
             g = self._graphs[key] = (g1, g2)
         g[0].replay()
         self._wait_labels()
@@ -222,17 +262,34 @@ class ResNest:
         return out * (float(h * w) / float(self.height * self.width))
 
     # ------------------------------------------------------------------ persistence (reference :57-78 is broken; this works)
-    def save_params(self):
-        os.makedirs(self.ckpt_dir, exist_ok=True)
+    # Format: a directory of .npz archives whose keys are the Keras variable names of the reference graph
+    # ("Conv1/kernel", "conv2_1_car_k0_att2_r1/bias", "batch_normalization_3/moving_variance", ...) and whose arrays are
+    # in Keras layouts (Conv2D HWIO, Conv2DTranspose HWOI): what `model.get_weights()` / `layer.set_weights()` on the
+    # reference side produce and accept, so weights trained on either stack interchange (INTEGRATION.md has the TF-side loop).
+    def save_params(self, path: Optional[str] = None):
+        path = self.ckpt_dir if path is None else path
+        os.makedirs(path, exist_ok=True)
         e = self.engine
-        torch.save({"variables": {k: v.cpu() for k, v in e.state_dict().items()}, "adam_m": e.adam_m.cpu(), "adam_v": e.adam_v.cpu(),
-                    "step": int(e.step_count.item())}, os.path.join(self.ckpt_dir, "tbi_resnest.pt"))
+        np.savez(os.path.join(path, "variables.npz"), **{k: v.cpu().numpy() for k, v in e.state_dict().items()})
+        opt = {"step": np.asarray(int(e.step_count.item()), dtype=np.int64)}
+        for tag, buf in (("m", e.adam_m), ("v", e.adam_v)):
+            for k, v in e._named(buf, None, trainable_only=True).items():
+                opt[f"{tag}/{k}"] = v.detach().cpu().numpy()
+        np.savez(os.path.join(path, "optimizer.npz"), **opt)
+        return path
 
-    def load_params(self):
+    def load_params(self, path: Optional[str] = None):
+        path = self.ckpt_dir if path is None else path
         e = self.engine
-        ck = torch.load(os.path.join(self.ckpt_dir, "tbi_resnest.pt"), map_location="cpu")
-        e.load_state_dict(ck["variables"])
-        e.adam_m.copy_(ck["adam_m"]); e.adam_v.copy_(ck["adam_v"]); e.step_count.fill_(ck["step"])
+        with np.load(os.path.join(path, "variables.npz")) as z:
+            e.load_state_dict({k: torch.from_numpy(z[k]) for k in z.files})
+        opt_path = os.path.join(path, "optimizer.npz")
+        if os.path.exists(opt_path):
+            with np.load(opt_path) as z:
+                for tag, buf in (("m", e.adam_m), ("v", e.adam_v)):
+                    for k, dst in e._named(buf, None, trainable_only=True).items():
+                        dst.copy_(torch.from_numpy(z[f"{tag}/{k}"]).to(e.device).reshape(dst.shape))
+                e.step_count.fill_(int(z["step"]))
 
     # convenience for tests / interchange
     def state_dict(self):
@@ -240,3 +297,7 @@ class ResNest:
 
     def load_state_dict(self, sd):
         self.engine.load_state_dict(sd)
+
+    def tensor_core_report(self):
+        """which tap-GEMM launches of the last steps left the tcgen05 path (see Engine.fallback_report)"""
+        return self.engine.fallback_report()

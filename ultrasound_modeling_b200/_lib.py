@@ -41,16 +41,55 @@ def is_stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile csrc/*.cu into libtbi_sm100.so for sm_100a (nvcc cross-compiles without a GPU).
-    Rebuilds only when the sources' content hash differs from the one recorded beside the .so."""
+    Rebuilds only when the sources' content hash differs from the one recorded beside the .so.
+    Safe under torchrun: one process builds (exclusive flock), into a temporary file that is renamed over the library, so no
+    rank can dlopen a half-written .so; the others wait on the lock and then find the library fresh."""
+    import fcntl
     if not force and not is_stale():
         return LIB_PATH
-    srcs = [_CSRC / s for s in SOURCES]
-    nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, srcs)]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True, cwd=str(_CSRC))
-    HASH_PATH.write_text(_source_hash() + "\n")
+    with open(str(LIB_PATH) + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():         # another process built it while we waited
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "nvcc")
+            objdir = _PKG / "build"
+            objdir.mkdir(exist_ok=True)
+            hdr = hashlib.sha256()
+            for d in sorted(_CSRC.glob("*.cuh")) + [_PKG.parent / "include" / "tbi_sm100.h"]:
+                hdr.update(d.name.encode()); hdr.update(d.read_bytes())
+            hdr.update(" ".join(NVCC_FLAGS).encode())
+            cflags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+            def compile_one(name):
+                """one translation unit -> object, reused while the file and every header are unchanged"""
+                src, obj = _CSRC / name, objdir / (name + ".o")
+                tag = hashlib.sha256(hdr.digest() + src.read_bytes()).hexdigest()
+                stamp = objdir / (name + ".hash")
+                if obj.exists() and stamp.exists() and stamp.read_text().strip() == tag:
+                    return
+                cmd = [nvcc, *cflags, "-c", "-o", str(obj), str(src)]
+                if verbose:
+                    print(" ".join(cmd), flush=True)
+                subprocess.run(cmd, check=True, cwd=str(_CSRC))
+                stamp.write_text(tag + "\n")
+
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+                list(pool.map(compile_one, SOURCES))
+            tmp = LIB_PATH.with_name(f".{LIB_PATH.name}.{os.getpid()}.tmp")
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(tmp), *[str(objdir / (n + ".o")) for n in SOURCES]]
+            if verbose:
+                print(" ".join(cmd), flush=True)
+            try:
+                subprocess.run(cmd, check=True, cwd=str(_CSRC))
+                os.replace(tmp, LIB_PATH)
+            finally:
+                if tmp.exists():
+                    tmp.unlink()
+            HASH_PATH.write_text(_source_hash() + "\n")
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
@@ -101,6 +140,8 @@ SIGNATURES = {
     "tbi_version": (_I, []),
     "tbi_last_error": (C.c_char_p, []),
     "tbi_device_ok": (_I, []),
+    "tbi_fallback_stats": (_I, [C.POINTER(C.c_int64), C.POINTER(C.c_int64), _I]),
+    "tbi_last_fallback": (C.c_char_p, []),
     "tbi_tapgemm_run": (_I, [C.POINTER(TapGemm), _VP]),
     "tbi_tapwgrad_run": (_I, [C.POINTER(TapWgrad), _VP]),
     "tbi_workspace_bytes": (_I64, [C.POINTER(TapWgrad)]),
@@ -138,6 +179,8 @@ SIGNATURES = {
     "tbi_cast": (_I, [_I, _I, _I64, _VP, _VP, _VP]),
     "tbi_adam_multi": (_I, [_I64, _VP, _VP, _VP, _VP, _VP, _F, _F, _F, _F, _F, _VP]),
     "tbi_adam_advance": (_I, [_VP, _VP]),
+    "tbi_adam_multi_dev": (_I, [_I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _F, _F, _VP]),
+    "tbi_sumsq": (_I, [_I64, _VP, _VP, _VP]),
 }
 
 _lib = None

@@ -703,9 +703,9 @@ __global__ void __launch_bounds__(32 * SL_J) softmax_loss_kernel(int N, int hw, 
 // block-diagonal dense expansion of a grouped kernel (tbi_conv_dense_expand): same two layouts as below for groups = 1 over
 // cin_total = groups*cin_g input channels, zero where input and output channel belong to different groups
 template <typename T>
-__global__ void pack_conv_expand_kernel(int mode, int ntaps, int groups, int cin_g, int cout_total, const float* __restrict__ w,
+__global__ void pack_conv_expand_kernel(int mode, int ntaps, int groups, int cin_g, int cin, int cout_total, const float* __restrict__ w,
                                         const float* __restrict__ scale, T* __restrict__ out) {
-    const int cout_g = cout_total / groups, cin = groups * cin_g;
+    const int cout_g = cout_total / groups;                  // cin = groups*cin_g rounded up to 16: rows past the last group are zero
     const long long total = (long long)ntaps * cin * cout_total;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int tap, ci, co;
@@ -716,7 +716,7 @@ __global__ void pack_conv_expand_kernel(int mode, int ntaps, int groups, int cin
             tap = ntaps - 1 - tp;
         }
         float v = 0.f;
-        if (ci / cin_g == co / cout_g) {
+        if (ci < groups * cin_g && ci / cin_g == co / cout_g) {
             v = w[((size_t)tap * cin_g + ci % cin_g) * cout_total + co];
             if (scale) v *= scale[co];
         }
@@ -725,8 +725,8 @@ __global__ void pack_conv_expand_kernel(int mode, int ntaps, int groups, int cin
 }
 
 // dw_hwio[tap][ci_g][co] += dense[tap][g(co)*cin_g + ci_g][co]   (the block-diagonal part of a dense weight gradient)
-__global__ void wgrad_gather_blocks_kernel(int ntaps, int groups, int cin_g, int cout_total, const float* __restrict__ dense, float* dw) {
-    const int cout_g = cout_total / groups, cin = groups * cin_g;
+__global__ void wgrad_gather_blocks_kernel(int ntaps, int groups, int cin_g, int cin, int cout_total, const float* __restrict__ dense, float* dw) {
+    const int cout_g = cout_total / groups;
     const long long total = (long long)ntaps * cin_g * cout_total;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int co = (int)(i % cout_total); long long t = i / cout_total; const int cig = (int)(t % cin_g); const int tap = (int)(t / cin_g);
@@ -901,6 +901,51 @@ __global__ void adam_kernel(long long count, float* __restrict__ p, const float*
     }
 }
 __global__ void adam_advance_kernel(int32_t* s) { if (threadIdx.x == 0 && blockIdx.x == 0) *s += 1; }
+
+// Adam with its hyper-parameters on the device (hyper = {lr, grad_scale, clip_norm}): a captured CUDA graph keeps following
+// a learning-rate schedule, and the global-norm clip of VisionTransformer.py:244 (tf.clip_by_global_norm) is one more factor
+// on the gradient: g * clip / max(||g||, clip) with ||g|| = sqrt(*gnorm_sq) * grad_scale.
+__global__ void adam_dev_kernel(long long count, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, const int32_t* step_count, const float* __restrict__ hyper,
+                                const float* __restrict__ gnorm_sq, float b1, float b2, float eps) {
+    const float t = (float)(*step_count + 1);
+    const float lr_t = hyper[0] * sqrtf(1.f - powf(b2, t)) / (1.f - powf(b1, t));
+    float gs = hyper[1];
+    const float clip = hyper[2];
+    if (clip > 0.f && gnorm_sq) { const float nrm = sqrtf(*gnorm_sq) * fabsf(gs); gs *= clip / fmaxf(nrm, clip); }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count / 4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pp = reinterpret_cast<float4*>(p)[i], gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+        float* pa = &pp.x; float* ga = &gg.x; float* ma = &mm.x; float* va = &vv.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gk = ga[k] * gs;
+            ma[k] = b1 * ma[k] + (1.f - b1) * gk;
+            va[k] = b2 * va[k] + (1.f - b2) * gk * gk;
+            pa[k] -= lr_t * ma[k] / (sqrtf(va[k]) + eps);
+        }
+        reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    for (long long i = (count / 4) * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) {
+        const float gk = g[i] * gs;
+        const float mk = b1 * m[i] + (1.f - b1) * gk, vk = b2 * v[i] + (1.f - b2) * gk * gk;
+        m[i] = mk; v[i] = vk; p[i] -= lr_t * mk / (sqrtf(vk) + eps);
+    }
+}
+
+// out += sum x^2 (global gradient norm): 16-byte loads, warp shuffles, one atomic per block
+__global__ void __launch_bounds__(256) sumsq_kernel(long long count, const float* __restrict__ x, float* out) {
+    __shared__ float red[32];
+    float l = 0.f;
+    const long long n4 = count / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 q = reinterpret_cast<const float4*>(x)[i];
+        l = fmaf(q.x, q.x, l); l = fmaf(q.y, q.y, l); l = fmaf(q.z, q.z, l); l = fmaf(q.w, q.w, l);
+    }
+    for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x) l = fmaf(x[i], x[i], l);
+    const float tot = block_reduce(l, red, false);
+    if (threadIdx.x == 0) atomicAdd(out, tot);
+}
 
 __global__ void dropout_mask_kernel(uint8_t* keep, long long count, unsigned long long seed, const int32_t* step_ptr) {
     const unsigned long long offset = step_ptr ? (unsigned long long)(*step_ptr) * (unsigned long long)count : 0ull;
@@ -1238,8 +1283,9 @@ extern "C" int tbi_pack_conv_weights(int dtype, int mode, int ksize, int groups,
     cudaStream_t s = (cudaStream_t)stream;
     const int ntaps = ksize * ksize;
     if (tbi_conv_dense_expand(dtype, groups, cin_g, cout_total / groups)) {
-        const unsigned ge = grid_for((long long)ntaps * groups * cin_g * cout_total, 256);
-        pack_conv_expand_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>(mode, ntaps, groups, cin_g, cout_total, w_hwio, scale, (__nv_bfloat16*)out);
+        const int cinp = (groups * cin_g + 15) & ~15;
+        const unsigned ge = grid_for((long long)ntaps * cinp * cout_total, 256);
+        pack_conv_expand_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>(mode, ntaps, groups, cin_g, cinp, cout_total, w_hwio, scale, (__nv_bfloat16*)out);
         TBI_CUDA_LAUNCH_CHECK("pack_conv_expand");
         return TBI_OK;
     }
@@ -1251,8 +1297,8 @@ extern "C" int tbi_pack_conv_weights(int dtype, int mode, int ksize, int groups,
     return TBI_OK;
 }
 
-int tbi_wgrad_gather_blocks(int ntaps, int groups, int cin_g, int cout_total, const float* dense, float* dw, cudaStream_t s) {
-    wgrad_gather_blocks_kernel<<<grid_for((long long)ntaps * cin_g * cout_total, 256), 256, 0, s>>>(ntaps, groups, cin_g, cout_total, dense, dw);
+int tbi_wgrad_gather_blocks(int ntaps, int groups, int cin_g, int cin_pad, int cout_total, const float* dense, float* dw, cudaStream_t s) {
+    wgrad_gather_blocks_kernel<<<grid_for((long long)ntaps * cin_g * cout_total, 256), 256, 0, s>>>(ntaps, groups, cin_g, cin_pad, cout_total, dense, dw);
     TBI_CUDA_LAUNCH_CHECK("wgrad_gather_blocks");
     return TBI_OK;
 }
@@ -1310,6 +1356,23 @@ extern "C" int tbi_adam_multi(int64_t count, float* p, const float* g, float* m,
     const unsigned gsz = grid_for(count / 4 + 1, 256, 8);
     adam_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>(count, p, g, m, v, step_count, lr, b1, b2, eps, grad_scale);
     TBI_CUDA_LAUNCH_CHECK("adam");
+    return TBI_OK;
+}
+extern "C" int tbi_adam_multi_dev(int64_t count, float* p, const float* g, float* m, float* v, const int32_t* step_count,
+                                  const float* hyper, const float* gnorm_sq, float b1, float b2, float eps, void* stream) {
+    TBI_CHECK((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0, TBI_ERR_BAD_ALIGN, "adam: 16B alignment");
+    TBI_CHECK(hyper != nullptr, TBI_ERR_BAD_SHAPE, "adam_dev: hyper is NULL");
+    const unsigned gsz = grid_for(count / 4 + 1, 256, 8);
+    adam_dev_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>(count, p, g, m, v, step_count, hyper, gnorm_sq, b1, b2, eps);
+    TBI_CUDA_LAUNCH_CHECK("adam_dev");
+    return TBI_OK;
+}
+extern "C" int tbi_sumsq(int64_t count, const float* x, float* out, void* stream) {
+    TBI_CHECK(((uintptr_t)x & 15) == 0, TBI_ERR_BAD_ALIGN, "sumsq: 16B alignment");
+    unsigned gsz = grid_for(count / 4 + 1, 256, 8);
+    if (gsz > 1184) gsz = 1184;
+    sumsq_kernel<<<gsz, 256, 0, (cudaStream_t)stream>>>(count, x, out);
+    TBI_CUDA_LAUNCH_CHECK("sumsq");
     return TBI_OK;
 }
 extern "C" int tbi_adam_advance(int32_t* step_count, void* stream) {

@@ -31,6 +31,25 @@ extern "C" int tbi_device_ok(void) {
     return p.major == 10 ? 1 : 0;
 }
 
+// Which bf16 launches under TBI_IMPL_AUTO left the tensor cores for the CUDA-core tap-GEMM, and why (the last reason): a user
+// can see that a layer shape fell off the tcgen05 path instead of silently running ~50x slower (tbi_fallback_stats).
+#include <atomic>
+static std::atomic<long long> g_fallback_gemm{0}, g_fallback_wgrad{0};
+static char g_fallback_why[256] = "";
+static std::mutex g_fallback_mu;
+static void note_fallback(std::atomic<long long>& ctr, const char* kind, const char* why, int cin_g, int cout_g, int groups) {
+    ctr.fetch_add(1, std::memory_order_relaxed);
+    std::lock_guard<std::mutex> lk(g_fallback_mu);
+    snprintf(g_fallback_why, sizeof(g_fallback_why), "%s (groups %d, cin/group %d, cout/group %d): %s", kind, groups, cin_g, cout_g, why);
+}
+extern "C" int tbi_fallback_stats(int64_t* tapgemm_simt, int64_t* tapwgrad_simt, int reset) {
+    if (tapgemm_simt) *tapgemm_simt = g_fallback_gemm.load();
+    if (tapwgrad_simt) *tapwgrad_simt = g_fallback_wgrad.load();
+    if (reset) { g_fallback_gemm = 0; g_fallback_wgrad = 0; std::lock_guard<std::mutex> lk(g_fallback_mu); g_fallback_why[0] = 0; }
+    return TBI_OK;
+}
+extern "C" const char* tbi_last_fallback(void) { return g_fallback_why; }
+
 extern "C" int tbi_tapgemm_run(const tbi_tapgemm* d, void* stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (d->impl == TBI_IMPL_SIMT) return tbi_tapgemm_simt(d, s);
@@ -42,6 +61,7 @@ extern "C" int tbi_tapgemm_run(const tbi_tapgemm* d, void* stream) {
     }
     if (ok) return tbi_tapgemm_tc(d, s);
     if (tbi_tapgemm_direct_supported(d)) return tbi_tapgemm_direct(d, s);
+    if (d->dtype == TBI_BF16) note_fallback(g_fallback_gemm, "tap-GEMM", why, d->cin_g, d->cout_g, d->groups);
     return tbi_tapgemm_simt(d, s);
 }
 
@@ -56,6 +76,7 @@ extern "C" int tbi_tapwgrad_run(const tbi_tapwgrad* d, void* stream) {
     }
     if (ok) return tbi_tapwgrad_tc(d, s);
     if (tbi_tapwgrad_direct_supported(d)) return tbi_tapwgrad_direct(d, s);
+    if (d->dtype == TBI_BF16) note_fallback(g_fallback_wgrad, "weight-gradient tap-GEMM", why, d->cin_g, d->cout_g, d->groups);
     return tbi_tapwgrad_simt(d, s);
 }
 
@@ -76,21 +97,31 @@ static int fill_conv_taps(int ksize, int dilation, int* dy, int* dx) {
 }
 
 // see include/tbi_sm100.h.  Expanded when the grouped form cannot use the tensor cores in some direction (K per group not a
-// multiple of 16) while the dense form can, and the dense layer stays small.
+// multiple of 16) while the dense form can, and the dense layer stays small.  The dense form reads pad16(cin) input channels:
+// a total input width that is not a multiple of 16 (radix 3: 12 groups x 5 channels = 60) needs pixel records padded with
+// zeros up to the next multiple of 16 (the engine stores such tensors that way); the pad rows of the pack are zero.
+static inline int pad16(int c) { return (c + 15) & ~15; }
 extern "C" int tbi_conv_dense_expand(int dtype, int groups, int cin_g, int cout_g) {
     static const bool off = getenv("TBI_NO_DENSE_EXPAND") != nullptr;
     if (off || dtype != TBI_BF16 || groups <= 1) return 0;
     if (cin_g % 16 == 0 && cout_g % 16 == 0) return 0;                       // grouped form is tensor-core eligible both ways
     const int cin = groups * cin_g, cout = groups * cout_g;
-    return (cin % 16 == 0 && cout % 16 == 0 && cin <= 256 && cout <= 1024) ? 1 : 0;
+    return (cout % 16 == 0 && pad16(cin) <= 256 && cout <= 1024) ? 1 : 0;
 }
 extern "C" int64_t tbi_conv_packed_elems(int dtype, int ksize, int groups, int cin_g, int cout_total) {
     const int64_t grouped = (int64_t)ksize * ksize * cin_g * cout_total;
-    return tbi_conv_dense_expand(dtype, groups, cin_g, cout_total / (groups > 0 ? groups : 1)) ? grouped * groups : grouped;
+    return tbi_conv_dense_expand(dtype, groups, cin_g, cout_total / (groups > 0 ? groups : 1)) ? (int64_t)ksize * ksize * pad16(groups * cin_g) * cout_total : grouped;
 }
 extern "C" int64_t tbi_conv2d_wgrad_workspace(int dtype, int ksize, int groups, int cin_total, int cout_total) {
     if (groups <= 1 || !tbi_conv_dense_expand(dtype, groups, cin_total / groups, cout_total / groups)) return 0;
-    return (int64_t)ksize * ksize * cin_total * cout_total * (int64_t)sizeof(float);
+    return (int64_t)ksize * ksize * pad16(cin_total) * cout_total * (int64_t)sizeof(float);
+}
+// the expanded form addresses pad16(c) channels of a view that names c of them: the record must have the room
+static int widen_view(tbi_view* v, int cpad, const char* what) {
+    TBI_CHECK(v->cstride - v->coff >= cpad, TBI_ERR_BAD_SHAPE, "%s: block-diagonal expansion addresses %d channels, the pixel record has room for %d "
+              "(store the tensor with zero-padded records)", what, cpad, v->cstride - v->coff);
+    v->c = cpad;
+    return TBI_OK;
 }
 
 static int check_conv_args(int ksize, int dilation) {
@@ -110,7 +141,10 @@ extern "C" int tbi_conv2d_fwd(int dtype, int impl, int n, int h, int w, int ksiz
     const int cin = src0->c + ((src1 && src1->ptr) ? src1->c : 0);
     TBI_CHECK(cin % groups == 0, TBI_ERR_BAD_SHAPE, "conv2d_fwd: cin %d %% groups %d", cin, groups);
     d.cin_g = cin / groups; d.cout_g = cout_total / groups;
-    if (tbi_conv_dense_expand(dtype, groups, d.cin_g, d.cout_g)) { d.groups = 1; d.cin_g = cin; d.cout_g = cout_total; }   // block-diagonal pack
+    if (tbi_conv_dense_expand(dtype, groups, d.cin_g, d.cout_g)) {           // block-diagonal pack over pad16(cin) input channels
+        d.groups = 1; d.cin_g = pad16(cin); d.cout_g = cout_total;
+        rc = widen_view(&d.src[0], d.cin_g, "conv2d_fwd input"); if (rc) return rc;
+    }
     d.in_stride = 1; d.ntaps = fill_conv_taps(ksize, dilation, d.dy, d.dx);
     d.w = w_packed; d.epi = *epi;
     if (d.epi.out_stride == 0) d.epi.out_stride = 1;
@@ -127,9 +161,14 @@ extern "C" int tbi_conv2d_dgrad(int dtype, int impl, int n, int h, int w, int ks
     d.src[0] = *dz;
     d.cin_g = dz->c / groups;            // K side = forward output channels
     d.cout_g = cin_total / groups;       // produced = forward input channels
-    if (tbi_conv_dense_expand(dtype, groups, d.cout_g, d.cin_g)) { d.groups = 1; d.cin_g = dz->c; d.cout_g = cin_total; }
     d.in_stride = 1; d.ntaps = fill_conv_taps(ksize, dilation, d.dy, d.dx);
     d.w = w_packed_dgrad; d.epi = *epi;
+    if (tbi_conv_dense_expand(dtype, groups, d.cout_g, d.cin_g)) {           // writes pad16(cin_total) channels; the pad lanes come out 0
+        d.groups = 1; d.cin_g = dz->c; d.cout_g = pad16(cin_total);
+        rc = widen_view(&d.epi.out, d.cout_g, "conv2d_dgrad output"); if (rc) return rc;
+        if (d.epi.dact != TBI_ACT_NONE) { rc = widen_view(&d.epi.dact_ref, d.cout_g, "conv2d_dgrad act' reference"); if (rc) return rc; }
+        if (d.epi.residual.ptr) { rc = widen_view(&d.epi.residual, d.cout_g, "conv2d_dgrad residual"); if (rc) return rc; }
+    }
     if (d.epi.out_stride == 0) d.epi.out_stride = 1;
     return tbi_tapgemm_run(&d, stream);
 }
@@ -156,11 +195,13 @@ extern "C" int tbi_conv2d_wgrad(int dtype, int impl, int n, int h, int w, int ks
         cudaStream_t s = (cudaStream_t)stream;
         if (cudaMemsetAsync(workspace, 0, (size_t)need, s) != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "conv2d_wgrad: memset");
         tbi_tapwgrad e = d;
-        e.groups = 1; e.cin_g = cin; e.cout_g = dz->c;
-        e.dw = (float*)workspace; e.tap_stride = (int64_t)cin * dz->c; e.ci_stride = dz->c; e.co_stride = 1;
+        const int cinp = pad16(cin);
+        e.groups = 1; e.cin_g = cinp; e.cout_g = dz->c;
+        rc = widen_view(&e.a_src[0], cinp, "conv2d_wgrad input"); if (rc) return rc;
+        e.dw = (float*)workspace; e.tap_stride = (int64_t)cinp * dz->c; e.ci_stride = dz->c; e.co_stride = 1;
         e.workspace = nullptr; e.workspace_bytes = 0;
         rc = tbi_tapwgrad_run(&e, stream); if (rc) return rc;
-        return tbi_wgrad_gather_blocks(d.ntaps, groups, d.cin_g, dz->c, (const float*)workspace, dw_hwio, s);
+        return tbi_wgrad_gather_blocks(d.ntaps, groups, d.cin_g, cinp, dz->c, (const float*)workspace, dw_hwio, s);
     }
     return tbi_tapwgrad_run(&d, stream);
 }

@@ -15,7 +15,7 @@ int  tbi_set_error(int code, const char* fmt, ...);
 
 static inline int tbi_dtype_size(int dtype) { return dtype == TBI_F32 ? 4 : 2; }
 int tbi_sm_count();
-int tbi_wgrad_gather_blocks(int ntaps, int groups, int cin_g, int cout_total, const float* dense, float* dw, cudaStream_t s);
+int tbi_wgrad_gather_blocks(int ntaps, int groups, int cin_g, int cin_pad, int cout_total, const float* dense, float* dw, cudaStream_t s);
 
 // ---- storage type <-> float -----------------------------------------------------------------
 template <typename T> __device__ __forceinline__ float ldf(const T* p);

@@ -127,6 +127,8 @@ class Engine:
         self._side_bwd = None
         self._side = None
         self._prep_pending = False
+        self.gen = 0
+        self.evicted: List[int] = []       # generations of builds whose buffers were released (graph caches purge these)
         self._define_layers()
         if not layout_only:
             self._alloc_params(seed)
@@ -167,7 +169,13 @@ class Engine:
                     nc = f"{stage}_car_k{k}"
                     k1.append((f"{nc}1_r{r}", g * cv11, (g + 1) * cv11)); k1bn.append((f"{nc}1_{r}bn", g * cv11, (g + 1) * cv11))
                     k2.append((f"{nc}2_r{r}", g * cvkk, (g + 1) * cvkk)); k2bn.append((f"{nc}2_{r}bn", g * cvkk, (g + 1) * cvkk))
-            c1 = add(ConvLayer(f"{stage}/c1", "conv", 1, cin, G * cv11, bn=True, act=ACT_ELU, keras=k1, keras_bn=k1bn))
+            # The fused 1x1 conv produces G*cv11 channels; when that is not a multiple of 16 (radix 3: 24/60/120/252) the layer is
+            # declared with its output width padded up to one: pad kernels/bias are zero and no Keras variable maps onto them
+            # (their gradients are exactly zero, so Adam never moves them), the stored tensor T1 then has 16-byte aligned,
+            # MMA-K-sized pixel records with zero pad lanes, and the grouped 3x3 conv behind it runs as a block-diagonal dense
+            # tcgen05 conv over the padded width (tbi_conv_dense_expand) instead of on CUDA cores.
+            c1w = (G * cv11 + 15) // 16 * 16
+            c1 = add(ConvLayer(f"{stage}/c1", "conv", 1, cin, c1w, bn=True, act=ACT_ELU, keras=k1, keras_bn=k1bn))
             c2 = add(ConvLayer(f"{stage}/c2", "conv", ks, G * cv11, G * cvkk, groups=G, bn=True, act=ACT_ELU, keras=k2, keras_bn=k2bn))
             c = cvkk
             att = dict(stage=stage, c=c, name=f"{stage}/att")
@@ -182,7 +190,7 @@ class Engine:
             if cin != out:
                 sc = add(ConvLayer(f"{stage}/sc", "conv", 1, cin, out, bn=True, act=ACT_ELU, keras=[(f"{stage}_cc", 0, out)],
                                    keras_bn=[(f"{stage}_scbn", 0, out)]))
-            self.stage_info.append(dict(stage=stage, cin=cin, out=out, cv11=cv11, cvkk=cvkk, G=G, c1=c1, c2=c2, att=att, cc2=cc2, sc=sc))
+            self.stage_info.append(dict(stage=stage, cin=cin, out=out, cv11=cv11, cvkk=cvkk, G=G, c1w=c1w, c1=c1, c2=c2, att=att, cc2=cc2, sc=sc))
             cin = out
         cin = SKIP_C[5]
         self.ups = []
@@ -202,6 +210,11 @@ class Engine:
         self.adam_v = self.P.alloc(dev)
         self.stats = self.S.alloc(dev)
         self.step_count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.draw_count = torch.zeros(1, dtype=torch.int32, device=dev)     # advances on every dropout draw (train or eval)
+        self.hyper = torch.tensor([1e-3, 1.0, 0.0], dtype=torch.float32, device=dev)     # lr, grad_scale, clip_norm
+        self._hyper_host = (1e-3, 1.0, 0.0)
+        self.gnorm_sq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.dropout_seed = 0x5EED
         # Keras defaults: glorot_uniform kernels, zero bias, BN gamma=1 beta=0 mean=0 var=1
         g = torch.Generator().manual_seed(seed)
         host = torch.zeros(self.params.numel(), dtype=torch.float32)
@@ -271,9 +284,11 @@ class Engine:
                     yield f"{an}2_r{r}/kernel", "P", nm + "/w2", (k, r, None, None)
                     yield f"{an}2_r{r}/bias", "P", nm + "/b2", (k, r)
 
-    def _named(self, pbuf, sbuf):
+    def _named(self, pbuf, sbuf, trainable_only=False):
         out = OrderedDict()
         for kn, store, flat, idx in self._keras_items():
+            if store != "P" and (trainable_only or sbuf is None):
+                continue
             t = self.P.get(pbuf, flat) if store == "P" else self.S.get(sbuf, flat)
             out[kn] = t[idx]
         return out
@@ -298,10 +313,37 @@ class Engine:
                            if not (k.endswith("/moving_mean") or k.endswith("/moving_variance")))
 
     # ------------------------------------------------------------------ buffers + programs
+    MAX_CACHED_BUILDS = 3
+
     def build(self, n: int):
-        """allocate activations for batch n and assemble the static call programs"""
+        """allocate activations for batch n and assemble the static call programs.
+
+        A build owns every activation/input buffer and the ctypes programs that point into them, so anything captured
+        against it (CUDA graphs) is only valid for THAT build: `self.gen` identifies the live build and callers key their
+        graph caches on it.  The reference loop alternates batch sizes (train 64 / test 1, TBI_ResNest.py:395,421), so the
+        last few builds are kept (buffers stay allocated, their graphs stay valid) and switching back is free; an evicted
+        build's generation is reported through `self.evicted` so graph caches can drop what pointed into it."""
         if n == self.N:
             return
+        cache = self.__dict__.setdefault("_builds", OrderedDict())
+        if self.N:
+            cache[self.N] = {k: self.__dict__[k] for k in self._build_keys}
+            cache.move_to_end(self.N)
+        if n in cache:
+            self.__dict__.update(cache.pop(n))
+            return
+        while len(cache) >= self.MAX_CACHED_BUILDS:
+            _, old = cache.popitem(last=False)
+            self.evicted.append(old["gen"])
+        first = "_build_keys" not in self.__dict__
+        before = set(self.__dict__)
+        self._gen_counter = self.__dict__.get("_gen_counter", 0) + 1
+        self.gen = self._gen_counter
+        self._build_fresh(n)
+        if first:                          # the attribute names a build owns (the same for every batch size)
+            self._build_keys = (set(self.__dict__) - before - {"_gen_counter", "_build_keys"}) | {"N", "gen"}
+
+    def _build_fresh(self, n: int):
         self.N = n
         dev, td = self.device, self.tdtype
         H, W = self.H, self.W
@@ -317,8 +359,10 @@ class Engine:
         for si, info in enumerate(self.stage_info):
             h, w = H >> (si + 1), W >> (si + 1)
             G, cv11, cvkk, out, K, R = info["G"], info["cv11"], info["cvkk"], info["out"], self.kpaths, self.radix
-            b = dict(T1=E(n, h, w, G * cv11), U=E(n, h, w, G * cvkk), V=E(n, h, w, K * cvkk), Y=E(n, h, w, out),
-                     dZ1=E(n, h, w, G * cv11), dZ2=E(n, h, w, G * cvkk), dV=E(n, h, w, K * cvkk), dY=E(n, h, w, out),
+            c1w = info["c1w"]
+            Z = lambda *shape: torch.zeros(shape, dtype=td, device=dev)      # pad lanes a kernel may not write must read as 0
+            b = dict(T1=(Z if c1w != G * cv11 else E)(n, h, w, c1w), U=E(n, h, w, G * cvkk), V=E(n, h, w, K * cvkk), Y=E(n, h, w, out),
+                     dZ1=(Z if c1w != G * cv11 else E)(n, h, w, c1w), dZ2=E(n, h, w, G * cvkk), dV=E(n, h, w, K * cvkk), dY=E(n, h, w, out),
                      gap=torch.empty(n, K, cvkk, dtype=torch.float32, device=dev),
                      h1=torch.empty(n, K, cvkk // 2, dtype=torch.float32, device=dev),
                      att=torch.empty(n, K, R, cvkk, dtype=torch.float32, device=dev))
@@ -505,7 +549,7 @@ class Engine:
             b = self.stage_buf[si]
             pin = self.pool[si]
             conv_fwd(info["c1"], h, w, view(pin), None, epi(out=view(b["T1"])))
-            conv_fwd(info["c2"], h, w, view(b["T1"]), None, epi(out=view(b["U"])))
+            conv_fwd(info["c2"], h, w, view(b["T1"], c=info["G"] * info["cv11"]), None, epi(out=view(b["U"])))
             nm = info["att"]["name"]
             sa = keep(SplitAtt(dt, n, h, w, self.kpaths, self.radix, info["cvkk"], ACT_ELU, BN_EPS,
                                _ptr(self.p(nm + "/w1")), _ptr(self.p(nm + "/b1")), _ptr(self.p(nm + "/gamma")), _ptr(self.p(nm + "/beta")),
@@ -591,16 +635,14 @@ class Engine:
                                                               _ptr(self.g(nm + "/beta")), _ptr(self.g(nm + "/w2")), _ptr(self.g(nm + "/b2")),
                                                               _ptr(self.att_scratch))))
             mark(nm)
-            conv_bwd(info["c2"], h, w, view(b["T1"]), None, view(b["dZ2"]),
-                     epi(out=view(b["dZ1"]), dact=ACT_ELU, dact_ref=view(b["T1"])))
+            creal = info["G"] * info["cv11"]
+            conv_bwd(info["c2"], h, w, view(b["T1"], c=creal), None, view(b["dZ2"]),
+                     epi(out=view(b["dZ1"], c=creal), dact=ACT_ELU, dact_ref=view(b["T1"], c=creal)))
             conv_bwd(info["c1"], h, w, view(pin), None, view(b["dZ1"]), epi(out=view(dpin), residual=view(dpin)))
         self.prog_bwd.append((L.tbi_avgpool2x2_bwd, (dt, n, H, W, bref(view(self.dpool[0])), bref(view(self.dstem[2])), 0, ACT_ELU, bref(view(self.t[2])))))
         conv_bwd(cv["conv2_1_2"], H, W, view(self.t[1]), None, view(self.dstem[2]), epi(out=view(self.dstem[1]), dact=ACT_ELU, dact_ref=view(self.t[1])))
         conv_bwd(cv["conv2_1_1"], H, W, view(self.t[0]), None, view(self.dstem[1]), epi(out=view(self.dstem[0]), dact=ACT_ELU, dact_ref=view(self.t[0])))
         conv_bwd(cv["Conv1"], H, W, view(self.x0), None, view(self.dstem[0]), None)
-        # tcgen05 wgrad workspace (split-K partials), sized for the largest layer
-        for (Lr, wargs, *_rest) in wgrads:
-            pass
         self.ws = None
         self._wgrads = wgrads
 
@@ -632,11 +674,16 @@ class Engine:
             torch.cuda.current_stream(self.device).wait_stream(self._side)
             self._prep_pending = False
 
-    def draw_dropout(self, seed: int = 0x5EED):
+    def draw_dropout(self, seed: Optional[int] = None):
+        """fresh keep-masks for upsample_0..2.  tf.nn.dropout draws on EVERY call, eval included (TBI_ResNest.py:215-216), so
+        the stream position is a dedicated device counter that advances per draw (not the Adam step, which only moves when
+        training); `dropout_seed` is mixed with the data-parallel rank by GradSync so replicas draw independent masks."""
+        seed = self.dropout_seed if seed is None else seed
         st = self.stream()
         for i, k in enumerate(self.keep):
             if k is not None:
-                check(self.L.tbi_dropout_mask(k.data_ptr(), k.numel(), seed + 7919 * i, self.step_count.data_ptr(), st), "dropout_mask")
+                check(self.L.tbi_dropout_mask(k.data_ptr(), k.numel(), seed + 7919 * i, self.draw_count.data_ptr(), st), "dropout_mask")
+        check(self.L.tbi_adam_advance(self.draw_count.data_ptr(), st), "draw_advance")
 
     def set_dropout(self, masks: Optional[Sequence[Optional[torch.Tensor]]]):
         """explicit 0/1 keep-masks (parity runs); None -> dropout disabled.  The device buffers hold the
@@ -692,11 +739,39 @@ class Engine:
         self.grads.zero_()
         self.run_bwd(0, len(self.prog_bwd))
 
-    def adam(self, lr: float, grad_scale: float = 1.0):
+    def set_hyper(self, lr: float, grad_scale: float = 1.0, clip_norm: float = 0.0):
+        """learning rate / gradient scale / global-norm clip live in a 3-float device buffer that the (possibly captured) Adam
+        launch reads, so changing `.learning_rate` between steps reaches a replayed CUDA graph.  Call OUTSIDE graph capture."""
+        want = (float(lr), float(grad_scale), float(clip_norm))
+        if want != self._hyper_host:
+            self.hyper.copy_(torch.tensor(want, dtype=torch.float32), non_blocking=False)
+            self._hyper_host = want
+
+    def adam(self, lr: Optional[float] = None, grad_scale: float = 1.0):
+        """one Keras-Adam update of the flat parameter buffer from the flat gradient buffer.  lr given: eager convenience form
+        (uploads the hyper-parameters first); lr None: uses whatever set_hyper() last uploaded (the graph-capturable form)."""
+        if lr is not None:
+            self.set_hyper(lr, grad_scale, self._hyper_host[2])
         st = self.stream()
-        check(self.L.tbi_adam_multi(self.P.total, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
-                                    self.adam_v.data_ptr(), self.step_count.data_ptr(), lr, 0.9, 0.999, 1e-7, grad_scale, st), "adam")
+        gn = None
+        if self._hyper_host[2] > 0.0:
+            self.gnorm_sq.zero_()
+            check(self.L.tbi_sumsq(self.P.total, self.grads.data_ptr(), self.gnorm_sq.data_ptr(), st), "sumsq")
+            gn = self.gnorm_sq.data_ptr()
+        check(self.L.tbi_adam_multi_dev(self.P.total, self.params.data_ptr(), self.grads.data_ptr(), self.adam_m.data_ptr(),
+                                        self.adam_v.data_ptr(), self.step_count.data_ptr(), self.hyper.data_ptr(), gn,
+                                        0.9, 0.999, 1e-7, st), "adam")
         check(self.L.tbi_adam_advance(self.step_count.data_ptr(), st), "adam_advance")
+
+    def fallback_report(self, reset: bool = False) -> dict:
+        """tap-GEMM launches (bf16, automatic dispatch) that ran on CUDA cores because the tcgen05 path refused their shape,
+        cumulative for this process, with the reason of the last one (tbi_fallback_stats / tbi_last_fallback)."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        check(self.L.tbi_fallback_stats(C.byref(a), C.byref(b), 0), "fallback_stats")
+        why = self.L.tbi_last_fallback().decode(errors="replace")
+        if reset:
+            check(self.L.tbi_fallback_stats(None, None, 1), "fallback_stats")
+        return dict(tapgemm_simt=int(a.value), tapwgrad_simt=int(b.value), last_reason=why)
 
     def launches_per_step(self, train: bool = True) -> int:
         """kernel launches of one step as the tensor-core build issues them (checked against the ncu launch list in

@@ -34,7 +34,12 @@ def plan_buckets(marks: Sequence[Tuple[int, int]], total: int, bucket_elems: int
 
 
 class GradSync:
-    def __init__(self, process_group=None, bucket_bytes: Optional[int] = None):
+    """average=True (default): Adam sees the MEAN of the per-replica gradients, which is what the reference's data-parallel
+    driver computes -- each replica's loss is divided by the global batch (compute_average_loss, VisionTransformer.py:225-227)
+    and MirroredStrategy SUMS the replica gradients in apply_gradients (MainParallel.py:130).  average=False applies the raw
+    SUM (what MirroredStrategy would do to TBI_ResNest.step's un-normalised [H,W] loss)."""
+
+    def __init__(self, process_group=None, bucket_bytes: Optional[int] = None, average: bool = True):
         if bucket_bytes is None:                             # TBI_BUCKET_MB: sweep knob for bench runs
             # 54 MB = two buckets for the ~108 MB of fp32 gradients: every bucket boundary also joins the weight-gradient side
             # stream of the backward (engine.run_bwd), so fewer, larger buckets keep more of that overlap
@@ -44,11 +49,21 @@ class GradSync:
             raise RuntimeError("GradSync needs torch.distributed to be initialised (backend nccl on GPUs)")
         self.pg = process_group
         self.world_size = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.average = average
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.comm_stream: Optional[torch.cuda.Stream] = None
         self._plan = None
         self._plan_key = None
         self._seg_graphs = {}
+
+    def attach(self, engine):
+        """replicated variables start identical on every replica (MirroredStrategy mirrors the creating replica's values): rank 0's
+        parameters, moving statistics and Adam state are broadcast; every replica then draws its own dropout masks (independent
+        noise per shard, as independent tf.nn.dropout calls per replica give)."""
+        for t in (engine.params, engine.stats, engine.adam_m, engine.adam_v, engine.step_count):
+            dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
+        engine.dropout_seed = 0x5EED + 1000003 * self.rank
 
     def allreduce(self, flat_slice: torch.Tensor):
         dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.pg)
@@ -130,7 +145,7 @@ class GradSync:
         graphs["post"].replay()
 
     def _ensure_plan(self, engine):
-        key = (id(engine), engine.N)
+        key = (id(engine), engine.gen)
         if self._plan_key != key:
             self._plan = plan_buckets(engine.bwd_marks, engine.P.total, self.bucket_elems)
             self._plan_key = key
