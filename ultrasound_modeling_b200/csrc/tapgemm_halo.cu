@@ -46,6 +46,7 @@ struct alignas(64) HaloParams {
     int sh_x, sh_y;                // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1 (divide)
     int flat;                      // resident + one halo per chunk + (ntaps, ksteps) has an unrolled issue loop
     int rank4;                     // stride-1 sources: 4-D tensor map (C, W, H, N) instead of the 5-D parity view
+    int pair, m_pairs;             // PAIR mode (cta_group::2): iterations are (slab, pair of M tiles); m_pairs = ceil(m_tiles / 2)
     unsigned long long* trace;     // debug timeline buffer or nullptr (a kernel parameter: testing it costs no memory access)
     tbi_epilogue epi;
 };
@@ -144,7 +145,81 @@ __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, cons
     }
 }
 
-template <int BN, int ACT, int DACT>
+// Streamed weights (one B stage per (chunk, tap)) with the tap count and the K steps per stage known at compile time: tap row
+// offsets and group boundaries sit in registers, the K steps of a stage are back-to-back MMAs with immediate address
+// increments (the generic loop below spends ~30 dependent instructions per MMA: table decode + loop-carried address
+// arithmetic; this one took upsample_4 forward from 322 to 304 us, upsample_2 from 215 to 194 us).
+// PAIR: the MMAs are cta_group::2 instructions (M = 256: this CTA's pixel tile and the peer's; each CTA supplies its halo and
+// half of the weight stage), issued by the leader CTA only; commits are multicast so both CTAs' producers and epilogues see
+// them, and the accumulator-free barrier collects the epilogue warps of both CTAs.
+template <int BN, bool PAIR, int NTAPS, int KSTEPS>
+__device__ __forceinline__ void streamed_mma_loop(const HaloParams& p, const Rings& R, uint32_t tmem_base, bool leader, uint32_t idesc,
+                                                  uint32_t a_base, uint32_t a_stage_lo, uint32_t a_hi, uint32_t b_base, uint32_t b_stage_lo,
+                                                  uint32_t b_hi, uint32_t row_lo) {
+    uint32_t toff[NTAPS];
+    uint32_t first_mask = 0, last_mask = 0;
+    int cur_ph = -1;
+    uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0, acc_it = 0;
+    for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+        const int ph = (p.nphase > 1 ? decode_tile(p, PAIR ? i % p.nslabs : i, BN).ph : 0);
+        if (ph != cur_ph) {
+            first_mask = last_mask = 0;
+#pragma unroll
+            for (int t = 0; t < NTAPS; ++t) {
+                toff[t] = ((uint32_t)p.t_row[ph][t] & 0x3FFu) * row_lo;
+                const int g = p.t_grp[ph][t];
+                if (t == 0 || p.t_grp[ph][t - 1] != g) first_mask |= 1u << t;
+                if (t + 1 == NTAPS || p.t_grp[ph][t + 1] != g) last_mask |= 1u << t;
+            }
+            cur_ph = ph;
+        }
+        const uint32_t buf = acc_it & 1u;
+        trace(p.trace, 1, acc_it, 0);
+        if (PAIR) { if (!tc::mbar_try_wait_cluster(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u)) { const long long t0 = clock64(); while (!tc::mbar_try_wait_cluster(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u)) { if (clock64() - t0 > 6000000000LL) { printf("tbi tcgen05 (pair): accumulator barrier timeout (block %d)\n", blockIdx.x); __trap(); } } } }
+        else tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+        tc::tc_fence_after();
+        trace(p.trace, 1, acc_it, 1);
+        const uint32_t tmem_d = tmem_base + buf * BN;
+        uint32_t a_lo = 0;
+        long long wait_a = 0, wait_b = 0, tw = 0;          // debug timeline only (p.trace): cycles this tile spent waiting for operands
+#pragma unroll 1
+        for (int c = 0; c < p.nchunks; ++c) {
+#pragma unroll
+            for (int t = 0; t < NTAPS; ++t) {
+                if ((first_mask >> t) & 1u) {
+                    if (p.trace) tw = clock64();
+                    tc::mbar_wait_bounded(&R.a_full[sa], a_par);
+                    if (p.trace) wait_a += clock64() - tw;
+                    trace(p.trace, 1, acc_it, 2);
+                    a_lo = a_base + sa * a_stage_lo;
+                }
+                if (p.trace) tw = clock64();
+                tc::mbar_wait_bounded(&R.b_full[sb], b_par);
+                if (p.trace) wait_b += clock64() - tw;
+                tc::tc_fence_after();
+                const uint32_t al = a_lo + toff[t], bl = b_base + sb * b_stage_lo;
+                if (leader) {
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                        if (PAIR) tc::umma_bf16_lh_pair(tmem_d, al + 2 * k, a_hi, bl + 2 * k, b_hi, idesc, (t | k) ? 1u : (c > 0 ? 1u : 0u));
+                        else      tc::umma_bf16_lh(tmem_d, al + 2 * k, a_hi, bl + 2 * k, b_hi, idesc, (t | k) ? 1u : (c > 0 ? 1u : 0u));
+                    }
+                    if (PAIR) tc::umma_commit_pair(&R.b_empty[sb]); else tc::umma_commit(&R.b_empty[sb]);
+                }
+                if (++sb == (uint32_t)p.b_stages) { sb = 0; b_par ^= 1u; }
+                if ((last_mask >> t) & 1u) {
+                    if (leader) { if (PAIR) tc::umma_commit_pair(&R.a_empty[sa]); else tc::umma_commit(&R.a_empty[sa]); }
+                    if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+                }
+            }
+        }
+        if (leader) { if (PAIR) tc::umma_commit_pair(&R.t_full[buf]); else tc::umma_commit(&R.t_full[buf]); }
+        trace(p.trace, 1, acc_it, 3);
+        if (p.trace && blockIdx.x == 0 && acc_it < 64) { p.trace[(64 + acc_it) * 8 + 4] = (unsigned long long)wait_a; p.trace[(64 + acc_it) * 8 + 5] = (unsigned long long)wait_b; }
+    }
+}
+
+template <int BN, bool PAIR, int ACT, int DACT>
 __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, const float* sbias, uint32_t tmem_base, int warp, int lane) {
     // Two groups of four warps (one warp per TMEM lane quadrant).  Group g owns accumulator buffer g, i.e. every
     // second tile, so the epilogues of consecutive tiles overlap (the per-tile chain wait -> tcgen05.ld -> loads ->
@@ -159,13 +234,24 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     TileCoord slab_t{};
     if (p.resident) slab_t = decode_tile(p, R.slab, BN);
     unsigned long long* tr = (warp == 0 && lane == 0) ? p.trace : nullptr;
+    const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
+    // PAIR: the accumulator-free barrier the MMA thread waits on lives in the leader CTA
+    uint32_t te_addr[2] = {0u, 0u};
+    if (PAIR) { te_addr[0] = tc::map_to_cta(tc::smem_u32(&R.t_empty[0]), 0); te_addr[1] = tc::map_to_cta(tc::smem_u32(&R.t_empty[1]), 0); }
     for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
         if ((int)(acc_it & 1u) != grp) continue;
         const uint32_t buf = acc_it & (NBUF - 1u);
-        const TileCoord t = decode_tile_warp(p, i, BN, lane, slab_t, i);
+        TileCoord t;
+        bool tile_ok = true;
+        if (PAIR) {
+            t = decode_tile(p, i % p.nslabs, BN);            // slab part: (N tile, group, phase)
+            const int mt = 2 * (i / p.nslabs) + (int)rank;   // this CTA's pixel tile of the pair
+            tile_ok = mt < p.m_tiles;                        // odd tile count: the last pair's second CTA repeats a tile and drops it
+            decode_mtile(p, tile_ok ? mt : 0, t.x0, t.y0, t.n0);
+        } else t = decode_tile_warp(p, i, BN, lane, slab_t, i);
         trace(tr, 2, acc_it, 0);
         const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
-        const bool valid = gx < p.gw && gy < p.gh;
+        const bool valid = tile_ok && gx < p.gw && gy < p.gh;
         const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
         const int ox = gx * p.out_stride + (p.nphase > 1 ? p.ph_off_x[t.ph] : p.epi.out_off_x);
         RowCtx rc{};
@@ -187,7 +273,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
                     trace(tr, 2, acc_it, 2);
                     tc::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
+                    if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(te_addr[buf & 1u]); else tc::mbar_arrive(&R.t_empty[buf]); }
                     trace(tr, 2, acc_it, 3);
                 }
                 if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + c, p.cout_g, t.cg * p.cout_g);
@@ -210,7 +296,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     }
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __grid_constant__ HaloParams p) {
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;            // columns per accumulator buffer
     constexpr uint32_t NBUF = halo_nbuf(BN), LGB = NBUF == 4 ? 2 : 1;
@@ -239,6 +325,10 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
     R.it_first = p.resident ? (int)(blockIdx.x / p.nslabs) : (int)blockIdx.x;
     R.it_stride = p.resident ? (int)(gridDim.x / p.nslabs) : (int)gridDim.x;
     R.it_count = p.resident ? p.m_tiles : p.total_tiles;
+    const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
+    if (PAIR) {                    // a cluster of two CTAs walks (slab, tile pair) iterations; CTA `rank` owns tile 2*pair + rank
+        R.it_first = (int)(blockIdx.x >> 1); R.it_stride = (int)(gridDim.x >> 1); R.it_count = p.m_pairs * p.nslabs;
+    }
 
     // the scheduler prefers higher warp ids: the two single-issuer warps get the highest ids so the epilogue math cannot starve them
     constexpr int W_TMA = HT_EPI_WARPS, W_MMA = HT_EPI_WARPS + 1;
@@ -248,13 +338,14 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         if (p.c0 < p.cin_g * p.cgroups) tc::prefetch_tmap(&p.a[1]);
         for (int s = 0; s < p.a_stages; ++s) { tc::mbar_init(&R.a_full[s], 1); tc::mbar_init(&R.a_empty[s], 1); }
         for (int s = 0; s < p.b_stages; ++s) { tc::mbar_init(&R.b_full[s], 1); tc::mbar_init(&R.b_empty[s], 1); }
-        for (int s = 0; s < (int)NBUF; ++s) { tc::mbar_init(&R.t_full[s], 1); tc::mbar_init(&R.t_empty[s], 4); }
+        for (int s = 0; s < (int)NBUF; ++s) { tc::mbar_init(&R.t_full[s], 1); tc::mbar_init(&R.t_empty[s], PAIR ? 8 : 4); }
         tc::mbar_init(R.b_res, 1);
         tc::fence_barrier_init();
     }
-    if (warp == W_MMA) tc::tmem_alloc<TMEM_COLS>(tslot);
+    if (warp == W_MMA) { if (PAIR) tc::tmem_alloc_pair<TMEM_COLS>(tslot); else tc::tmem_alloc<TMEM_COLS>(tslot); }
     tc::tc_fence_before();
     __syncthreads();
+    if (PAIR) tc::cluster_sync_all();                       // the peer's barriers exist before anything is signalled across the pair
     tc::tc_fence_after();
     const uint32_t tmem_base = *tslot;
 
@@ -273,7 +364,12 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         }
         for (int i = R.it_first; i < R.it_count; i += R.it_stride) {
             TileCoord t;
-            if (p.resident) { t = slab_t; decode_mtile(p, i, t.x0, t.y0, t.n0); } else t = decode_tile(p, i, BN);
+            if (PAIR) {
+                t = decode_tile(p, i % p.nslabs, BN);
+                int mt = 2 * (i / p.nslabs) + (int)rank;
+                if (mt >= p.m_tiles) mt = p.m_tiles - 1;                 // odd tile count: load something valid, the epilogue drops it
+                decode_mtile(p, mt, t.x0, t.y0, t.n0);
+            } else if (p.resident) { t = slab_t; decode_mtile(p, i, t.x0, t.y0, t.n0); } else t = decode_tile(p, i, BN);
             for (int c = 0; c < p.nchunks; ++c) {
                 const int ch = c * p.kc;
                 int src = 0, cch = ch + (p.cgroups > 1 ? t.cg * p.cin_g : 0);
@@ -283,7 +379,16 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                     trace(p.trace, 0, a_it, 0);
                     tc::mbar_wait_bounded(&R.a_empty[sa], a_par);
                     trace(p.trace, 0, a_it, 1);
-                    if (leader) {
+                    if (leader && PAIR) {
+                        // both CTAs' halos complete on the LEADER's barrier (it expects the pair's bytes)
+                        if (rank == 0) tc::mbar_expect_tx(&R.a_full[sa], 2u * (uint32_t)p.a_tx);
+                        const uint32_t bar = tc::map_to_cta(tc::smem_u32(&R.a_full[sa]), 0);
+                        if (p.rank4)
+                            tc::tma_load_4d_pair(R.a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], bar, cch, t.x0 + p.g_ox[grp], t.y0 + p.g_oy[grp], t.n0);
+                        else
+                            tc::tma_load_5d_pair(R.a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], bar,
+                                                 p.a_cbase[src] + cch + p.g_ax[grp] * p.a_cpix[src], t.x0 + p.g_ox[grp], p.g_ay[grp], t.y0 + p.g_oy[grp], t.n0);
+                    } else if (leader) {
                         tc::mbar_expect_tx(&R.a_full[sa], p.a_tx);
                         if (p.rank4)
                             tc::tma_load_4d(R.a_ring + (size_t)sa * p.a_stage_bytes, &p.a[src], &R.a_full[sa], cch, t.x0 + p.g_ox[grp], t.y0 + p.g_oy[grp], t.n0);
@@ -296,7 +401,11 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                     if (p.resident) continue;
                     while (tap < p.ntaps && p.t_grp[t.ph][tap] == grp) {
                         tc::mbar_wait_bounded(&R.b_empty[sb], b_par);
-                        if (leader) {
+                        if (leader && PAIR) {                    // this CTA's half of the weight stage: rows [rank*BN/2, +BN/2) of the N tile
+                            if (rank == 0) tc::mbar_expect_tx(&R.b_full[sb], 2u * (uint32_t)p.b_tx);
+                            tc::tma_load_2d_pair(R.b_ring + (size_t)sb * p.b_stage_bytes, &p.b, tc::map_to_cta(tc::smem_u32(&R.b_full[sb]), 0),
+                                                 (int)p.t_kidx[t.ph][tap] * p.cin_g + ch, t.ph * p.cout_total + t.cg * p.cout_g + t.nc0 + (int)rank * (BN / 2));
+                        } else if (leader) {
                             tc::mbar_expect_tx(&R.b_full[sb], p.b_tx);
                             tc::tma_load_2d(R.b_ring + (size_t)sb * p.b_stage_bytes, &p.b, &R.b_full[sb], (int)p.t_kidx[t.ph][tap] * p.cin_g + ch,
                                             t.ph * p.cout_total + t.cg * p.cout_g + t.nc0);
@@ -308,10 +417,11 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             }
         }
         __syncwarp();
-    } else if (warp == W_MMA) {
+    } else if (warp == W_MMA && (!PAIR || rank == 0)) {
         // ===================== MMA issuer: warp-uniform loop (descriptors live in uniform registers), elected lane issues =====================
+        // (PAIR: the leader CTA issues for both; the peer's MMA warp only owns its half of the TMEM allocation)
         const bool leader = tc::elect_one();
-        const uint32_t idesc = tc::make_idesc_bf16(128, BN, 0, 0);
+        const uint32_t idesc = tc::make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
         const uint32_t layout = p.kc == 64 ? 2u : p.kc == 32 ? 4u : 6u;
         const uint64_t da_base = tc::smem_desc_base(16, (uint32_t)p.pitch * p.row_bytes, layout);       // 8-row group == one halo tile row
         const uint64_t db_base = tc::smem_desc_base(16, 8u * p.row_bytes, layout);
@@ -355,6 +465,21 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             }
 #undef TBI_FLAT
             flat_done = true;
+        }
+        if (!flat_done && !p.resident && BN >= 64 && ksteps == 4) {
+            // ---- weights streamed, 64-channel stages: unrolled issue stream per tap count (NBUF == 2 for BN >= 64) ----
+            const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
+#define TBI_STREAM(NT) streamed_mma_loop<BN, PAIR, NT, 4>(p, R, tmem_base, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo)
+            if constexpr (BN >= 64) {
+                switch (p.ntaps) {
+                    case 1:  TBI_STREAM(1); flat_done = true; break;
+                    case 4:  TBI_STREAM(4); flat_done = true; break;
+                    case 9:  TBI_STREAM(9); flat_done = true; break;
+                    case 16: TBI_STREAM(16); flat_done = true; break;
+                    default: break;
+                }
+            }
+#undef TBI_STREAM
         }
         if (flat_done) {
         } else if (p.resident) {
@@ -447,13 +572,14 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             }
         }
         __syncwarp();
-    } else {
+    } else if (warp < HT_EPI_WARPS) {
         // ===================== epilogue (warp w owns TMEM lanes [32*(w%4), +32)) =====================
-        TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_role<BN, A_, D_>(p, R, sbias, tmem_base, warp, lane)));
+        TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_role<BN, PAIR, A_, D_>(p, R, sbias, tmem_base, warp, lane)));
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == W_MMA) tc::tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (PAIR) tc::cluster_sync_all();                       // the peer may still signal this CTA's barriers / read its operands
+    if (warp == W_MMA) { if (PAIR) tc::tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tc::tmem_dealloc<TMEM_COLS>(tmem_base); }
 }
 
 inline uint32_t r1024(uint32_t x) { return (x + 1023u) & ~1023u; }
@@ -486,13 +612,23 @@ int halo_act_tmap(CUtensorMap* out, const tbi_view& v, int n, int stride, int kc
     return tbi_make_tmap_bf16(out, base, 5, dims, strides, box, kc * 2);
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 int launch_halo(const HaloParams& p, int grid, size_t smem, cudaStream_t s) {
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tapgemm_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
+    std::call_once(once, [] { attr_err = cudaFuncSetAttribute(tapgemm_halo_kernel<BN, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); });
     if (attr_err != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(attr_err));
-    tapgemm_halo_kernel<BN><<<grid, HT_THREADS, smem, s>>>(p);
+    if (PAIR) {
+        cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(HT_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, tapgemm_halo_kernel<BN, PAIR>, p);
+        if (e != cudaSuccess) return tbi_set_error(TBI_ERR_CUDA, "tapgemm_halo (pair): %s", cudaGetErrorString(e));
+        return TBI_OK;
+    }
+    tapgemm_halo_kernel<BN, PAIR><<<grid, HT_THREADS, smem, s>>>(p);
     TBI_CUDA_LAUNCH_CHECK("tapgemm_halo");
     return TBI_OK;
 }
@@ -541,6 +677,11 @@ bool plan_taps(const tbi_tapgemm* d, TapPlan* tp) {
 
 }  // namespace
 
+// debug/test knob (not part of the public header): minimum number of (slab, tile-pair) iterations for PAIR mode; tests lower
+// it to drive small shapes (odd tile counts, partial tiles) through the cta_group::2 path.  <= 0 restores the default.
+static int g_pair_min = 0;
+extern "C" int tbi_debug_set_pair_min(int v) { g_pair_min = v; return 0; }
+
 // debug: device buffer of 3*64*8 uint64 (or nullptr to disable); not part of the public header
 extern "C" int tbi_debug_set_halo_trace(void* buf) {
     g_halo_trace_host = (unsigned long long*)buf;
@@ -588,26 +729,38 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     int bn = 128;
     while (bn > 16 && bn / 2 >= d->cout_g) bn >>= 1;
     if (p.narrow) bn = 16;                                   // the element-wise epilogue exists for 16-column tiles only
+    p.n_tiles = (d->cout_g + bn - 1) / bn;
+    p.total_tiles = p.m_tiles * p.cgroups * p.nphase * p.n_tiles;
+    p.nslabs = p.n_tiles * p.cgroups * p.nphase;
+    p.m_pairs = (p.m_tiles + 1) / 2;
+    // PAIR (cta_group::2): streamed 128-column tiles of 64-channel stages with enough tile pairs for every SM pair; the
+    // resident / small-K layers keep the single-CTA schedules (their weights are not re-streamed)
+    static const bool no_pair = getenv("TBI_TC_NO_PAIR") != nullptr;
+    const long long slab_bytes_full = (long long)(d->cin_g / kc) * d->ntaps * (long long)r1024((uint32_t)(bn * kc * 2));
+    static const bool no_resident0 = getenv("TBI_TC_NO_RESIDENT") != nullptr;
+    const bool would_be_resident = !no_resident0 && slab_bytes_full <= 72 * 1024 && p.nslabs <= 2 * tbi_sm_count() &&
+                                   slab_bytes_full + 2 * (long long)r1024((uint32_t)(bw * bh * kc * 2)) <= 104 * 1024 && (d->cin_g / kc) * d->ntaps <= 192;
+    p.pair = (!no_pair && !would_be_resident && bn == 128 && !p.narrow && kc == 64 && d->cout_g % 128 == 0 &&
+              (d->ntaps == 1 || d->ntaps == 4 || d->ntaps == 9 || d->ntaps == 16) &&
+              (long long)p.m_pairs * p.nslabs >= (g_pair_min > 0 ? (long long)g_pair_min : (long long)tbi_sm_count())) ? 1 : 0;
+    const int b_rows = p.pair ? bn / 2 : bn;                 // PAIR: each CTA streams half of the N tile's weight rows
     {
         const uint64_t K = (uint64_t)d->ntaps * d->cin_g;
         uint64_t dims[2] = {K, (uint64_t)p.cout_total * p.nphase};
         uint64_t strides[1] = {K * 2};
-        uint32_t box[2] = {(uint32_t)kc, (uint32_t)bn};
+        uint32_t box[2] = {(uint32_t)kc, (uint32_t)b_rows};
         rc = tbi_make_tmap_bf16(&p.b, const_cast<void*>(d->w), 2, dims, strides, box, kc * 2);
         if (rc) return rc;
     }
-    p.n_tiles = (d->cout_g + bn - 1) / bn;
-    p.total_tiles = p.m_tiles * p.cgroups * p.nphase * p.n_tiles;
-    p.a_tx = bw * bh * kc * 2; p.b_tx = bn * kc * 2;
+    p.a_tx = bw * bh * kc * 2; p.b_tx = b_rows * kc * 2;
     p.a_stage_bytes = (int)r1024((uint32_t)p.a_tx); p.b_stage_bytes = (int)r1024((uint32_t)p.b_tx);
     // ~104 KB per CTA so that two CTAs share an SM (TBI_HALO_BUDGET_KB > 113 -> one CTA per SM with deeper rings)
     static const int budget_kb = getenv("TBI_HALO_BUDGET_KB") ? atoi(getenv("TBI_HALO_BUDGET_KB")) : 104;
     const int budget = budget_kb * 1024;
     const int max_ctas = (budget_kb > 113 ? 1 : 2) * tbi_sm_count();
-    p.nslabs = p.n_tiles * p.cgroups * p.nphase;
     const long long slab_bytes = (long long)p.nchunks * d->ntaps * p.b_stage_bytes;
     static const bool no_resident = getenv("TBI_TC_NO_RESIDENT") != nullptr;
-    p.resident = (!no_resident && slab_bytes <= 72 * 1024 && p.nslabs <= max_ctas && slab_bytes + 2 * p.a_stage_bytes <= budget &&
+    p.resident = (!p.pair && !no_resident && slab_bytes <= 72 * 1024 && p.nslabs <= max_ctas && slab_bytes + 2 * p.a_stage_bytes <= budget &&
                   p.nchunks * d->ntaps <= 192) ? 1 : 0;
     {
         static const bool no_flat = getenv("TBI_TC_NO_FLAT") != nullptr;
@@ -631,20 +784,27 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         grid = per_slab * p.nslabs;
     } else {
         // a halo stage feeds ntaps/ngroups weight tiles: two halo stages are enough, the weight ring gets the rest
-        p.a_stages = 2;
+        p.a_stages = budget_kb > 113 ? 4 : 2;
         int bs = (budget - p.a_stages * p.a_stage_bytes) / p.b_stage_bytes;
-        if (bs > 8) bs = 8;
+        if (bs > (budget_kb > 113 ? 16 : 8)) bs = budget_kb > 113 ? 16 : 8;
         if (bs < 2) bs = 2;
         p.b_stages = bs;
         grid = max_ctas;
         if (grid > p.total_tiles) grid = p.total_tiles;
+        if (p.pair) {                                        // clusters of two: one pair per (slab, tile pair) iteration slot
+            const long long its = (long long)p.m_pairs * p.nslabs;
+            long long pairs = max_ctas / 2;
+            if (pairs > its) pairs = its;
+            grid = (int)(2 * pairs);
+        }
     }
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512 +
                         ((size_t)p.cout_total * 4 + 64) + (size_t)(2 * (p.a_stages + p.b_stages) + 8) * 8;
+    if (p.pair) return launch_halo<128, true>(p, grid, smem, s);
     switch (bn) {
-        case 128: return launch_halo<128>(p, grid, smem, s);
-        case 64:  return launch_halo<64>(p, grid, smem, s);
-        case 32:  return launch_halo<32>(p, grid, smem, s);
-        default:  return launch_halo<16>(p, grid, smem, s);
+        case 128: return launch_halo<128, false>(p, grid, smem, s);
+        case 64:  return launch_halo<64, false>(p, grid, smem, s);
+        case 32:  return launch_halo<32, false>(p, grid, smem, s);
+        default:  return launch_halo<16, false>(p, grid, smem, s);
     }
 }

@@ -36,6 +36,7 @@ struct alignas(64) TcWgradParams {
     int ci_tiles, co_tiles, ntaps;
     int nb;                       // 64-channel blocks of the co tile (BN = 64*nb)
     int stages, tiles_per_cta;
+    int ci_tile_base, co_tile_base;   // this launch covers ci tiles [base, base + ci_tiles) and co tiles [base, base + co_tiles)
     int b_cbase, b_cpix;
     signed char aqy[16], aqx[16], bqy[16], bqx[16], bay[16], bax[16];
     float* dw;
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_co
     const int tile_end = min(total_tiles, tile_beg + p.tiles_per_cta);
     const int iters = tile_end - tile_beg;
     const int tw = 1 << p.ltw, th = 1 << p.lth, tn = KP >> (p.ltw + p.lth);
-    const int ci0 = ci_t * 128, co0 = co_t * BN;
+    const int ci0 = (ci_t + p.ci_tile_base) * 128, co0 = (co_t + p.co_tile_base) * BN;
 
     if (warp == 0) {
         if (lane == 0 && iters > 0) {
@@ -253,6 +254,19 @@ int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s) {
     const char* why = "";
     if (!tbi_tapwgrad_tc_supported(d, &why)) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapwgrad_tc: %s", why);
     if (tbi_tapwgrad_small_supported(d)) return tbi_tapwgrad_small(d, s);
+    // CTA pairs (cta_group::2, tapwgrad_tc2.cu) take every pair of 128-channel tiles of the M operand; an odd last tile (e.g. the
+    // 64 skip channels of upsample_4's 320-channel input) is left to the single-CTA kernel below
+    const tbi_wgrad_pair_plan pl = tbi_tapwgrad_pair_plan(d);
+    int rest_ci_base = 0, rest_ci_tiles = -1, rest_co_base = 0, rest_co_tiles = -1;
+    if (pl.ok) {
+        int rcp = tbi_tapwgrad_pair(d, pl, s); if (rcp) return rcp;
+        if (pl.m_tiles % 2 == 0) {
+            if (d->dbias) return tbi_colsum(d->dtype, (int64_t)d->n * d->b_src.h * d->b_src.w, &d->b_src, d->dbias, (void*)s);
+            return TBI_OK;
+        }
+        if (pl.m_is_a) { rest_ci_base = pl.m_tiles - 1; rest_ci_tiles = 1; }
+        else           { rest_co_base = pl.m_tiles - 1; rest_co_tiles = 1; }       // M = co in 128-channel tiles == this kernel's BN = 128 tiles
+    }
     TcWgradParams p; memset(&p, 0, sizeof(p));
     int ltw = wg_ilog2_ceil(d->gw); if (ltw > 3) ltw = 3;
     int lth = wg_ilog2_ceil(d->gh); if (lth > 6 - ltw) lth = 6 - ltw;
@@ -266,6 +280,8 @@ int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s) {
     p.nb = d->cout_g > 64 ? 2 : 1;
     const int bn = 64 * p.nb;
     p.co_tiles = (d->cout_g + bn - 1) / bn;
+    if (rest_ci_tiles > 0) { p.ci_tile_base = rest_ci_base; p.ci_tiles = rest_ci_tiles; }
+    if (rest_co_tiles > 0) { p.co_tile_base = rest_co_base; p.co_tiles = rest_co_tiles; }
     for (int t = 0; t < d->ntaps; ++t) {
         p.aqy[t] = (signed char)d->a_dy[t]; p.aqx[t] = (signed char)d->a_dx[t];
         if (d->b_stride == 1) { p.bqy[t] = (signed char)d->b_dy[t]; p.bqx[t] = (signed char)d->b_dx[t]; p.bay[t] = 0; p.bax[t] = 0; }

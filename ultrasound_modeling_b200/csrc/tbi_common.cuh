@@ -94,6 +94,9 @@ int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s);
 bool tbi_tapgemm_tc_supported(const tbi_tapgemm* d, const char** why);
 bool tbi_tapwgrad_tc_supported(const tbi_tapwgrad* d, const char** why);
 int64_t tbi_tapwgrad_tc_workspace(const tbi_tapwgrad* d);
+struct tbi_wgrad_pair_plan { int ok; int m_is_a; int T; int m_pairs; int m_tiles; };
+tbi_wgrad_pair_plan tbi_tapwgrad_pair_plan(const tbi_tapwgrad* d);                       // CTA-pair (cta_group::2) weight gradient, tapwgrad_tc2.cu
+int tbi_tapwgrad_pair(const tbi_tapwgrad* d, const tbi_wgrad_pair_plan& pl, cudaStream_t s);
 bool tbi_tapwgrad_small_supported(const tbi_tapwgrad* d);      // few-input-channel stride-1 conv wgrad (tap-packed M, TMEM-resident)
 int tbi_tapwgrad_small(const tbi_tapwgrad* d, cudaStream_t s);
 int tbi_splitatt_fwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, cudaStream_t s);     // 1 launched, 0 not applicable
