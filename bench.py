@@ -105,6 +105,76 @@ def run_reference(args):
                       "gpu_launches": 0, "wall_s": time.perf_counter() - t0}))
 
 
+def other_configs(args, dev):
+    """The BASELINE.json configurations other than the headline one, measured in the same driver-run process so that the
+    record carries them (rank 0, one GPU): configs[1] split-attention microbench (three shapes, fwd / bwd HBM GB/s),
+    configs[2] with the reference-default radix 4 x kpaths 4 and the reference driver's own radix 3 x kpaths 4
+    (TBI_ResNest.py:461), configs[3] 512x512 r4k4 batch 16, configs[4] the inference sweep (Variant A forward, and Variant B
+    encoder+decoder forward at the [N,256,80,10] shape TBIEvaluator.py:186,238 feeds).  Each is a short run: CUDA events,
+    3 warm-up calls, device-resident synthetic inputs."""
+    import torch
+    from oracle import tbi_resnest_oracle as O
+    from oracle import resnest_decoder_oracle as B
+    from ultrasound_modeling_b200.TBI_ResNest import ResNest
+    import bench_splitatt
+
+    def timed(f, reps, warm=3):
+        for _ in range(warm):
+            f()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            f()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    sa = bench_splitatt.main(emit=False, reps=5)
+    out["splitatt_config1"] = [{"shape_U_r": r["shape_U_r"], "fwd_us": round(r["fwd"]["us"], 2), "fwd_GBps": round(r["fwd"]["GBps"], 1),
+                                "fwd_frac_of_hbm_peak": round(r["fwd"]["frac_of_hbm_peak"], 3), "bwd_us": round(r["bwd"]["us"], 2),
+                                "bwd_GBps": round(r["bwd"]["GBps"], 1), "bwd_frac_of_hbm_peak": round(r["bwd"]["frac_of_hbm_peak"], 3),
+                                "peak_gbs": r["peak_gbs"], "method": r["method"]} for r in sa]
+    torch.cuda.empty_cache()
+    train = []
+    for (hw, n, r, k, tag) in ((256, 64, 4, 4, "configs[2] with reference defaults r4k4"), (256, 64, 3, 4, "configs[2] with the reference driver's r3k4"),
+                               (512, 16, 4, 4, "configs[3]: 512x512 r4k4 batch 16")):
+        net = ResNest(hw, hw, 1, 3, 3, radix=r, kpaths=k, dtype="bf16", use_cuda_graph=True, device=str(dev))
+        x, y = O.synthetic_batch(2, hw, hw, seed=3000)
+        x = x.repeat(n // 2, 1, 1, 1).to(dev); y = y.repeat(n // 2, 1, 1, 1).to(dev)
+        net.engine.fallback_report(reset=True)
+        ms = timed(lambda: net.step(x, y, train=True), 10, warm=4)
+        fb = net.engine.fallback_report()
+        train.append({"config": tag, "size": hw, "batch": n, "radix": r, "kpaths": k, "ms_per_step": round(ms, 3), "img_per_s": round(n / ms * 1e3, 1),
+                      "cuda_core_fallback_launches": fb["tapgemm_simt"] + fb["tapwgrad_simt"]})
+        del net, x, y
+        torch.cuda.empty_cache()
+    out["train_other"] = train
+    infer = []
+    net = ResNest(256, 256, 1, 3, 3, radix=2, kpaths=1, dtype="bf16", use_cuda_graph=False, device=str(dev))
+    for n in (1, 8, 64, 256):
+        x, _ = O.synthetic_batch(min(n, 4), 256, 256)
+        x = x.repeat((n + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:n].to(dev)
+        ms = timed(lambda: net.predict(x, dropout_masks=False), 10)
+        infer.append({"model": "Variant A forward 256x256x1 r2k1 bf16", "batch": n, "ms": round(ms, 3), "img_per_s": round(n / ms * 1e3, 1)})
+    del net
+    torch.cuda.empty_cache()
+    try:
+        from ultrasound_modeling_b200.ResNest import ResNest as EncB
+        from ultrasound_modeling_b200.Decoder import DecoderCup
+        for n in (1, 32):
+            enc = EncB(256, 80, 10, 3, radix=3, kpaths=3, dtype="bf16", device=str(dev)); dec = DecoderCup(3, dtype="bf16", device=str(dev))
+            x = B.synthetic_input(n).to(dev); tok = B.synthetic_tokens(n).to(dev)
+            ms = timed(lambda: dec(tok, enc(x)[1]), 5)
+            infer.append({"model": "Variant B encoder+decoder forward [N,256,80,10] r3k3 bf16", "batch": n, "ms": round(ms, 3), "img_per_s": round(n / ms * 1e3, 1)})
+            del enc, dec
+    except Exception as exc:                                     # noqa: BLE001 -- a side measurement must not take the headline down
+        infer.append({"model": "Variant B", "error": repr(exc)[:200]})
+    out["inference_sweep_config4"] = infer
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_name(args):
     return (f"TBI_ResNest full training step, batch {args.batch}/GPU, {args.size}x{args.size}x1, radix {args.radix} kpaths {args.kpaths} "
             f"(BASELINE.json configs[2])")
@@ -213,9 +283,12 @@ def run_ours(args):
         peak = pk["bf16_tflops"]                                 # burst figure: this kernel is timed alone (B200_PROFILING.md)
         peak_sus = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])   # sustained figure: for the whole step
         step_flops = 3.0 * O.forward_flops_per_image(args.size, args.size, 1, 3, 3, args.radix, args.kpaths) * B
-        traffic = 397.05e6 * (B / 64.0) * (args.size / 256.0) ** 2 if args.dtype == "bf16" else None
-        roof = {"bound": "tensor", "kernel": f"tapgemm_halo_kernel<128>: {name} Conv2DTranspose k4 s2 fwd [{B},{h},{w},{cin}]->[{B},{2*h},{2*w},{cout}] (one 4-phase launch)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "peak_source": pk_kind + " (burst bf16, kernel timed alone with L2 flushed between launches)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of exactly this launch (N=64, 256x256, bf16) in the committed capture
+        # profiles/r2_ncu_upsample4_fwd.md (169.2 MB read + 230.2 MB written; algorithmic 436 MB); null for any other shape
+        traffic = 399.46e6 if (args.dtype == "bf16" and B == 64 and args.size == 256) else None
+        roof = {"bound": "tensor", "kernel": f"tapgemm_halo_kernel<128, pair>: {name} Conv2DTranspose k4 s2 fwd [{B},{h},{w},{cin}]->[{B},{2*h},{2*w},{cout}] (one 4-phase launch, cta_group::2)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": "profiles/r2_ncu_upsample4_fwd.md (ncu --set full capture of this launch)",
+                "peak_source": pk_kind + " (burst bf16, kernel timed alone with L2 flushed between launches)",
                 "ms_per_call": kms, "flops_per_call": flops_call, "step_tflops": step_flops * world * args.steps / (ms / 1e3) / 1e12 / world,
                 "step_frac_of_peak_sustained": step_flops * args.steps / (ms / 1e3) / 1e12 / peak_sus}
         cpu_val, cores, sample = cpu_oracle_rate(args.radix, args.kpaths, args.size, seconds=args.cpu_seconds)
@@ -230,6 +303,13 @@ def run_ours(args):
                "roofline": roof,
                "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                "clocks": sampler.summary() if sampler else None}
+        if world == 1 and not args.no_extras and B == 64 and args.size == 256:
+            del net, e
+            torch.cuda.empty_cache()
+            try:
+                out["other_configs"] = other_configs(args, dev)
+            except Exception as exc:                             # noqa: BLE001 -- side measurements must not take the headline down
+                out["other_configs"] = {"error": repr(exc)[:300]}
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -252,6 +332,7 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs (split-attention microbench, r4k4/r3k4/512, inference sweep)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -48,7 +48,9 @@ def _time_graph(g, reps, before=None):
     return sorted(times)[len(times) // 2]
 
 
-def main(tag=None, shapes=((128, 32), (64, 64), (32, 128))):
+def main(tag=None, shapes=((128, 32), (64, 64), (32, 128)), emit=True, reps=7):
+    """prints one JSON line per shape (emit=True) and returns the list of records"""
+    out = []
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]; src = "measured"
     except Exception:
@@ -83,18 +85,23 @@ def main(tag=None, shapes=((128, 32), (64, 64), (32, 128))):
                 ("bwd", lambda i: sas[i].backward(us[i], dvs[i], out=dus[i], grads=grads, scratch=scr[i]), 2 * R + 2))
         for name, fn, passes in legs:
             ring = _graph(lambda: [fn(i) for i in range(nbuf)])
-            ms = _time_graph(ring, 7) / nbuf
+            ms = _time_graph(ring, reps) / nbuf
             one = _graph(lambda: fn(0))
             iso = _time_graph(one, 10, do_flush)
             res[name] = {"us": ms * 1e3, "algorithmic_MB": passes * nhwc_b / 1e6, "GBps": passes * nhwc_b / ms / 1e6,
                          "frac_of_hbm_peak": passes * nhwc_b / ms / 1e6 / peak, "isolated_us": iso * 1e3,
                          "isolated_frac": passes * nhwc_b / iso / 1e6 / peak}
-        print(json.dumps({"metric": "split-attention HBM GB/s", "shape_U_r": [N, h, h, c], "radix": R, "kpaths": K, "dtype": "bf16",
-                          "peak_gbs": peak, "peak_source": src, **({"variant": tag} if tag else {}),
-                          "method": f"us: back-to-back launches in one CUDA graph over a ring of {nbuf} buffer sets "
-                                    f"({nbuf * (2 * R + 1) * nhwc_b >> 20} MB > L2); isolated_us: single launch after an L2 flush, "
-                                    f"includes ~{floor_us:.1f} us graph-launch/event floor",
-                          "floor_us": floor_us, **res}), flush=True)
+        rec = {"metric": "split-attention HBM GB/s", "shape_U_r": [N, h, h, c], "radix": R, "kpaths": K, "dtype": "bf16",
+               "peak_gbs": peak, "peak_source": src, **({"variant": tag} if tag else {}),
+               "method": f"us: back-to-back launches in one CUDA graph over a ring of {nbuf} buffer sets "
+                         f"({nbuf * (2 * R + 1) * nhwc_b >> 20} MB > L2); isolated_us: single launch after an L2 flush, "
+                         f"includes ~{floor_us:.1f} us graph-launch/event floor",
+               "floor_us": floor_us, **res}
+        out.append(rec)
+        if emit:
+            print(json.dumps(rec), flush=True)
+        del sas, us, dvs, vs, dus, scr
+    return out
 
 
 def sweep():

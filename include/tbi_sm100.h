@@ -298,7 +298,10 @@ int tbi_layernorm_c_bwd(int dtype, int64_t npix, int c, const tbi_view* x, const
 int tbi_splitatt_shared_fwd(int dtype, int n, int h, int w, int kpaths, int radix, int c, const tbi_view* u,
                             const tbi_view* v, const float* w1, const float* b1, const float* ln_gamma,
                             const float* ln_beta, float ln_eps, int act, const float* w2, const float* b2,
-                            float* att, void* stream);
+                            float* att, int cgroup, void* stream);
+/* cgroup (0 = c): channels between the first channels of consecutive cardinals in the u / v / du / dv records.  With
+ * cgroup > c every cardinal's slice is zero-padded (c = 10 in a 16-channel slot), which keeps the slices 16-byte aligned
+ * for the tensor-core convolutions on either side; the pad lanes are neither read nor written here.              */
 
 /* backward of the above.  att = the forward's att buffer (R*a); scratch: fp32 [2][n][K*c].  dV -> dU; the parameter
  * gradients (same shapes as the parameters) are ADDED.  One pass over (U, dV) for sum_p U and sum_p dV*U, the FC chain
@@ -307,7 +310,7 @@ int tbi_splitatt_shared_bwd(int dtype, int n, int h, int w, int kpaths, int radi
                             const tbi_view* dv, const tbi_view* du, const float* w1, const float* b1,
                             const float* ln_gamma, const float* ln_beta, float ln_eps, int act, const float* w2,
                             const float* att, float* dw1, float* db1, float* dln_gamma, float* dln_beta,
-                            float* dw2, float* db2, float* scratch, void* stream);
+                            float* dw2, float* db2, float* scratch, int cgroup, void* stream);
 
 /* x fp32/fp64 host-layout NHWC -> storage dtype (device to device)                               */
 int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void* src, void* dst, void* stream);

@@ -118,9 +118,20 @@ def _pair(dtype, H, W, n, cuda_device):
     return enc, dec, pe, pd, x, tok, grid
 
 
+def _fallbacks(reset=False):
+    """bf16 tap-GEMM launches that left the tensor cores for the CUDA-core kernel (tbi_fallback_stats)"""
+    import ctypes
+    from ultrasound_modeling_b200 import _lib
+    a, b = ctypes.c_int64(0), ctypes.c_int64(0)
+    L = _lib.lib()
+    L.tbi_fallback_stats(ctypes.byref(a), ctypes.byref(b), 1 if reset else 0)
+    return int(a.value), int(b.value), L.tbi_last_fallback().decode()
+
+
 @pytest.mark.parametrize("dtype,H,W,n", [(torch.float32, 64, 32, 2), (torch.float32, 256, 80, 1), (torch.bfloat16, 64, 32, 2), (torch.bfloat16, 256, 80, 2)])
 def test_encoder_decoder_parity(cuda_device, dtype, H, W, n):
     enc, dec, pe, pd, x, tok, grid = _pair(dtype, H, W, n, cuda_device)
+    _fallbacks(reset=True)
     oe = B.ResNestEncoderOracle(10, 3, 3, 3, pe); od = B.DecoderCupOracle(3, pd, grid=grid)
     x4w, fw = oe(x)
     x4, feats = enc(x.float())
@@ -156,6 +167,10 @@ def test_encoder_decoder_parity(cuda_device, dtype, H, W, n):
     assert worst < 2 * tol
     decided = margin > 2 * tol
     assert float(same[decided].float().mean()) >= 0.999 and agree >= 0.99
+    if dtype == torch.bfloat16:
+        # odd-width layers (3/7/10/21/30/63/85/126/255 channels, the 10 input planes, the 8 token channels of the head) are stored in
+        # zero-padded 16-channel records: nothing may have left the tcgen05 path
+        assert _fallbacks()[:2] == (0, 0), _fallbacks()
 
 
 def test_lazy_build_and_golden(cuda_device):
@@ -238,11 +253,14 @@ def test_encoder_decoder_backward(cuda_device, dtype, H, W, n):
     2e-2 one by one (conv / convT / LayerNorm / split-attention gradient tests)."""
     enc, dec, pe, pd, x, tok, grid = _pair(dtype, H, W, n, cuda_device)
     ref, gz, g4 = _oracle_grads(pe, pd, x, tok, grid)
+    _fallbacks(reset=True)
     x4, feats = enc.forward(x.float(), record=True)
     z = dec.forward(tok.float(), feats, logits=True, record=True)
     dhid, dfeats = dec.backward(gz.float())
     assert all(d is not None for d in dfeats)
     dx = enc.backward(g4.float(), dfeats)
+    if dtype == torch.bfloat16:
+        assert _fallbacks()[:2] == (0, 0), _fallbacks()      # forward, data gradients and weight gradients all on tcgen05
     got = {"dx": dx, "dhidden": dhid}
     got.update({"enc/" + k: g for k, g in enc.gradients().items()}); got.update({"dec/" + k: g for k, g in dec.gradients().items()})
     assert set(got) == set(ref)

@@ -26,23 +26,38 @@ _DIL = (1, 2, 4, 8)          # conv*_0: 1x1; conv*_1..3: 3x3 dilated 2, 4, 8 (De
 
 def _convt(layer, x, x2, name, cout, out_f32=False):
     """Conv2DTranspose k3 s2 'same' over the virtual concat (x, x2), no norm / activation (Decoder.py:57-59,120); recorded for
-    backward when the store is recording"""
+    backward when the store is recording.  bf16 storage: a second source whose width is not a multiple of 16 (the 8 token
+    channels in front of the head, Decoder.py:140-141) is copied into zero-padded 16-channel records and the matching kernel
+    rows are zero, and a gradient narrower than 8 channels (the 3-class head) is widened to 16-channel records, so that
+    forward, data gradient and weight gradient all stay on the tensor-core path."""
     s = layer._s
-    cin = x.shape[3] + (x2.shape[3] if x2 is not None else 0)
-    w = s.kernel(name + "/kernel", (3, 3, cout, cin))
+    c0, c2 = x.shape[3], (x2.shape[3] if x2 is not None else 0)
+    w = s.kernel(name + "/kernel", (3, 3, cout, c0 + c2))
     b = s.vector(name + "/bias", cout, 0.0)
-    y = ops.conv2d_transpose_s2(x, w, b, x2=x2, out_f32=out_f32)
+    c2p = ops.pad_channels(c2, x.dtype) if x2 is not None else 0
+    x2p, wk = x2, w
+    if c2p != c2:
+        x2p = torch.zeros(*x2.shape[:3], c2p, dtype=x2.dtype, device=x2.device)
+        x2p[..., :c2] = x2
+        wk = torch.zeros(3, 3, cout, c0 + c2p, dtype=torch.float32, device=w.device)
+        wk[..., :c0 + c2] = w
+    y = ops.conv2d_transpose_s2(x, wk, b, x2=x2p, out_f32=out_f32)
     if s.recording:
         def bwd():
             dz = s.gget(y)
             if dz is None:
                 return
-            dxs, dw, db = ops.conv2d_transpose_s2_grads(x, w, dz.to(x.dtype), x2=x2)
-            s.pacc(name + "/kernel", dw); s.pacc(name + "/bias", db)
+            dz = dz.to(x.dtype)
+            if x.dtype == torch.bfloat16 and cout % 8 != 0:
+                dzp = torch.zeros(*dz.shape[:3], ops.pad_channels(cout, x.dtype), dtype=dz.dtype, device=dz.device)
+                dzp[..., :cout] = dz
+                dz = dzp
+            dxs, dw, db = ops.conv2d_transpose_s2_grads(x, wk, dz, x2=x2p)
+            s.pacc(name + "/kernel", dw[..., :c0 + c2].contiguous()); s.pacc(name + "/bias", db)
             if x2 is None:
                 s.gacc(x, dxs)
             else:
-                s.gacc(x, dxs[0]); s.gacc(x2, dxs[1])
+                s.gacc(x, dxs[0]); s.gacc(x2, dxs[1][..., :c2].contiguous().reshape(x2.shape))
         s.tape.append(bwd)
     return y
 

@@ -105,33 +105,65 @@ class _Layer:
 
     # -- Keras layer equivalents on NHWC device tensors --------------------------------------
     def _conv(self, x, name, k, cout, *, dilation=1, bn=None, act=ACT_NONE, residual=None, x2=None, out=None, out_coff=0, out_f32=False,
-              need_dx=True):
-        cin = x.shape[3] + (x2.shape[3] if x2 is not None else 0)
-        w = self._s.kernel(f"{self._p}{name}/kernel", (k, k, cin, cout))
+              need_dx=True, cin=None, cmap=None, out_slot=None):
+        """Conv2D + [BN] + [act] (+ residual).  Stored bf16 activations have their channels zero-padded to a multiple of 16
+        (ops.pad_channels), so x may be physically wider than its ``cin`` logical channels and the output is allocated wider
+        than ``cout``: the Keras-shaped master kernel is scattered into a zero kernel of the physical shape each call (rows
+        ``cmap`` = physical position of every logical input channel, default the first cin), the convolution runs on the
+        tensor-core path at the physical widths, pad output lanes come out exactly 0 (zero kernel columns, zero bias, identity
+        BN, act(0) = 0), and the gradients are gathered back to the Keras shapes.  ``out``/``out_coff``/``out_slot``: write a
+        slot of out_slot >= cout physical channels of a wider buffer."""
+        cx = x.shape[3]
+        cx_real = cx if cin is None else cin
+        c2 = x2.shape[3] if x2 is not None else 0
+        w = self._s.kernel(f"{self._p}{name}/kernel", (k, k, cx_real + c2, cout))
         b = self._s.vector(f"{self._p}{name}/bias", cout, 0.0)
         bnp = None
         if bn is not None:
             q = f"{self._p}{bn}/"
             bnp = (self._s.vector(q + "gamma", cout, 1.0), self._s.vector(q + "beta", cout, 0.0),
                    self._s.vector(q + "moving_mean", cout, 0.0), self._s.vector(q + "moving_variance", cout, 1.0))
-        y = ops.conv2d(x, w, b, dilation=dilation, bn=bnp, act=act, residual=residual, x2=x2, out=out, out_coff=out_coff, out_f32=out_f32)
+        cout_p = (out_slot or cout) if out is not None else (cout if out_f32 else ops.pad_channels(cout, x.dtype))
+        padded = cx != cx_real or cmap is not None or cout_p != cout
+        rows = None
+        if padded:
+            dev = x.device
+            rows = torch.as_tensor(cmap, device=dev, dtype=torch.long) if cmap is not None else torch.arange(cx_real, device=dev)
+            wk = torch.zeros(k, k, cx + c2, cout_p, dtype=torch.float32, device=dev)
+            wk[:, :, rows, :cout] = w[:, :, :cx_real]
+            if c2:
+                wk[:, :, cx:, :cout] = w[:, :, cx_real:]
+            bk = torch.zeros(cout_p, dtype=torch.float32, device=dev); bk[:cout] = b
+            bnk = None
+            if bnp is not None:
+                fill = (1.0, 0.0, 0.0, 1.0)                      # identity BN on the pad lanes
+                bnk = tuple(torch.full((cout_p,), f, dtype=torch.float32, device=dev) for f in fill)
+                for dst, src in zip(bnk, bnp):
+                    dst[:cout] = src
+        else:
+            wk, bk, bnk = w, b, bnp
+        y = ops.conv2d(x, wk, bk, dilation=dilation, bn=bnk, act=act, residual=residual, x2=x2, out=out, out_coff=out_coff, out_f32=out_f32)
         if self._s.recording:
             s, pre = self._s, f"{self._p}{name}/"
 
             def bwd():
                 buf, off = (out, out_coff) if out is not None else (y, 0)
-                dy = s.gget(buf, off, cout)
+                dy = s.gget(buf, off, cout_p)
                 if dy is None:
                     return
                 if residual is not None:
                     s.gacc(residual, dy)
-                dz = ops.act_bwd(dy, buf if buf.shape[3] == cout else buf[..., off:off + cout].contiguous(), act) if act != ACT_NONE else dy
-                scale = ops.fold_bn(cout, b, bnp, x.device)[0] if bnp is not None else None
-                dxs, dw, db = ops.conv2d_grads(x, w, dz, dilation=dilation, scale=scale, x2=x2, need_dx=need_dx)
-                if bnp is not None:
-                    dgam, dbet = ops.bn_param_grad(w, dw, b, db, bnp)              # dw, db: raw -> true gradients, in place
-                    s.pacc(f"{self._p}{bn}/gamma", dgam); s.pacc(f"{self._p}{bn}/beta", dbet)
-                s.pacc(pre + "kernel", dw); s.pacc(pre + "bias", db)
+                dz = ops.act_bwd(dy, buf if buf.shape[3] == cout_p else buf[..., off:off + cout_p].contiguous(), act) if act != ACT_NONE else dy
+                scale = ops.fold_bn(cout_p, bk, bnk, x.device)[0] if bnk is not None else None
+                dxs, dw, db = ops.conv2d_grads(x, wk, dz, dilation=dilation, scale=scale, x2=x2, need_dx=need_dx)
+                if bnk is not None:
+                    dgam, dbet = ops.bn_param_grad(wk, dw, bk, db, bnk)            # dw, db: raw -> true gradients, in place
+                    s.pacc(f"{self._p}{bn}/gamma", dgam[:cout]); s.pacc(f"{self._p}{bn}/beta", dbet[:cout])
+                if padded:                                                         # back to the Keras shapes
+                    dwr = dw[:, :, rows, :cout]
+                    dw = torch.cat([dwr, dw[:, :, cx:, :cout]], 2) if c2 else dwr
+                    db = db[:cout]
+                s.pacc(pre + "kernel", dw.contiguous()); s.pacc(pre + "bias", db.contiguous())
                 if need_dx:
                     if x2 is None:
                         s.gacc(x, dxs)
@@ -198,11 +230,11 @@ class cardinal(_Layer):
         self.cvkk = int(outchannel / kpaths)
         self.split = split_attention(self.cvkk, radix, atrous, wDecay, _store=_store, _prefix=_prefix + "split/")
 
-    def features(self, x, out, out_coff):
-        """U of this cardinal written into channels [out_coff, out_coff+cvkk) of ``out``"""
-        y = self._conv(x, "conv1", 1, self.cv11, dilation=self.atrous)
-        y = self._ln(y, "conv1_bn")
-        self._conv(y, "conv2", self.ksize, self.cvkk, dilation=self.atrous, out=out, out_coff=out_coff)
+    def features(self, x, out, out_coff, out_slot=None):
+        """U of this cardinal written into channels [out_coff, out_coff+cvkk) of ``out`` (a slot of out_slot >= cvkk channels)"""
+        y = self._conv(x, "conv1", 1, self.cv11, dilation=self.atrous)       # stored with cv11 padded to a multiple of 16 (bf16)
+        y = self._ln(y, "conv1_bn", c=self.cv11)
+        self._conv(y, "conv2", self.ksize, self.cvkk, dilation=self.atrous, out=out, out_coff=out_coff, out_slot=out_slot, cin=self.cv11)
         self._ln(out, "conv2_bn", coff=out_coff, c=self.cvkk)
 
 
@@ -218,12 +250,13 @@ class residual_S(_Layer):
     def forward(self, x):
         n, h, w, _ = x.shape
         K, c = self.kpaths, self.cardinal_blocks[0].cvkk
-        u = torch.empty(n, h, w, K * c, dtype=x.dtype, device=x.device)            # the K cardinals write their slice: no concat pass
+        cp = ops.pad_channels(c, x.dtype)                                          # slot width of one cardinal in u / v (bf16: multiple of 16)
+        u = torch.zeros(n, h, w, K * cp, dtype=x.dtype, device=x.device)           # the K cardinals write their slot: no concat pass
         for k, blk in enumerate(self.cardinal_blocks):
-            blk.features(x, u, k * c)
+            blk.features(x, u, k * cp, cp)
         per = [blk.split.params() for blk in self.cardinal_blocks]
         stacked = [torch.stack([p[i] for p in per]).contiguous() for i in range(6)]
-        v, att = ops.splitatt_shared(u, K, self.radix, *stacked, act=ACT_LRELU, return_att=True)
+        v, att = ops.splitatt_shared(u, K, self.radix, *stacked, act=ACT_LRELU, return_att=True, c=c)
         if self._s.recording:
             s = self._s
 
@@ -231,7 +264,7 @@ class residual_S(_Layer):
                 dv = s.gget(v)
                 if dv is None:
                     return
-                du, g = ops.splitatt_shared_bwd(u, dv, att, K, self.radix, *stacked[:5], act=ACT_LRELU)
+                du, g = ops.splitatt_shared_bwd(u, dv, att, K, self.radix, *stacked[:5], act=ACT_LRELU, c=c)
                 s.gacc(u, du)
                 c2 = c // 2
                 for k_, blk in enumerate(self.cardinal_blocks):
@@ -242,7 +275,8 @@ class residual_S(_Layer):
             s.tape.append(bwd)
         sc = self._conv(x, "convtmp_sc", 1, self.outchannel, dilation=self.atrous)
         sc = self._ln(sc, "convtmp_scbn")
-        return self._conv(v, "concats_2", self.ksize, self.outchannel, dilation=self.atrous, residual=sc)
+        cmap = [k * cp + i for k in range(K) for i in range(c)] if cp != c else None      # logical channel -> position in the slotted record
+        return self._conv(v, "concats_2", self.ksize, self.outchannel, dilation=self.atrous, residual=sc, cin=K * c, cmap=cmap)
 
     __call__ = forward
 
@@ -268,10 +302,17 @@ class ResNest(_Layer):
     def forward(self, x, record=False):
         """record=True keeps what backward() needs (the tape of this call)"""
         x = torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=self.device, dtype=self.tdtype).contiguous()
+        cin = x.shape[3]
+        cpad = ops.pad_channels(cin, self.tdtype)
+        if cpad != cin:                                    # the 10 input planes are stored as 16-channel records (zero pad lanes)
+            xp = torch.zeros(*x.shape[:3], cpad, dtype=x.dtype, device=x.device)
+            xp[..., :cin] = x
+            x = xp
         if record:
             self._s.start_recording()
         x0 = x
-        x = self._conv(x, "initial_conv", 3, 16, act=ACT_LRELU)
+        self._cin = cin
+        x = self._conv(x, "initial_conv", 3, 16, act=ACT_LRELU, cin=cin)
         x = self._conv(x, "convtmp_1", 3, 32, bn="convtmp_1bn", act=ACT_LRELU)
         x = self._conv(x, "convtmp_2", 3, 32, bn="convtmp_2bn", act=ACT_LRELU)
         x_1 = self.conv_1(self._pool(x))
@@ -292,7 +333,8 @@ class ResNest(_Layer):
             if d is not None:
                 self._s.gacc(f, dev(d))
         self._s.run_backward()
-        return self._s.gget(x0)
+        g = self._s.gget(x0)
+        return g if g is None or g.shape[3] == self._cin else g[..., :self._cin].contiguous()
 
     def gradients(self):
         """variable name -> fp32 gradient of the last backward() (trainable variables only: no moving statistics)"""

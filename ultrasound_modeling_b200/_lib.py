@@ -173,8 +173,8 @@ SIGNATURES = {
     "tbi_conv2d_wgrad_workspace": (_I64, [_I, _I, _I, _I, _I]),
     "tbi_layernorm_c_fwd": (_I, [_I, _I64, _I, _PV, _VP, _VP, _F, _I, _PV, _VP]),
     "tbi_layernorm_c_bwd": (_I, [_I, _I64, _I, _PV, _PV, _PV, _VP, _F, _I, _PV, _VP, _VP, _VP]),
-    "tbi_splitatt_shared_fwd": (_I, [_I, _I, _I, _I, _I, _I, _I, _PV, _PV, _VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _VP]),
-    "tbi_splitatt_shared_bwd": (_I, [_I, _I, _I, _I, _I, _I, _I, _PV, _PV, _PV, _VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tbi_splitatt_shared_fwd": (_I, [_I, _I, _I, _I, _I, _I, _I, _PV, _PV, _VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _I, _VP]),
+    "tbi_splitatt_shared_bwd": (_I, [_I, _I, _I, _I, _I, _I, _I, _PV, _PV, _PV, _VP, _VP, _VP, _VP, _F, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "tbi_dropout_mask": (_I, [_VP, _I64, C.c_uint64, _VP, _VP]),
     "tbi_cast": (_I, [_I, _I, _I64, _VP, _VP, _VP]),
     "tbi_adam_multi": (_I, [_I64, _VP, _VP, _VP, _VP, _VP, _F, _F, _F, _F, _F, _VP]),

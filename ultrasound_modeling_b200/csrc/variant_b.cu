@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) layernorm_c_bwd_kernel(long long npix, in
 
 // raw[n][ch] += sum over a chunk of pixels of u[n,p,ch]
 template <typename T>
-__global__ void __launch_bounds__(256) shared_gap_kernel(int hw, int C, tbi_view u, float* raw, int pix_per_block) {
+__global__ void __launch_bounds__(256) shared_gap_kernel(int hw, int C, int c, int cpad, tbi_view u, float* raw, int pix_per_block) {
     const int n = blockIdx.y;
     const int pbeg = blockIdx.x * pix_per_block, pend = min(hw, pbeg + pix_per_block);
     const T* ub = (const T*)u.ptr + (size_t)n * hw * u.cstride + u.coff;
@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) shared_gap_kernel(int hw, int C, tbi_view
     if (lp >= pl) return;
     for (int ch = lc; ch < C; ch += cl) {
         float s = 0.f;
-        for (int p = pbeg + lp; p < pend; p += pl) s += ldf(ub + (size_t)p * u.cstride + ch);
+        const int pch = ch + (ch / c) * cpad;               // cardinal k's channels start at k*(c + cpad) in a padded record
+        for (int p = pbeg + lp; p < pend; p += pl) s += ldf(ub + (size_t)p * u.cstride + pch);
         atomicAdd(raw + (size_t)n * C + ch, s);
     }
 }
@@ -158,18 +159,19 @@ __global__ void __launch_bounds__(128) shared_fc_kernel(int hw, int K, int R, in
 
 // v[n,p,ch] = u[n,p,ch] * att[n][ch]
 template <typename T>
-__global__ void __launch_bounds__(256) shared_scale_kernel(long long total, int hw, int C, tbi_view u, tbi_view v, const float* __restrict__ att) {
+__global__ void __launch_bounds__(256) shared_scale_kernel(long long total, int hw, int C, int c, int cpad, tbi_view u, tbi_view v, const float* __restrict__ att) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ch = (int)(i % C); const long long pg = i / C; const int n = (int)(pg / hw);
-        const float x = ldf((const T*)u.ptr + (size_t)pg * u.cstride + u.coff + ch);
-        stf((T*)v.ptr + (size_t)pg * v.cstride + v.coff + ch, x * att[(size_t)n * C + ch]);
+        const int pch = ch + (ch / c) * cpad;
+        const float x = ldf((const T*)u.ptr + (size_t)pg * u.cstride + u.coff + pch);
+        stf((T*)v.ptr + (size_t)pg * v.cstride + v.coff + pch, x * att[(size_t)n * C + ch]);
     }
 }
 
 // ---- backward of the shared-input split attention --------------------------------------------------------------------
 // su[n][ch] += sum_p u ; sdu[n][ch] += sum_p dv*u   (one pass over u and dv)
 template <typename T>
-__global__ void __launch_bounds__(256) shared_bwd_reduce_kernel(int hw, int C, tbi_view u, tbi_view dv, float* su, float* sdu, int pix_per_block) {
+__global__ void __launch_bounds__(256) shared_bwd_reduce_kernel(int hw, int C, int c, int cpad, tbi_view u, tbi_view dv, float* su, float* sdu, int pix_per_block) {
     const int n = blockIdx.y;
     const int pbeg = blockIdx.x * pix_per_block, pend = min(hw, pbeg + pix_per_block);
     const T* ub = (const T*)u.ptr + (size_t)n * hw * u.cstride + u.coff;
@@ -179,9 +181,10 @@ __global__ void __launch_bounds__(256) shared_bwd_reduce_kernel(int hw, int C, t
     if (lp >= pl) return;
     for (int ch = lc; ch < C; ch += cl) {
         float s = 0.f, sd = 0.f;
+        const int pch = ch + (ch / c) * cpad;
         for (int p = pbeg + lp; p < pend; p += pl) {
-            const float x = ldf(ub + (size_t)p * u.cstride + ch);
-            s += x; sd = fmaf(ldf(db + (size_t)p * dv.cstride + ch), x, sd);
+            const float x = ldf(ub + (size_t)p * u.cstride + pch);
+            s += x; sd = fmaf(ldf(db + (size_t)p * dv.cstride + pch), x, sd);
         }
         atomicAdd(su + (size_t)n * C + ch, s);
         atomicAdd(sdu + (size_t)n * C + ch, sd);
@@ -271,12 +274,13 @@ __global__ void __launch_bounds__(128) shared_fc_bwd_kernel(int hw, int K, int R
 
 // du[n,p,ch] = dv[n,p,ch] * att[n][ch] + dgs[n][ch]
 template <typename T>
-__global__ void __launch_bounds__(256) shared_du_kernel(long long total, int hw, int C, tbi_view dv, tbi_view du, const float* __restrict__ att,
+__global__ void __launch_bounds__(256) shared_du_kernel(long long total, int hw, int C, int c, int cpad, tbi_view dv, tbi_view du, const float* __restrict__ att,
                                                         const float* __restrict__ dgs) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int ch = (int)(i % C); const long long pg = i / C; const int n = (int)(pg / hw);
-        const float g = ldf((const T*)dv.ptr + (size_t)pg * dv.cstride + dv.coff + ch);
-        stf((T*)du.ptr + (size_t)pg * du.cstride + du.coff + ch, fmaf(g, att[(size_t)n * C + ch], dgs[(size_t)n * C + ch]));
+        const int pch = ch + (ch / c) * cpad;
+        const float g = ldf((const T*)dv.ptr + (size_t)pg * dv.cstride + dv.coff + pch);
+        stf((T*)du.ptr + (size_t)pg * du.cstride + du.coff + pch, fmaf(g, att[(size_t)n * C + ch], dgs[(size_t)n * C + ch]));
     }
 }
 
@@ -319,10 +323,12 @@ extern "C" int tbi_layernorm_c_bwd(int dtype, int64_t npix, int c, const tbi_vie
 
 extern "C" int tbi_splitatt_shared_fwd(int dtype, int n, int h, int w, int kpaths, int radix, int c, const tbi_view* u, const tbi_view* v,
                                        const float* w1, const float* b1, const float* ln_gamma, const float* ln_beta, float ln_eps, int act,
-                                       const float* w2, const float* b2, float* att, void* stream) {
+                                       const float* w2, const float* b2, float* att, int cgroup, void* stream) {
     TBI_CHECK(u && v && w1 && b1 && ln_gamma && ln_beta && w2 && b2 && att, TBI_ERR_BAD_SHAPE, "splitatt_shared_fwd: null argument");
-    TBI_CHECK(c >= 2 && kpaths >= 1 && radix >= 1 && u->c == kpaths * c && v->c == kpaths * c, TBI_ERR_BAD_SHAPE,
-              "splitatt_shared_fwd: u/v must have kpaths*c = %d channels (got %d, %d)", kpaths * c, u->c, v->c);
+    if (cgroup <= 0) cgroup = c;
+    const int cpad = cgroup - c;
+    TBI_CHECK(c >= 2 && kpaths >= 1 && radix >= 1 && cpad >= 0 && u->c == kpaths * cgroup && v->c == kpaths * cgroup, TBI_ERR_BAD_SHAPE,
+              "splitatt_shared_fwd: u/v must have kpaths*cgroup = %d channels (got %d, %d)", kpaths * cgroup, u->c, v->c);
     TBI_CHECK(c <= 2048, TBI_ERR_UNSUPPORTED, "splitatt_shared_fwd: c = %d > 2048", c);
     cudaStream_t s = (cudaStream_t)stream;
     const int hw = h * w, C = kpaths * c;
@@ -335,13 +341,13 @@ extern "C" int tbi_splitatt_shared_fwd(int dtype, int n, int h, int w, int kpath
     const unsigned ge = grid_cap((long long)n * hw * C, 256 * 4, 16);
     const size_t fsm = (size_t)(c + c / 2 + c + 32) * sizeof(float);
     if (dtype == TBI_F32) {
-        shared_gap_kernel<float><<<gg, 256, 0, s>>>(hw, C, *u, att, ppb);
+        shared_gap_kernel<float><<<gg, 256, 0, s>>>(hw, C, c, cpad, *u, att, ppb);
         shared_fc_kernel<<<dim3((unsigned)n, (unsigned)kpaths), 128, fsm, s>>>(hw, kpaths, radix, c, w1, b1, ln_gamma, ln_beta, ln_eps, act, w2, b2, att);
-        shared_scale_kernel<float><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, *u, *v, att);
+        shared_scale_kernel<float><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, c, cpad, *u, *v, att);
     } else if (dtype == TBI_BF16) {
-        shared_gap_kernel<__nv_bfloat16><<<gg, 256, 0, s>>>(hw, C, *u, att, ppb);
+        shared_gap_kernel<__nv_bfloat16><<<gg, 256, 0, s>>>(hw, C, c, cpad, *u, att, ppb);
         shared_fc_kernel<<<dim3((unsigned)n, (unsigned)kpaths), 128, fsm, s>>>(hw, kpaths, radix, c, w1, b1, ln_gamma, ln_beta, ln_eps, act, w2, b2, att);
-        shared_scale_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, *u, *v, att);
+        shared_scale_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, c, cpad, *u, *v, att);
     } else return tbi_set_error(TBI_ERR_UNSUPPORTED, "splitatt_shared_fwd dtype");
     TBI_CUDA_LAUNCH_CHECK("splitatt_shared_fwd");
     return TBI_OK;
@@ -350,11 +356,13 @@ extern "C" int tbi_splitatt_shared_fwd(int dtype, int n, int h, int w, int kpath
 extern "C" int tbi_splitatt_shared_bwd(int dtype, int n, int h, int w, int kpaths, int radix, int c, const tbi_view* u, const tbi_view* dv,
                                        const tbi_view* du, const float* w1, const float* b1, const float* ln_gamma, const float* ln_beta,
                                        float ln_eps, int act, const float* w2, const float* att, float* dw1, float* db1, float* dln_gamma,
-                                       float* dln_beta, float* dw2, float* db2, float* scratch, void* stream) {
+                                       float* dln_beta, float* dw2, float* db2, float* scratch, int cgroup, void* stream) {
     TBI_CHECK(u && dv && du && w1 && b1 && ln_gamma && ln_beta && w2 && att && dw1 && db1 && dln_gamma && dln_beta && dw2 && db2 && scratch,
               TBI_ERR_BAD_SHAPE, "splitatt_shared_bwd: null argument");
-    TBI_CHECK(c >= 2 && kpaths >= 1 && radix >= 1 && u->c == kpaths * c && dv->c == kpaths * c && du->c == kpaths * c, TBI_ERR_BAD_SHAPE,
-              "splitatt_shared_bwd: u/dv/du must have kpaths*c = %d channels", kpaths * c);
+    if (cgroup <= 0) cgroup = c;
+    const int cpad = cgroup - c;
+    TBI_CHECK(c >= 2 && kpaths >= 1 && radix >= 1 && cpad >= 0 && u->c == kpaths * cgroup && dv->c == kpaths * cgroup && du->c == kpaths * cgroup, TBI_ERR_BAD_SHAPE,
+              "splitatt_shared_bwd: u/dv/du must have kpaths*cgroup = %d channels", kpaths * cgroup);
     TBI_CHECK(c <= 2048, TBI_ERR_UNSUPPORTED, "splitatt_shared_bwd: c = %d > 2048", c);
     cudaStream_t s = (cudaStream_t)stream;
     const int hw = h * w, C = kpaths * c;
@@ -367,13 +375,13 @@ extern "C" int tbi_splitatt_shared_bwd(int dtype, int n, int h, int w, int kpath
     const dim3 gg((unsigned)((hw + ppb - 1) / ppb), (unsigned)n);
     const unsigned ge = grid_cap((long long)n * hw * C, 256 * 4, 16);
     const size_t fsm = (size_t)(2 * c + 3 * (c / 2) + 32) * sizeof(float);
-    if (dtype == TBI_F32) shared_bwd_reduce_kernel<float><<<gg, 256, 0, s>>>(hw, C, *u, *dv, su, sdu, ppb);
-    else if (dtype == TBI_BF16) shared_bwd_reduce_kernel<__nv_bfloat16><<<gg, 256, 0, s>>>(hw, C, *u, *dv, su, sdu, ppb);
+    if (dtype == TBI_F32) shared_bwd_reduce_kernel<float><<<gg, 256, 0, s>>>(hw, C, c, cpad, *u, *dv, su, sdu, ppb);
+    else if (dtype == TBI_BF16) shared_bwd_reduce_kernel<__nv_bfloat16><<<gg, 256, 0, s>>>(hw, C, c, cpad, *u, *dv, su, sdu, ppb);
     else return tbi_set_error(TBI_ERR_UNSUPPORTED, "splitatt_shared_bwd dtype");
     shared_fc_bwd_kernel<<<dim3((unsigned)n, (unsigned)kpaths), 128, fsm, s>>>(hw, kpaths, radix, c, w1, b1, ln_gamma, ln_beta, ln_eps, act, w2, att, su, sdu,
                                                                                dw1, db1, dln_gamma, dln_beta, dw2, db2);
-    if (dtype == TBI_F32) shared_du_kernel<float><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, *dv, *du, att, su);
-    else shared_du_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, *dv, *du, att, su);
+    if (dtype == TBI_F32) shared_du_kernel<float><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, c, cpad, *dv, *du, att, su);
+    else shared_du_kernel<__nv_bfloat16><<<ge, 256, 0, s>>>((long long)n * hw * C, hw, C, c, cpad, *dv, *du, att, su);
     TBI_CUDA_LAUNCH_CHECK("splitatt_shared_bwd");
     return TBI_OK;
 }

@@ -788,6 +788,7 @@ class Engine:
                 c += k
             return c
         n = count(self.prog_prepare) + count(self.prog_fwd) + count(self.prog_loss)
+        n += sum(1 for k in self.keep if k is not None) + 1       # dropout masks + the draw counter
         if train:
-            n += count(self.prog_bwd) + 2 + sum(1 for k in self.keep if k is not None) - 1     # -1: the stem wgrad needs no separate column sum
+            n += count(self.prog_bwd) + 2 - 1                      # Adam + its counter; -1: the stem wgrad needs no separate column sum
         return n

@@ -326,33 +326,43 @@ def layernorm_c_bwd(x, y, dy, gamma, act=ACT_NONE, eps=LN_EPS):
     return dx, dg, db
 
 
-def splitatt_shared(u, kpaths, radix, w1, b1, ln_gamma, ln_beta, w2, b2, act, eps=LN_EPS, return_att=False):
-    """Variant-B split attention (ResNest.py:171-199): R identical inputs, shared dense2.  u: [n,h,w,K*c];
+def splitatt_shared(u, kpaths, radix, w1, b1, ln_gamma, ln_beta, w2, b2, act, eps=LN_EPS, return_att=False, c=None):
+    """Variant-B split attention (ResNest.py:171-199): R identical inputs, shared dense2.  u: [n,h,w,K*cg] with the K cardinals'
+    c channels at offsets k*cg (cg = c unless the slices are zero-padded to a 16-channel multiple, pass c then);
     w1 [K,c,c/2], b1 [K,c/2], ln_gamma/ln_beta [K,c/2], w2 [K,c/2,c], b2 [K,c] (fp32)."""
     L = _lib.lib()
     n, h, w, C_ = u.shape
-    c = C_ // kpaths
-    v = torch.empty_like(u)
-    att = torch.empty(n, C_, dtype=torch.float32, device=u.device)
+    cg = C_ // kpaths
+    c = cg if c is None else c
+    v = torch.zeros_like(u) if cg != c else torch.empty_like(u)          # pad lanes are never written: they must read 0
+    att = torch.empty(n, kpaths * c, dtype=torch.float32, device=u.device)
     args = [_f32(t) for t in (w1, b1, ln_gamma, ln_beta, w2, b2)]
     check(L.tbi_splitatt_shared_fwd(_dt(u), n, h, w, kpaths, radix, c, _vp(view(u)), _vp(view(v)), _p(args[0]), _p(args[1]), _p(args[2]),
-                                    _p(args[3]), eps, act, _p(args[4]), _p(args[5]), _p(att), _st()), "splitatt_shared_fwd")
+                                    _p(args[3]), eps, act, _p(args[4]), _p(args[5]), _p(att), cg, _st()), "splitatt_shared_fwd")
     return (v, att) if return_att else v
 
 
-def splitatt_shared_bwd(u, dv, att, kpaths, radix, w1, b1, ln_gamma, ln_beta, w2, act, eps=LN_EPS):
+def splitatt_shared_bwd(u, dv, att, kpaths, radix, w1, b1, ln_gamma, ln_beta, w2, act, eps=LN_EPS, c=None):
     """backward of splitatt_shared: -> (du, dict of parameter gradients stacked over the K cardinals like the parameters).
     att = the buffer the forward returned with return_att=True."""
     L = _lib.lib()
     n, h, w, C_ = u.shape
-    c = C_ // kpaths
-    du = torch.empty_like(u)
+    cg = C_ // kpaths
+    c = cg if c is None else c
+    du = torch.zeros_like(u) if cg != c else torch.empty_like(u)
     args = [_f32(t) for t in (w1, b1, ln_gamma, ln_beta, w2)]
     z = lambda t: torch.zeros(t.shape, dtype=torch.float32, device=u.device)
     g = dict(w1=z(args[0]), b1=z(args[1]), ln_gamma=z(args[2]), ln_beta=z(args[3]), w2=z(args[4]),
              b2=torch.zeros(kpaths, c, dtype=torch.float32, device=u.device))
-    scratch = torch.empty(2 * n * C_, dtype=torch.float32, device=u.device)
+    scratch = torch.empty(2 * n * kpaths * c, dtype=torch.float32, device=u.device)
     check(L.tbi_splitatt_shared_bwd(_dt(u), n, h, w, kpaths, radix, c, _vp(view(u)), _vp(view(dv)), _vp(view(du)), _p(args[0]), _p(args[1]),
                                     _p(args[2]), _p(args[3]), eps, act, _p(args[4]), _p(att), _p(g["w1"]), _p(g["b1"]), _p(g["ln_gamma"]),
-                                    _p(g["ln_beta"]), _p(g["w2"]), _p(g["b2"]), _p(scratch), _st()), "splitatt_shared_bwd")
+                                    _p(g["ln_beta"]), _p(g["w2"]), _p(g["b2"]), _p(scratch), cg, _st()), "splitatt_shared_bwd")
     return du, g
+
+
+def pad_channels(c: int, dtype) -> int:
+    """physical channel count of a stored activation with c logical channels: bf16 tensors are stored with their channels
+    rounded up to a multiple of 16 (zero pad lanes) so that every pixel record is 16-byte aligned and a whole number of MMA
+    K steps -- what keeps odd-width layers (Variant B: 3/7/10/21/30/63/85/126/255 channels) on the tcgen05 path"""
+    return (c + 15) // 16 * 16 if dtype == torch.bfloat16 else c
