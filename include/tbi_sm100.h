@@ -312,6 +312,27 @@ int tbi_splitatt_shared_bwd(int dtype, int n, int h, int w, int kpaths, int radi
                             const float* att, float* dw1, float* db1, float* dln_gamma, float* dln_beta,
                             float* dw2, float* db2, float* scratch, int cgroup, void* stream);
 
+/* ---- ViT bridge of Variant B (VisionTransformer.py:9-190) -------------------------------------------------------
+ * Multi-head self-attention core for short sequences (the reference: 80 tokens, 4 heads of 128 channels): q, k, v, ctx are
+ * [n, tokens, heads*head_dim] in `dtype` (head h = channels [h*head_dim, (h+1)*head_dim), the reference's split_heads :26-31),
+ * probs fp32 [n, heads, tokens, tokens] = softmax_keys(q k^T * scale) (returned to the caller as the attention weights and
+ * kept for the backward pass); ctx = probs v.  The reference scales by 1/sqrt(num_heads) (:42), so scale is an argument.
+ * One CTA per (image, head) holds Q, K, V and the score matrix in shared memory: tokens*(head_dim+1)*12 + tokens^2*4 bytes
+ * must fit in 220 KB (16 for the backward).  replaces: Attention.forward :33-54 between the four Dense layers.            */
+int tbi_attention_fwd(int dtype, int n, int tokens, int heads, int head_dim, float scale, const void* q, const void* k,
+                      const void* v, void* ctx, float* probs, void* stream);
+int tbi_attention_bwd(int dtype, int n, int tokens, int heads, int head_dim, float scale, const void* q, const void* k,
+                      const void* v, const float* probs, const void* dctx, void* dq, void* dk, void* dv, void* stream);
+/* exact GELU, 0.5 x (1 + erf(x / sqrt 2)) (tf.keras.activations.gelu, Mlp.forward :67-73); bwd: dx = dy * gelu'(x)        */
+int tbi_gelu_fwd(int dtype, int64_t count, const void* x, void* y, void* stream);
+int tbi_gelu_bwd(int dtype, int64_t count, const void* x, const void* dy, void* dx, void* stream);
+/* softmax over nc classes + tf.keras.losses.CategoricalCrossentropy(label_smoothing, reduction=NONE) on the probabilities +
+ * tf.nn.compute_average_loss(global_batch_size) (VisionTransformer.py:205-206,225-227): *loss_sum += sum over the npix pixels
+ * of the per-pixel loss / global_batch (caller zeroes it); probs fp32 [npix, nc]; dlogits (may be NULL) = d loss / d logits.
+ * This is the label-smoothed variant of tbi_softmax_loss_fwd_bwd named in SURVEY 8(b).                                    */
+int tbi_softmax_cce_fwd_bwd(int64_t npix, int nc, float label_smoothing, float global_batch, const float* logits,
+                            const float* y, float* probs, float* loss_sum, float* dlogits, void* stream);
+
 /* x fp32/fp64 host-layout NHWC -> storage dtype (device to device)                               */
 int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void* src, void* dst, void* stream);
 

@@ -94,12 +94,12 @@ class DecoderBlock(_Layer):
 class DecoderCup(_Layer):
     """Decoder.py:98-146."""
 
-    def __init__(self, num_classes, wDecay=None, *, grid=(16, 5), dtype="bf16", device="cuda", seed=0):
-        super().__init__(VariableStore(device, seed), "")
+    def __init__(self, num_classes, wDecay=None, *, grid=(16, 5), dtype="bf16", device="cuda", seed=0, _store=None, _prefix=""):
+        super().__init__(_store if _store is not None else VariableStore(device, seed), _prefix)
         self.num_classes, self.wDecay, self.grid = num_classes, wDecay, tuple(grid)
         self.tdtype = torch.bfloat16 if dtype in ("bf16", torch.bfloat16) else torch.float32
         self.device = torch.device(device)
-        self.blocks = [DecoderBlock(c, wDecay, _store=self._s, _prefix=f"block_{i}/") for i, c in enumerate((256, 128, 64))]
+        self.blocks = [DecoderBlock(c, wDecay, _store=self._s, _prefix=f"{_prefix}block_{i}/") for i, c in enumerate((256, 128, 64))]
 
     def load_variables(self, variables):
         self._s.load(variables)
@@ -125,7 +125,7 @@ class DecoderCup(_Layer):
             views.append(v)
             return v
 
-        if record:
+        if s.recording:
             def gather():                                                           # first on the tape = last to run
                 g = None
                 for v in views:
@@ -133,6 +133,8 @@ class DecoderCup(_Layer):
                     if gv is not None:
                         g = gv.reshape(y.shape) if g is None else g + gv.reshape(y.shape)
                 self._dhidden = g
+                if g is not None:
+                    s.gacc(y, g)                                                    # for a producer of the tokens on the same tape (the ViT bridge)
             s.tape.append(gather)
         x = token_view(n, gh, gw, -1)
         x = self._conv(x, "conv_more", 3, 256)
@@ -144,7 +146,7 @@ class DecoderCup(_Layer):
             skips.append(skip)
             x = blk.forward(x, skip, extra)
             extra = token_view(n, gh * 2 ** (i + 1), gw * 2 ** (i + 1), -1)         # Decoder.py:140-141, consumed by the next layer
-        z = _convt(self, x, extra, "head", self.num_classes, out_f32=True)
+        z = _convt(self, x, extra, self._p + "head", self.num_classes, out_f32=True)
         self._io = (z, skips)
         if logits:
             return z

@@ -42,10 +42,38 @@ class VariableStore:
         self.tgrads: Dict[int, torch.Tensor] = {}
         self._alive = []
         self.grads: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self.flat = None             # set by freeze(): dict(params, grads, m, v, names, gviews)
 
     def start_recording(self):
         self.recording = True
         self.tape.clear(); self.tgrads.clear(); self._alive.clear(); self.grads.clear()
+        if self.flat is not None:
+            self.flat["grads"].zero_()
+
+    def freeze(self):
+        """Move every TRAINABLE variable into one flat fp32 buffer (the tensors in ``vars`` become views of it) with parallel
+        flat buffers for gradients and the two Adam moments: one fused optimizer launch, one contiguous all-reduce, and the
+        global gradient norm is one reduction.  Call after the first forward pass (variables are created lazily)."""
+        if self.flat is not None:
+            return self.flat
+        names = [k for k in self.vars if not (k.endswith("/moving_mean") or k.endswith("/moving_variance"))]
+        offs, total = {}, 0
+        for k in names:
+            offs[k] = total
+            total += (self.vars[k].numel() + 3) // 4 * 4                 # 16-byte aligned slices
+        dev = self.device
+        P = torch.zeros(total, dtype=torch.float32, device=dev)
+        G = torch.zeros(total, dtype=torch.float32, device=dev)
+        gviews = {}
+        for k in names:
+            t = self.vars[k]
+            view = P[offs[k]:offs[k] + t.numel()].view(t.shape)
+            view.copy_(t)
+            self.vars[k] = view
+            gviews[k] = G[offs[k]:offs[k] + t.numel()].view(t.shape)
+        self.flat = dict(params=P, grads=G, m=torch.zeros_like(P), v=torch.zeros_like(P), names=names, gviews=gviews, offsets=offs,
+                         step=torch.zeros(1, dtype=torch.int32, device=dev))
+        return self.flat
 
     def gacc(self, t: torch.Tensor, g: torch.Tensor, coff: int = 0):
         """add g into channels [coff, coff + g.channels) of the gradient buffer of activation buffer t"""
@@ -66,6 +94,11 @@ class VariableStore:
         return G if (coff == 0 and c == G.shape[-1]) else G[..., coff:coff + c].contiguous()
 
     def pacc(self, name: str, g: torch.Tensor):
+        if self.flat is not None and name in self.flat["gviews"]:
+            view = self.flat["gviews"][name]
+            view.add_(g.reshape(view.shape))
+            self.grads[name] = view
+            return
         self.grads[name] = self.grads[name] + g if name in self.grads else g.clone()
 
     def run_backward(self):
@@ -96,7 +129,11 @@ class VariableStore:
 
     def load(self, variables: Dict[str, torch.Tensor]):
         for k, v in variables.items():
-            self.vars[k] = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).detach().to(device=self.device, dtype=torch.float32).contiguous()
+            t = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v).detach().to(device=self.device, dtype=torch.float32).contiguous()
+            if self.flat is not None and k in self.vars and k in self.flat["gviews"]:
+                self.vars[k].copy_(t.reshape(self.vars[k].shape))        # frozen: the variable is a view of the flat buffer
+            else:
+                self.vars[k] = t
 
 
 class _Layer:
@@ -284,13 +321,14 @@ class residual_S(_Layer):
 class ResNest(_Layer):
     """ResNest.py:4-58."""
 
-    def __init__(self, height, width, channel, ksize, radix=4, kpaths=4, wDecay=None, *, dtype="bf16", device="cuda", seed=0):
-        store = VariableStore(device, seed)
-        super().__init__(store, "")
+    def __init__(self, height, width, channel, ksize, radix=4, kpaths=4, wDecay=None, *, dtype="bf16", device="cuda", seed=0,
+                 _store=None, _prefix=""):
+        store = _store if _store is not None else VariableStore(device, seed)
+        super().__init__(store, _prefix)
         self.height, self.width, self.channel, self.ksize, self.radix, self.kpaths, self.wDecay = height, width, channel, ksize, radix, kpaths, wDecay
         self.tdtype = torch.bfloat16 if dtype in ("bf16", torch.bfloat16) else torch.float32
         self.device = torch.device(device)
-        mk = lambda name, out: residual_S(ksize=ksize, outchannel=out, radix=radix, kpaths=kpaths, wDecay=wDecay, _store=store, _prefix=name + "/")
+        mk = lambda name, out: residual_S(ksize=ksize, outchannel=out, radix=radix, kpaths=kpaths, wDecay=wDecay, _store=store, _prefix=_prefix + name + "/")
         self.conv_1, self.conv_2, self.conv_3, self.conv_4 = mk("conv_1", 64), mk("conv_2", 128), mk("conv_3", 256), mk("conv_4", 512)
 
     def load_variables(self, variables):

@@ -366,3 +366,50 @@ def pad_channels(c: int, dtype) -> int:
     rounded up to a multiple of 16 (zero pad lanes) so that every pixel record is 16-byte aligned and a whole number of MMA
     K steps -- what keeps odd-width layers (Variant B: 3/7/10/21/30/63/85/126/255 channels) on the tcgen05 path"""
     return (c + 15) // 16 * 16 if dtype == torch.bfloat16 else c
+
+
+# ------------------------------------------------------------------------------------------ ViT bridge (VisionTransformer.py)
+def attention(q, k, v, heads, scale):
+    """softmax(q k^T * scale) v per head; q, k, v: [n, tokens, heads*d] -> (ctx [n, tokens, heads*d], probs fp32 [n, heads, tokens, tokens])"""
+    L = _lib.lib()
+    n, t, c = q.shape
+    ctx = torch.empty_like(q)
+    probs = torch.empty(n, heads, t, t, dtype=torch.float32, device=q.device)
+    check(L.tbi_attention_fwd(_dt(q), n, t, heads, c // heads, float(scale), _p(q), _p(k), _p(v), _p(ctx), _p(probs), _st()), "attention_fwd")
+    return ctx, probs
+
+
+def attention_bwd(q, k, v, probs, dctx, heads, scale):
+    L = _lib.lib()
+    n, t, c = q.shape
+    dq, dk, dv = torch.empty_like(q), torch.empty_like(q), torch.empty_like(q)
+    check(L.tbi_attention_bwd(_dt(q), n, t, heads, c // heads, float(scale), _p(q), _p(k), _p(v), _p(probs), _p(dctx.contiguous()), _p(dq), _p(dk), _p(dv), _st()),
+          "attention_bwd")
+    return dq, dk, dv
+
+
+def gelu(x):
+    L = _lib.lib()
+    y = torch.empty_like(x)
+    check(L.tbi_gelu_fwd(_dt(x), x.numel(), _p(x), _p(y), _st()), "gelu_fwd")
+    return y
+
+
+def gelu_bwd(x, dy):
+    L = _lib.lib()
+    dx = torch.empty_like(x)
+    check(L.tbi_gelu_bwd(_dt(x), x.numel(), _p(x), _p(dy.contiguous()), _p(dx), _st()), "gelu_bwd")
+    return dx
+
+
+def softmax_cce(logits, y, label_smoothing, global_batch, need_grad=True):
+    """softmax + label-smoothed CategoricalCrossentropy / global_batch (VisionTransformer.py:205-206,225-227)
+    -> (probs, scalar loss tensor, dlogits or None)"""
+    L = _lib.lib()
+    nc = logits.shape[-1]
+    npix = logits.numel() // nc
+    probs = torch.empty_like(logits)
+    loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    dlog = torch.empty_like(logits) if need_grad else None
+    check(L.tbi_softmax_cce_fwd_bwd(npix, nc, float(label_smoothing), float(global_batch), _p(logits), _p(y), _p(probs), _p(loss), _p(dlog), _st()), "softmax_cce")
+    return probs, loss, dlog
