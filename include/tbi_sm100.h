@@ -333,6 +333,27 @@ int tbi_gelu_bwd(int dtype, int64_t count, const void* x, const void* dy, void* 
 int tbi_softmax_cce_fwd_bwd(int64_t npix, int nc, float label_smoothing, float global_batch, const float* logits,
                             const float* y, float* probs, float* loss_sum, float* dlogits, void* stream);
 
+/* ---- device-side data path and evaluator epilogue --------------------------------------------
+ * label2vec (Dataset.py:41-52, Dataset_2.py:6-20): scalar label map [npix] -> soft one-hot fp32 [npix, num_classes]
+ *   3 classes: c2 = min(label-1, 1) where label >= 1.05; c1 = 1 - c2 where label > 0.95; c0 = 1 where label <= 0.95
+ *   2 classes: (1 - label, label)                                                                                     */
+int tbi_label2vec(int64_t npix, int num_classes, const float* label, float* y, void* stream);
+/* DataAugs.dataAug (DataAugs.py:82-102) for a whole device-resident batch, out of place: x [n,h,w,c], label [n,h,w] fp32.
+ * params: int32 [n][16], one sample's decisions in the order the reference draws them:
+ *   [0] imageReduc on (r%3 != 0)  [1] clips (r%3)  [2..5],[6..9] clip k = (row, column, half height, half width)
+ *   [10] shift on (t%2)  [11] rows  [12] columns  [13] direction  [14] noise on (t%3 != 0)
+ * The stages are evaluated per output pixel at the source pixel it reads: imageReduc zeroes the image where the label is 0
+ * (its erosion loop never fires in the reference), clip zeroes image and label in a rectangle, shift translates both with
+ * zero fill, noisy adds N(0,1)/5000 (counter-based generator keyed by seed).  The reference's loop bounds (rows/columns
+ * H-1 / W-1 are skipped by clip and shift) are reproduced.                                                                */
+int tbi_data_aug(int n, int h, int w, int c, const float* x, const float* label, const int32_t* params, uint64_t seed,
+                 float* x_out, float* label_out, void* stream);
+/* evaluator epilogue (TBIEvaluator.py:238-252): probs = softmax(logits) (may be NULL), prob_out = probs[..., -1],
+ * prob_o = 1 - p0 - 0.5 p1 + p2 (may be NULL)                                                                             */
+int tbi_softmax_prob_maps(int64_t npix, int nc, const float* logits, float* probs, float* prob_out, float* prob_o, void* stream);
+/* brain-mask pre-pass (TBIEvaluator.py:225-231): x[pixel, :] = 0 where round(mask_probs[pixel, 0]) == 1                  */
+int tbi_apply_brain_mask(int64_t npix, int mask_classes, int c, const float* mask_probs, float* x, void* stream);
+
 /* x fp32/fp64 host-layout NHWC -> storage dtype (device to device)                               */
 int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void* src, void* dst, void* stream);
 

@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 LIB_PATH = _PKG / "libtbi_sm100.so"
 HASH_PATH = _PKG / "libtbi_sm100.so.hash"
-SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_halo.cu", "tapwgrad_tc.cu", "tapwgrad_tc2.cu", "tapwgrad_small.cu", "direct_small.cu", "splitatt_fused.cu", "bandwidth.cu", "variant_b.cu", "vit.cu"]
+SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_halo.cu", "tapwgrad_tc.cu", "tapwgrad_tc2.cu", "tapwgrad_small.cu", "direct_small.cu", "splitatt_fused.cu", "bandwidth.cu", "variant_b.cu", "vit.cu", "data.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -180,6 +180,10 @@ SIGNATURES = {
     "tbi_gelu_fwd": (_I, [_I, _I64, _VP, _VP, _VP]),
     "tbi_gelu_bwd": (_I, [_I, _I64, _VP, _VP, _VP, _VP]),
     "tbi_softmax_cce_fwd_bwd": (_I, [_I64, _I, _F, _F, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tbi_label2vec": (_I, [_I64, _I, _VP, _VP, _VP]),
+    "tbi_data_aug": (_I, [_I, _I, _I, _I, _VP, _VP, _VP, C.c_uint64, _VP, _VP, _VP]),
+    "tbi_softmax_prob_maps": (_I, [_I64, _I, _VP, _VP, _VP, _VP, _VP]),
+    "tbi_apply_brain_mask": (_I, [_I64, _I, _I, _VP, _VP, _VP]),
     "tbi_dropout_mask": (_I, [_VP, _I64, C.c_uint64, _VP, _VP]),
     "tbi_cast": (_I, [_I, _I, _I64, _VP, _VP, _VP]),
     "tbi_adam_multi": (_I, [_I64, _VP, _VP, _VP, _VP, _VP, _F, _F, _F, _F, _F, _VP]),
