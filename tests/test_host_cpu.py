@@ -68,6 +68,18 @@ def test_plan_buckets_tiles_the_buffer():
     assert plan_buckets(marks, 1000, 10 ** 9) == [(20, 0, 1000)]
 
 
+def test_plan_buckets_at_named_boundaries():
+    from ultrasound_modeling_b200.parallel import plan_buckets_at
+    marks = [(3, 900), (5, 700), (9, 650), (12, 100), (20, 0)]
+    assert plan_buckets_at(marks, 1000, (700, 100)) == [(5, 700, 1000), (12, 100, 700), (20, 0, 100)]
+    assert plan_buckets_at(marks, 1000, (800,)) == [(5, 800, 1000), (20, 0, 800)]           # a cut between marks waits for the next mark
+    assert plan_buckets_at(marks, 1000, ()) == [(20, 0, 1000)]
+    # the engine's cuts: decoder | two deepest encoder stages | rest, tiling the flat buffer
+    e = Engine(256, 256, 1, 3, 3, 2, 1, layout_only=True)
+    hi, lo = e.bucket_cuts
+    assert 0 < lo < hi < e.P.total and (e.P.total - hi) * 4 > 80 << 20 and lo * 4 < 4 << 20
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 

@@ -201,6 +201,10 @@ class Engine:
             self.ups.append(dict(layer=up, drop=drop, cin=cin, out=out))
             cin = out + SKIP_C[4 - i]
         self.head = add(ConvLayer("f_tran", "convt", 4, cin, self.num_class, keras=[("f_tran", 0, self.num_class)]))
+        # all-reduce bucket boundaries for data parallelism (parallel.GradSync), as flat offsets: [upsample_0 .. head] (~85 MiB,
+        # final once upsample_0's weight gradient is done, a little over half way through the backward), [conv3_2, conv4_1]
+        # (~17 MiB), and the rest (~3 MiB) at the end of the backward
+        self.bucket_cuts = (self.P.specs["upsample_0/w"].offset, self.P.specs["conv3_2/c1/w"].offset)
 
     def _alloc_params(self, seed):
         dev = self.device

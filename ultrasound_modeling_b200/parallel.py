@@ -33,6 +33,25 @@ def plan_buckets(marks: Sequence[Tuple[int, int]], total: int, bucket_elems: int
     return out
 
 
+def plan_buckets_at(marks: Sequence[Tuple[int, int]], total: int, cuts: Sequence[int]) -> List[Tuple[int, int, int]]:
+    """Buckets with boundaries at the given flat offsets (descending = backward order): bucket i is all-reduced as soon as the
+    backward program has finalised every gradient at offset >= cuts[i].  Same output format as plan_buckets."""
+    out: List[Tuple[int, int, int]] = []
+    hi = total
+    want = sorted((c for c in set(cuts) if 0 < c < total), reverse=True)
+    for calls, wm in marks:
+        wm = min(wm, hi)
+        while want and wm <= want[0]:
+            lo = want.pop(0)
+            if hi > lo:
+                out.append((calls, lo, hi)); hi = lo
+        if wm == 0 and hi > 0:
+            out.append((calls, 0, hi)); hi = 0
+    if hi > 0:
+        out.append((marks[-1][0] if marks else 0, 0, hi))
+    return out
+
+
 class GradSync:
     """average=True (default): Adam sees the MEAN of the per-replica gradients, which is what the reference's data-parallel
     driver computes -- each replica's loss is divided by the global batch (compute_average_loss, VisionTransformer.py:225-227)
@@ -147,5 +166,13 @@ class GradSync:
     def _ensure_plan(self, engine):
         key = (id(engine), engine.gen)
         if self._plan_key != key:
-            self._plan = plan_buckets(engine.bwd_marks, engine.P.total, self.bucket_elems)
+            cuts = getattr(engine, "bucket_cuts", None)
+            if cuts and os.environ.get("TBI_BUCKET_MB") is None:
+                # boundaries where the backward's TIMELINE makes them free (Engine.bucket_cuts): the decoder's transposed convs
+                # hold ~80 % of the gradient bytes and are final after ~55 % of the backward, the two deepest encoder stages
+                # most of the rest; what is left for the end of the backward (the wide, slow, nearly parameter-free
+                # full-resolution layers) is a few MB, so the exposed tail all-reduce is short
+                self._plan = plan_buckets_at(engine.bwd_marks, engine.P.total, cuts)
+            else:
+                self._plan = plan_buckets(engine.bwd_marks, engine.P.total, self.bucket_elems)
             self._plan_key = key
