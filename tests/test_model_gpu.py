@@ -200,13 +200,15 @@ def test_cuda_graph_replay_equals_eager(ResNest):
 
 
 def test_head_forward_as_gemm_plus_scatter(ResNest, monkeypatch):
-    """tbi_convt_scatter_y + pack mode 3 (engine experiment TBI_HEAD_FWD_GEMM, off by default): the head's transposed conv as one
-    GEMM per input pixel followed by the 4-tap scatter gives the same logits as the per-phase transposed conv -- to fp32
-    rounding with Y kept in fp32, to bf16 rounding of the four terms with Y in bf16."""
+    """tbi_convt_scatter_y + pack mode 3 (the engine's default for the bf16 head; TBI_HEAD_FWD_GEMM=0 turns it off): the head's
+    transposed conv as one GEMM per input pixel followed by the 4-tap scatter gives the same logits as the per-phase
+    transposed conv -- to fp32 rounding with Y kept in fp32, to bf16 rounding of the four terms with Y in bf16."""
     x, y = O.synthetic_batch(2, 64, 64)
     masks = O.dropout_masks(2, 64, 64)
+    monkeypatch.setenv("TBI_HEAD_FWD_GEMM", "0")
     _, base = build_pair(ResNest, 64, 2, 1, "bf16", graph=False)
     _, _, p0 = base.step(x, y, train=False, dropout_masks=masks)
+    assert not base.engine.head_fwd_gemm
     for mode, tol in (("1", 5e-6), ("bf16", 1e-2)):
         monkeypatch.setenv("TBI_HEAD_FWD_GEMM", mode)
         _, net = build_pair(ResNest, 64, 2, 1, "bf16", graph=False)

@@ -42,6 +42,7 @@ struct alignas(64) HaloParams {
     int a_cbase[2], a_cpix[2];
     int out_stride, ph_off_y[4], ph_off_x[4];
     int narrow;
+    int f32wide;                   // fp32 output, 16-byte vector stores from the accumulator registers (bias only)
     int resident, nslabs;          // weights-resident mode: a CTA keeps one (N tile, group, phase) weight slab in smem
     int sh_x, sh_y;                // log2(tiles_x), log2(tiles_y) when both are powers of two, else -1 (divide)
     int flat;                      // resident + one halo per chunk + (ntaps, ksteps) has an unrolled issue loop
@@ -255,7 +256,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
         const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
         const int ox = gx * p.out_stride + (p.nphase > 1 ? p.ph_off_x[t.ph] : p.epi.out_off_x);
         RowCtx rc{};
-        if (valid && !p.narrow) {
+        if (valid && !p.narrow && !p.f32wide) {
             rc = make_row_ctx(p.epi, n, oy, ox);
             if (rc.bias) rc.bias = sbias;
         }
@@ -276,7 +277,19 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
                     if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(te_addr[buf & 1u]); else tc::mbar_arrive(&R.t_empty[buf]); }
                     trace(tr, 2, acc_it, 3);
                 }
-                if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + c, p.cout_g, t.cg * p.cout_g);
+                if (valid && p.f32wide) {
+                    // fp32 row of this pixel, columns [nc0 + c, +32) clipped to cout_g (a multiple of 4)
+                    float* o = (float*)p.epi.out.ptr + pix_off(p.epi.out, n, oy, ox) + t.nc0 + c;
+                    const float* bsm = p.epi.bias ? sbias + t.nc0 + c : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        if (t.nc0 + c + j < p.cout_g) {
+                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                            if (bsm) { v.x += bsm[j]; v.y += bsm[j + 1]; v.z += bsm[j + 2]; v.w += bsm[j + 3]; }
+                            *reinterpret_cast<float4*>(o + j) = v;
+                        }
+                    }
+                } else if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + c, p.cout_g, t.cg * p.cout_g);
             }
             trace(tr, 2, acc_it, 4);
         } else {
@@ -710,6 +723,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     p.kc = kc; p.nchunks = d->cin_g / kc; p.row_bytes = kc * 2;
     p.ngroups = tp.ngroups; p.ntaps = d->ntaps; p.pitch = TW + tp.ex;
     p.narrow = tbi_tc_narrow(d) ? 1 : 0;
+    p.f32wide = tbi_tc_f32wide(d) ? 1 : 0;
     p.epi = d->epi;
     p.out_stride = d->nphase > 1 ? 2 : (d->epi.out_stride ? d->epi.out_stride : 1);
     for (int gi = 0; gi < tp.ngroups; ++gi) { p.g_ox[gi] = tp.ox[gi]; p.g_oy[gi] = tp.oy[gi]; p.g_ax[gi] = tp.ax[gi]; p.g_ay[gi] = tp.ay[gi]; }

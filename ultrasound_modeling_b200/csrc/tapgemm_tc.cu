@@ -248,9 +248,10 @@ bool tbi_tapgemm_tc_supported(const tbi_tapgemm* d, const char** why) {
     if (!aligned_view(d->src[0]) || !aligned_view(d->src[1])) NO("source view not 16-byte aligned");
     if (d->in_stride == 2 && ((d->src[0].h | d->src[0].w) & 1)) NO("stride-2 gather needs even source dims");
     const tbi_epilogue& e = d->epi;
-    if (e.out_f32 && !narrow) NO("fp32 output");
+    const bool f32wide = tbi_tc_f32wide(d);
+    if (e.out_f32 && !narrow && !f32wide) NO("fp32 output");
     if (e.act != TBI_ACT_NONE && e.dact != TBI_ACT_NONE) NO("activation and activation-derivative in one epilogue");
-    if (!narrow) {
+    if (!narrow && !f32wide) {
         if (!aligned_view(e.out) || !aligned_view(e.residual) || !aligned_view(e.dact_ref) || !aligned_view(e.out2) || !aligned_view(e.residual2))
             NO("epilogue view not 16-byte aligned");
         if (e.split_c % 8 != 0) NO("split_c");

@@ -82,8 +82,18 @@ __device__ __forceinline__ void epilogue_store(const tbi_epilogue& e, int n, int
 // "narrow" tensor-core epilogue: 16-column accumulator tiles written element by element through epilogue_store() (any output
 // dtype).  Used when there are fewer than 8 output channels (the 3-class head) and for fp32 outputs of up to 64 columns (the
 // head's forward as a per-input-pixel GEMM, engine.py) -- the vectorised epilogue writes bf16 only.
+bool tbi_tapgemm_halo_supported(const tbi_tapgemm* d);          // persistent halo-addressed variant (spatial >= 16x8)
+// "wide fp32" epilogue of the halo kernel: fp32 outputs written as 16-byte vectors straight from the accumulator registers
+// (bias only: no activation, residual, act', dropout or split).  Used by the head's forward as a per-input-pixel GEMM
+// (48 fp32 columns), where the element-wise narrow epilogue cost more than the 16x fewer MMAs saved.
+static inline bool tbi_tc_f32wide(const tbi_tapgemm* d) {
+    const tbi_epilogue& e = d->epi;
+    return d->groups == 1 && e.out_f32 && d->cout_g >= 16 && d->cout_g % 4 == 0 && e.act == TBI_ACT_NONE && e.dact == TBI_ACT_NONE &&
+           !e.residual.ptr && !e.drop_keep && e.split_c == 0 && e.out.cstride % 4 == 0 && e.out.coff % 4 == 0 &&
+           ((uintptr_t)e.out.ptr & 15) == 0 && tbi_tapgemm_halo_supported(d);
+}
 static inline bool tbi_tc_narrow(const tbi_tapgemm* d) {
-    return d->groups == 1 && (d->cout_g < 8 || (d->epi.out_f32 && d->cout_g <= 64));
+    return d->groups == 1 && (d->cout_g < 8 || (d->epi.out_f32 && d->cout_g <= 64 && !tbi_tc_f32wide(d)));
 }
 
 // entry points implemented per translation unit
@@ -101,7 +111,6 @@ bool tbi_tapwgrad_small_supported(const tbi_tapwgrad* d);      // few-input-chan
 int tbi_tapwgrad_small(const tbi_tapwgrad* d, cudaStream_t s);
 int tbi_splitatt_fwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, cudaStream_t s);     // 1 launched, 0 not applicable
 int tbi_splitatt_bwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* dv, const tbi_view* du, float* scratch, cudaStream_t s);
-bool tbi_tapgemm_halo_supported(const tbi_tapgemm* d);          // persistent halo-addressed variant (spatial >= 16x8)
 int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s);
 int tbi_tapgemm_direct(const tbi_tapgemm* d, cudaStream_t s);   // few-input-channel direct conv (stem)
 int tbi_tapwgrad_direct(const tbi_tapwgrad* d, cudaStream_t s);

@@ -391,14 +391,13 @@ class Engine:
         if self.head_gather:
             self.head_g = torch.zeros(n, H // 2, W // 2, 64, dtype=td, device=dev)
             self.head_wg = torch.empty(self.head.cin * 64, dtype=td, device=dev)
-        # EXPERIMENT (off by default, TBI_HEAD_FWD_GEMM=1|bf16): the head's forward as ONE GEMM per input pixel,
-        # Y[n,H/2,W/2, 16 taps x num_class (padded to 64)], followed by the 4-tap scatter into the logits.  With 3 output channels
-        # the per-phase transposed conv is MMA-dispatch-bound (160 N=16 MMAs per 128 outputs: 267 us against a 60 us HBM floor).
-        # Measured: Y in bf16 -> step 9.61 -> 9.52 ms but the bf16 r4k4 gradient test leaves the 2e-2 bar (each logit becomes a
-        # sum of four bf16-rounded terms); Y in fp32 (48 columns through the element-wise "narrow" tcgen05 epilogue,
-        # tbi_tc_narrow) -> exact, but that epilogue costs more than the MMAs save (9.85 ms; 10.55 ms on the CUDA-core path).
-        # Needs a vectorised fp32 epilogue, or the scatter fused into the GEMM epilogue: round-2 item.
-        mode = os.environ.get("TBI_HEAD_FWD_GEMM", "0")
+        # The head's forward as ONE GEMM per input pixel, Y[n,H/2,W/2, 16 taps x num_class] in fp32, followed by the 4-tap
+        # scatter into the logits (tbi_convt_scatter_y).  With 3 output channels the per-phase transposed conv is
+        # MMA-dispatch-bound (160 N=16 MMAs per 128 outputs: 263 us against a 60 us HBM floor); the GEMM form issues 16x fewer
+        # MMAs and its 48 fp32 columns leave through the wide fp32 epilogue (16-byte stores from the accumulator registers).
+        # fp32 Y keeps the logits exact to fp32 rounding (with Y in bf16 every logit is a sum of four bf16-rounded terms and
+        # the r4k4 gradient test leaves its 2e-2 bar: TBI_HEAD_FWD_GEMM=bf16, measurement only).  TBI_HEAD_FWD_GEMM=0: off.
+        mode = os.environ.get("TBI_HEAD_FWD_GEMM", "1")
         self.head_fwd_gemm = self.head_gather and mode in ("1", "bf16")
         if self.head_fwd_gemm:
             self.head_yc = 64 if mode == "bf16" else 16 * self.num_class          # fp32: exactly the real columns (narrow epilogue)
