@@ -202,6 +202,23 @@ int tbi_convt_scatter_y(int y_dtype, int n, int h, int w, int ksize, int cout, c
 /* taps of output-parity phase (a,b): returns count; ky/kx = kernel index, dy/dx = input offset.  */
 int tbi_convt_phase_taps(int ksize, int a, int b, int* ky, int* kx, int* dy, int* dx);
 
+/* One-launch weight preparation: every packing mode above is an index map
+ *     out[out_tap[t] + a*out_a + b*out_b] = S[src_tap_index[t]*src_tap + a*src_a + b] * scale(co),  co = co_base + (co_is_a ? a : b)
+ * of one tap's fp32 master matrix S[A][B] (b contiguous), scale = gamma/sqrt(var+eps) (BN folded) or 1 (gamma NULL).  The
+ * caller builds a table of items once (device memory; tile_begin = running sum of ntaps*tiles_a*tiles_b with
+ * tiles_x = ceil(X/32)), zero-fills padded destinations once, and tbi_prepare_run executes the whole table per step;
+ * tbi_bn_fold_multi does the same for the per-channel scale / folded-bias vectors of all layers.                         */
+typedef struct {
+    const float* src; void* out; const float* gamma; const float* var;
+    int32_t ntaps, A, B, co_is_a, co_base, tile_begin, tiles_a, tiles_b;
+    int64_t src_tap, src_a, out_a, out_b;
+    int32_t src_tap_index[TBI_MAX_TAPS];
+    int64_t out_tap[TBI_MAX_TAPS];
+} tbi_prep_item;
+typedef struct { int32_t c, pad_; const float *gamma, *beta, *mean, *var, *bias; float *scale, *fbias; } tbi_fold_item;
+int tbi_prepare_run(int dtype, const tbi_prep_item* items_dev, int nitems, int total_tiles, float bn_eps, void* stream);
+int tbi_bn_fold_multi(const tbi_fold_item* items_dev, int nitems, float bn_eps, void* stream);
+
 /* Folded BN-inference affine of a conv layer, and the matching parameter gradients.
  * fold:  scale[c] = gamma/sqrt(var+eps);  fbias[c] = (bias-mean)*scale+beta   (gamma NULL: scale=1, fbias=bias)
  * grads (after wgrad produced dw_raw = A^T dz and dbias_raw = colsum(dz), both w.r.t. pre-activation z):

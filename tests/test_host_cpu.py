@@ -98,7 +98,12 @@ def _dp_worker(rank, world, port, q):
         gs.allreduce(flat[lo:hi])
     gathered = [torch.zeros(total) for _ in range(world)]
     dist.all_gather(gathered, mine)
-    q.put((rank, bool(torch.allclose(flat, sum(gathered), atol=1e-6)), gs.world_size))
+    # the evaluation-side collectives of MainParallel.py:159-163: gather along the batch axis, SUM of scalars
+    shard = torch.full((2, 3, 1), float(rank))
+    g = gs.gather(shard)
+    ok_gather = tuple(g.shape) == (2 * world, 3, 1) and all(float(g[2 * r].mean()) == r for r in range(world))
+    ok_sum = float(gs.reduce_sum(torch.tensor(float(rank + 1)))) == world * (world + 1) / 2
+    q.put((rank, bool(torch.allclose(flat, sum(gathered), atol=1e-6)) and ok_gather and ok_sum, gs.world_size))
     dist.destroy_process_group()
 
 

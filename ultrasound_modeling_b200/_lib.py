@@ -124,6 +124,19 @@ class TapWgrad(C.Structure):
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_int64)]
 
 
+class PrepItem(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("out", C.c_void_p), ("gamma", C.c_void_p), ("var", C.c_void_p),
+                ("ntaps", C.c_int32), ("A", C.c_int32), ("B", C.c_int32), ("co_is_a", C.c_int32), ("co_base", C.c_int32),
+                ("tile_begin", C.c_int32), ("tiles_a", C.c_int32), ("tiles_b", C.c_int32),
+                ("src_tap", C.c_int64), ("src_a", C.c_int64), ("out_a", C.c_int64), ("out_b", C.c_int64),
+                ("src_tap_index", C.c_int32 * MAX_TAPS), ("out_tap", C.c_int64 * MAX_TAPS)]
+
+
+class FoldItem(C.Structure):
+    _fields_ = [("c", C.c_int32), ("pad_", C.c_int32), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mean", C.c_void_p),
+                ("var", C.c_void_p), ("bias", C.c_void_p), ("scale", C.c_void_p), ("fbias", C.c_void_p)]
+
+
 class SplitAtt(C.Structure):
     _fields_ = [("dtype", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("kpaths", C.c_int32),
                 ("radix", C.c_int32), ("c", C.c_int32), ("act", C.c_int32), ("bn_eps", C.c_float),
@@ -156,6 +169,8 @@ SIGNATURES = {
     "tbi_convt_gather_dz": (_I, [_I, _I, _I, _I, _I, _I, _PV, _PV, _VP]),
     "tbi_convt_scatter_y": (_I, [_I, _I, _I, _I, _I, _I, _PV, _VP, _PV, _VP]),
     "tbi_convt_phase_taps": (_I, [_I, _I, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "tbi_prepare_run": (_I, [_I, _VP, _I, _I, _F, _VP]),
+    "tbi_bn_fold_multi": (_I, [_VP, _I, _F, _VP]),
     "tbi_bn_fold": (_I, [_I, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP]),
     "tbi_bn_param_grad": (_I, [_I, _I64, _I64, _I64, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP]),
     "tbi_avgpool2x2_fwd": (_I, [_I, _I, _I, _I, _PV, _PV, _VP]),

@@ -1400,3 +1400,96 @@ extern "C" int tbi_cast(int src_is_f32, int dst_dtype, int64_t count, const void
     TBI_CUDA_LAUNCH_CHECK("cast");
     return TBI_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// One-launch weight preparation (tbi_prepare_run, tbi_bn_fold_multi)
+// ---------------------------------------------------------------------------------------------
+// The per-layer entry points above (tbi_pack_conv_weights / tbi_pack_convt_weights / tbi_bn_fold) cost ~85 launches per step;
+// although they ran on a side stream under the stem's forward they took 0.35 ms of the 8.9 ms step (measured by skipping
+// them).  Every packing mode is the same operation on a different index map:
+//     out[out_tap[t] + a*out_a + b*out_b] = S[src_tap_index[t]*src_tap + a*src_a + b] * scale(co),   co = co_base + (co_is_a ? a : b)
+// with S the fp32 master kernel of one tap as a matrix [A][B] (b contiguous) and scale = gamma/sqrt(var+eps) (BN folded) or 1.
+// A table of such items (built once by the host, tbi_prep_item) is executed by ONE launch: a block moves a 32x32 tile through
+// shared memory so that both the fp32 reads and the packed writes are coalesced whichever of a/b is contiguous in the output.
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256) prepare_kernel(const tbi_prep_item* __restrict__ items, int nitems, int total_tiles, float eps) {
+    __shared__ float tile[32][33];
+    __shared__ int s_item;
+    for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {            // binary search: last item with tile_begin <= tix
+            int lo = 0, hi = nitems - 1;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (items[mid].tile_begin <= tix) lo = mid; else hi = mid - 1; }
+            s_item = lo;
+        }
+        __syncthreads();
+        const tbi_prep_item& it = items[s_item];
+        int r = tix - it.tile_begin;
+        const int tb = r % it.tiles_b; r /= it.tiles_b;
+        const int ta = r % it.tiles_a; const int t = r / it.tiles_a;
+        const int a0 = ta * 32, b0 = tb * 32;
+        const float* src = it.src + (long long)it.src_tap_index[t] * it.src_tap;
+        // read: threads along b (contiguous in the source)
+        const int b = b0 + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = a0 + threadIdx.y + 8 * j;
+            float v = 0.f;
+            if (a < it.A && b < it.B) {
+                v = src[(long long)a * it.src_a + b];
+                if (it.gamma) { const int co = it.co_base + (it.co_is_a ? a : b); v *= it.gamma[co] * rsqrtf(it.var[co] + eps); }
+            }
+            tile[threadIdx.y + 8 * j][threadIdx.x] = v;
+        }
+        __syncthreads();
+        T* out = (T*)it.out + it.out_tap[t];
+        if (it.out_b == 1) {                                    // b contiguous in the output as well: straight copy
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int a = a0 + threadIdx.y + 8 * j;
+                if (a < it.A && b < it.B) stf(out + (long long)a * it.out_a + b, tile[threadIdx.y + 8 * j][threadIdx.x]);
+            }
+        } else {                                                // a contiguous (or strided) in the output: threads along a
+            const int a = a0 + threadIdx.x;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int bb = b0 + threadIdx.y + 8 * j;
+                if (a < it.A && bb < it.B) stf(out + (long long)a * it.out_a + (long long)bb * it.out_b, tile[threadIdx.x][threadIdx.y + 8 * j]);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void bn_fold_multi_kernel(const tbi_fold_item* __restrict__ items, float eps) {
+    const tbi_fold_item& it = items[blockIdx.x];
+    for (int i = threadIdx.x; i < it.c; i += blockDim.x) {
+        const float b = it.bias ? it.bias[i] : 0.f;
+        if (it.gamma) {
+            const float s = it.gamma[i] * rsqrtf(it.var[i] + eps);
+            it.scale[i] = s; it.fbias[i] = (b - it.mean[i]) * s + it.beta[i];
+        } else { it.scale[i] = 1.f; it.fbias[i] = b; }
+    }
+}
+
+}  // namespace
+
+extern "C" int tbi_prepare_run(int dtype, const tbi_prep_item* items_dev, int nitems, int total_tiles, float bn_eps, void* stream) {
+    TBI_CHECK(items_dev && nitems > 0 && total_tiles > 0, TBI_ERR_BAD_SHAPE, "prepare_run: empty table");
+    long long grid = total_tiles;
+    const long long cap = (long long)tbi_sm_count() * 32;
+    if (grid > cap) grid = cap;
+    if (dtype == TBI_F32) prepare_kernel<float><<<(unsigned)grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(items_dev, nitems, total_tiles, bn_eps);
+    else if (dtype == TBI_BF16) prepare_kernel<__nv_bfloat16><<<(unsigned)grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(items_dev, nitems, total_tiles, bn_eps);
+    else return tbi_set_error(TBI_ERR_UNSUPPORTED, "prepare_run dtype");
+    TBI_CUDA_LAUNCH_CHECK("prepare_run");
+    return TBI_OK;
+}
+
+extern "C" int tbi_bn_fold_multi(const tbi_fold_item* items_dev, int nitems, float bn_eps, void* stream) {
+    TBI_CHECK(items_dev && nitems > 0, TBI_ERR_BAD_SHAPE, "bn_fold_multi: empty table");
+    bn_fold_multi_kernel<<<nitems, 256, 0, (cudaStream_t)stream>>>(items_dev, bn_eps);
+    TBI_CUDA_LAUNCH_CHECK("bn_fold_multi");
+    return TBI_OK;
+}

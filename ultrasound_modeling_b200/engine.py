@@ -390,7 +390,7 @@ class Engine:
         self.head_gather = self.dt == BF16 and 16 * self.num_class <= 64
         if self.head_gather:
             self.head_g = torch.zeros(n, H // 2, W // 2, 64, dtype=td, device=dev)
-            self.head_wg = torch.empty(self.head.cin * 64, dtype=td, device=dev)
+            self.head_wg = torch.zeros(self.head.cin * 64, dtype=td, device=dev)
         # The head's forward as ONE GEMM per input pixel, Y[n,H/2,W/2, 16 taps x num_class] in fp32, followed by the 4-tap
         # scatter into the logits (tbi_convt_scatter_y).  With 3 output channels the per-phase transposed conv is
         # MMA-dispatch-bound (160 N=16 MMAs per 128 outputs: 263 us against a 60 us HBM floor); the GEMM form issues 16x fewer
@@ -402,7 +402,7 @@ class Engine:
         if self.head_fwd_gemm:
             self.head_yc = 64 if mode == "bf16" else 16 * self.num_class          # fp32: exactly the real columns (narrow epilogue)
             self.head_y = torch.empty(n, H // 2, W // 2, self.head_yc, dtype=td if mode == "bf16" else torch.float32, device=dev)
-            self.head_wf = torch.empty(self.head_yc * self.head.cin, dtype=td, device=dev)
+            self.head_wf = torch.zeros(self.head_yc * self.head.cin, dtype=td, device=dev)
         self.loss_map = torch.empty(H, W, dtype=torch.float32, device=dev)
         self.correct = torch.zeros(1, dtype=torch.int32, device=dev)
         # packed compute weights + folded BN
@@ -415,7 +415,7 @@ class Engine:
                 nel = int(self.L.tbi_conv_packed_elems(self.dt, L.k, L.groups, L.cin_g, L.cout))
                 ws_need = max(ws_need, int(self.L.tbi_conv2d_wgrad_workspace(self.dt, L.k, L.groups, L.cin, L.cout)))
             nel_b = L.k * L.k * L.cin * self.dl_c if L is self.head else nel
-            self.packed[L.name] = dict(wf=torch.empty(nel, dtype=td, device=dev), wb=torch.empty(nel_b, dtype=td, device=dev),
+            self.packed[L.name] = dict(wf=torch.zeros(nel, dtype=td, device=dev), wb=torch.zeros(nel_b, dtype=td, device=dev),
                                        scale=torch.empty(L.cout, dtype=torch.float32, device=dev),
                                        fbias=torch.empty(L.cout, dtype=torch.float32, device=dev))
         self.wgrad_ws = torch.empty(ws_need, dtype=torch.uint8, device=dev) if ws_need else None
@@ -462,38 +462,40 @@ class Engine:
                 e.out_stride = 1
             return e
 
-        def prepare(Lr: ConvLayer):
+        # weight preparation: two item tables (prep.py) per part -- the stem's on the main stream (needed at once), everything
+        # else on a side stream under the stem's forward.  Each part is ONE fold launch + ONE pack launch.
+        from . import prep as P_
+        esz = 2 if dt == BF16 else 4
+
+        def prep_rows(Lr: ConvLayer):
             pk = self.packed[Lr.name]
-            if Lr.bn:
-                self.prog_prepare.append((L.tbi_bn_fold, (Lr.cout, _ptr(self.p(Lr.name + "/gamma")), _ptr(self.p(Lr.name + "/beta")),
-                                                          _ptr(self.s(Lr.name + "/mean")), _ptr(self.s(Lr.name + "/var")),
-                                                          _ptr(self.p(Lr.name + "/b")), BN_EPS, _ptr(pk["scale"]), _ptr(pk["fbias"]))))
-            else:
-                self.prog_prepare.append((L.tbi_bn_fold, (Lr.cout, None, None, None, None, _ptr(self.p(Lr.name + "/b")), BN_EPS,
-                                                          _ptr(pk["scale"]), _ptr(pk["fbias"]))))
-            sc = _ptr(pk["scale"]) if Lr.bn else None
+            bnp = [_ptr(self.p(Lr.name + "/gamma")), _ptr(self.p(Lr.name + "/beta")), _ptr(self.s(Lr.name + "/mean")), _ptr(self.s(Lr.name + "/var"))] if Lr.bn else [None] * 4
+            fold = (Lr.cout, *bnp, _ptr(self.p(Lr.name + "/b")), _ptr(pk["scale"]), _ptr(pk["fbias"]))
+            g_, v_ = (bnp[0], bnp[3]) if Lr.bn else (None, None)
             wp = _ptr(self.p(Lr.name + "/w"))
+            items = []
             if Lr.kind == "conv":
-                self.prog_prepare.append((L.tbi_pack_conv_weights, (dt, 0, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, sc, _ptr(pk["wf"]))))
-                self.prog_prepare.append((L.tbi_pack_conv_weights, (dt, 1, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, sc, _ptr(pk["wb"]))))
+                items += P_.conv_items(L, dt, esz, 0, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, g_, v_, _ptr(pk["wf"]))
+                items += P_.conv_items(L, dt, esz, 1, Lr.k, Lr.groups, Lr.cin_g, Lr.cout, wp, g_, v_, _ptr(pk["wb"]))
             else:
                 cpad = self.dl_c if Lr is self.head else 0
-                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 0, Lr.k, Lr.cin, Lr.cout, 0, wp, sc, _ptr(pk["wf"]))))
-                self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 1, Lr.k, Lr.cin, Lr.cout, cpad, wp, sc, _ptr(pk["wb"]))))
+                items += P_.convt_items(L, esz, 0, Lr.k, Lr.cin, Lr.cout, 0, wp, g_, v_, _ptr(pk["wf"]))
+                items += P_.convt_items(L, esz, 1, Lr.k, Lr.cin, Lr.cout, cpad, wp, g_, v_, _ptr(pk["wb"]))
                 if Lr is self.head and self.head_gather:
-                    self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 2, Lr.k, Lr.cin, Lr.cout, 64, wp, sc, _ptr(self.head_wg))))
+                    items += P_.convt_items(L, esz, 2, Lr.k, Lr.cin, Lr.cout, 64, wp, g_, v_, _ptr(self.head_wg))
                 if Lr is self.head and self.head_fwd_gemm:
-                    self.prog_prepare.append((L.tbi_pack_convt_weights, (dt, 3, Lr.k, Lr.cin, Lr.cout, self.head_yc, wp, sc, _ptr(self.head_wf))))
+                    items += P_.convt_items(L, 2 if self.head_wf.dtype == torch.bfloat16 else 4, 3, Lr.k, Lr.cin, Lr.cout, self.head_yc, wp, g_, v_, _ptr(self.head_wf))
+            return fold, items
 
-        # weight packing of everything behind the full-resolution stem runs on a side stream, overlapped with the stem's
-        # forward (the pack/fold launches are ~85 tiny grids, ~0.6 ms when serialised in front of the step)
         stem = ("Conv1", "conv2_1_1", "conv2_1_2")
-        for name in stem:
-            prepare(self.convs[name])
-        self.prep_split = len(self.prog_prepare)
-        for Lr in self.convs.values():
-            if Lr.name not in stem:
-                prepare(Lr)
+        parts = ([self.convs[nm] for nm in stem], [Lr for Lr in self.convs.values() if Lr.name not in stem])
+        self.prep_tables = []
+        for layers in parts:
+            folds, items = [], []
+            for Lr in layers:
+                f, it = prep_rows(Lr)
+                folds.append(f); items += it
+            self.prep_tables.append((P_.FoldTable(folds, self.device), P_.PrepTable(items, self.device)))
 
         def conv_fwd(Lr, h, w, src0, src1, e):
             pk = self.packed[Lr.name]
@@ -660,16 +662,19 @@ class Engine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def prepare(self):
-        """fold BN and pack the compute copies of the weights.  The stem's (tiny) on the current stream; the rest on a side
-        stream that forward() joins after the stem -- fork and join are event waits, so this also captures into a CUDA graph."""
-        self._run(self.prog_prepare[:self.prep_split], self.stream())
+        """fold BN and refresh the compute copies of the weights: per part one fold launch + one pack launch over a prebuilt item
+        table (prep.py).  The stem's part on the current stream; the rest on a side stream that forward() joins after the stem --
+        fork and join are event waits, so this also captures into a CUDA graph."""
+        (f0, p0), (f1, p1) = self.prep_tables
+        st = self.stream()
+        f0.run(self.L, BN_EPS, st); p0.run(self.L, self.dt, BN_EPS, st)
         if not self.overlap_prepare:
-            self._run(self.prog_prepare[self.prep_split:], self.stream())
+            f1.run(self.L, BN_EPS, st); p1.run(self.L, self.dt, BN_EPS, st)
             return
         if self._side is None:
             self._side = torch.cuda.Stream(self.device)
         self._side.wait_stream(torch.cuda.current_stream(self.device))
-        self._run(self.prog_prepare[self.prep_split:], self._side.cuda_stream)
+        f1.run(self.L, BN_EPS, self._side.cuda_stream); p1.run(self.L, self.dt, BN_EPS, self._side.cuda_stream)
         self._prep_pending = True
 
     def _join_prepare(self):
@@ -790,7 +795,7 @@ class Engine:
                     k += 1
                 c += k
             return c
-        n = count(self.prog_prepare) + count(self.prog_fwd) + count(self.prog_loss)
+        n = 4 + count(self.prog_fwd) + count(self.prog_loss)          # weight preparation: (fold + pack) x (stem, rest)
         n += sum(1 for k in self.keep if k is not None) + 1       # dropout masks + the draw counter
         if train:
             n += count(self.prog_bwd) + 2 - 1                      # Adam + its counter; -1: the stem wgrad needs no separate column sum

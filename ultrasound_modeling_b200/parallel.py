@@ -87,6 +87,20 @@ class GradSync:
     def allreduce(self, flat_slice: torch.Tensor):
         dist.all_reduce(flat_slice, op=dist.ReduceOp.SUM, group=self.pg)
 
+    def gather(self, t: torch.Tensor) -> torch.Tensor:
+        """eval-side counterpart of mirrored_strategy.gather(values, axis=0) (MainParallel.py:160,163): every replica's
+        per-shard tensor (class scores [B/world, H, W, C], labels) concatenated along the batch axis, on every rank"""
+        t = t.contiguous()
+        parts = [torch.empty_like(t) for _ in range(self.world_size)]
+        dist.all_gather(parts, t, group=self.pg)
+        return torch.cat(parts, dim=0)
+
+    def reduce_sum(self, t: torch.Tensor) -> torch.Tensor:
+        """mirrored_strategy.reduce(SUM, per_replica_value, axis=None) for the loss / metric scalars (MainParallel.py:131-134,159)"""
+        out = t.detach().clone()
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.pg)
+        return out
+
     def backward_and_sync(self, engine):
         """run engine.prog_bwd, interleaving bucket all-reduces on a side stream"""
         self._ensure_plan(engine)
