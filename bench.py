@@ -171,6 +171,24 @@ def other_configs(args, dev):
     except Exception as exc:                                     # noqa: BLE001 -- a side measurement must not take the headline down
         infer.append({"model": "Variant B", "error": repr(exc)[:200]})
     out["inference_sweep_config4"] = infer
+    # the model MainParallel.py trains (VisionTransformer.py: Variant B encoder + 8-block ViT bridge + DecoderCup), per-replica
+    # batches of the reference driver (MainParallel.py:205 uses a global batch of 64), CUDA-graph replay of loss + backward
+    vb = []
+    try:
+        from oracle import vit_oracle as V
+        from ultrasound_modeling_b200.VisionTransformer import VisionTransformer
+        for n, graph in ((16, True), (64, True), (16, False)):
+            net = VisionTransformer(n, dtype="bf16", device=str(dev), use_cuda_graph=graph)
+            x = V.B.synthetic_input(2, 256, 80, 10).repeat(n // 2, 1, 1, 1).to(dev); y = V.synthetic_labels(2, 256, 80).repeat(n // 2, 1, 1, 1).to(dev)
+            ms = timed(lambda: net.train_step(x, y), 5, warm=4)
+            msf = timed(lambda: net.forward(x), 5, warm=4)
+            vb.append({"model": "VisionTransformer train_step / forward [N,256,80,10] bf16", "batch": n, "cuda_graph": graph, "train_ms": round(ms, 3),
+                       "train_img_per_s": round(n / ms * 1e3, 1), "forward_ms": round(msf, 3), "forward_img_per_s": round(n / msf * 1e3, 1)})
+            del net, x, y
+            torch.cuda.empty_cache()
+    except Exception as exc:                                     # noqa: BLE001
+        vb.append({"model": "VisionTransformer", "error": repr(exc)[:300]})
+    out["variant_b_vit"] = vb
     torch.cuda.empty_cache()
     return out
 

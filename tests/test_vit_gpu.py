@@ -146,3 +146,37 @@ def test_gradients_bf16_track_the_oracle(cuda_device):
     a_, b_ = ctypes.c_int64(0), ctypes.c_int64(0)
     L.tbi_fallback_stats(ctypes.byref(a_), ctypes.byref(b_), 0)
     assert (a_.value, b_.value) == (0, 0), (a_.value, b_.value, L.tbi_last_fallback())      # the whole step stays on tcgen05
+
+
+def test_cuda_graph_replay_equals_eager(cuda_device):
+    """train_step / step / forward through CUDA-graph replay (two eager calls, capture, replays) track the eager path over six
+    optimizer steps, across a batch-size change and back (graphs are keyed by input shape and variable-storage generation)"""
+    from ultrasound_modeling_b200.VisionTransformer import VisionTransformer
+    o = V.VisionTransformerOracle(2, img_size=(64, 32), num_classes=3, learning_rate=1e-3, dtype=torch.float64, num_layers=2)
+    nets = [VisionTransformer(2, img_size=(64, 32), num_classes=3, learning_rate=1e-3, dtype="fp32", device=str(cuda_device), num_layers=2,
+                              use_cuda_graph=g) for g in (False, True)]
+    for net in nets:
+        net.load_variables(o.state_dict())
+    x2 = V.B.synthetic_input(2, 64, 32, 10); y2 = V.synthetic_labels(2, 64, 32)
+    x4 = V.B.synthetic_input(4, 64, 32, 10, seed=77); y4 = V.synthetic_labels(4, 64, 32, seed=78)
+    losses = [[], []]
+    for (x, y) in [(x2, y2)] * 4 + [(x4, y4)] * 4 + [(x2, y2)] * 2:
+        for i, net in enumerate(nets):
+            loss, probs = net.train_step(x, y)
+            losses[i].append(float(loss))
+    assert len(nets[1]._graphs) >= 2 and all(e["graph"] is not None for e in nets[1]._graphs.values())
+    assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-4, losses
+    va, vb = nets[0].variables(), nets[1].variables()
+    # fp32 atomics reorder sums between runs; Adam turns rounding-level differences into steps of at most lr
+    diffs = torch.cat([(va[k] - vb[k]).abs().reshape(-1) for k in va])
+    assert float((diffs > 1e-3 * 2e-2).double().mean()) < 1e-3 and float(diffs.max()) < 1e-2
+    for _ in range(4):
+        (la, pa), (lb, pb) = nets[0].step(x2, y2), nets[1].step(x2, y2)
+        fa, fb = nets[0].forward(x4), nets[1].forward(x4)
+    assert abs(float(la) - float(lb)) < 1e-3 * abs(float(la)) and rel(pb, pa) < 2e-3 and rel(fb[0], fa[0]) < 2e-3
+    assert len(fb[1]) == 2 and rel(fb[1][0], fa[1][0]) < 2e-3
+    # a learning-rate change reaches the replayed step (the Adam tail reads a device buffer)
+    before = nets[1].variables()["decoder/head/bias"].clone()
+    nets[1].optimizer.learning_rate = 0.0
+    nets[1].train_step(x2, y2)
+    assert torch.equal(before, nets[1].variables()["decoder/head/bias"])

@@ -43,6 +43,8 @@ class VariableStore:
         self._alive = []
         self.grads: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         self.flat = None             # set by freeze(): dict(params, grads, m, v, names, gviews)
+        self._rows = {}
+        self.generation = 0          # bumped whenever a variable's storage moves (freeze, load): captured CUDA graphs key on it
 
     def start_recording(self):
         self.recording = True
@@ -71,9 +73,19 @@ class VariableStore:
             view.copy_(t)
             self.vars[k] = view
             gviews[k] = G[offs[k]:offs[k] + t.numel()].view(t.shape)
+        self.generation += 1
         self.flat = dict(params=P, grads=G, m=torch.zeros_like(P), v=torch.zeros_like(P), names=names, gviews=gviews, offsets=offs,
                          step=torch.zeros(1, dtype=torch.int32, device=dev))
         return self.flat
+
+    def index_rows(self, key) -> torch.Tensor:
+        """device index vector for a channel map (tuple of positions, or an int = arange), built once: a host list turned into
+        a device tensor inside a CUDA-graph capture would be a pageable host-to-device copy, which capture refuses"""
+        t = self._rows.get(key)
+        if t is None:
+            t = self._rows[key] = (torch.arange(key, device=self.device) if isinstance(key, int)
+                                   else torch.tensor(list(key), dtype=torch.long).to(self.device))
+        return t
 
     def gacc(self, t: torch.Tensor, g: torch.Tensor, coff: int = 0):
         """add g into channels [coff, coff + g.channels) of the gradient buffer of activation buffer t"""
@@ -134,6 +146,7 @@ class VariableStore:
                 self.vars[k].copy_(t.reshape(self.vars[k].shape))        # frozen: the variable is a view of the flat buffer
             else:
                 self.vars[k] = t
+                self.generation += 1
 
 
 class _Layer:
@@ -165,7 +178,7 @@ class _Layer:
         rows = None
         if padded:
             dev = x.device
-            rows = torch.as_tensor(cmap, device=dev, dtype=torch.long) if cmap is not None else torch.arange(cx_real, device=dev)
+            rows = self._s.index_rows(tuple(cmap) if cmap is not None else cx_real)
             wk = torch.zeros(k, k, cx + c2, cout_p, dtype=torch.float32, device=dev)
             wk[:, :, rows, :cout] = w[:, :, :cx_real]
             if c2:

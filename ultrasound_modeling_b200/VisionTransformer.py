@@ -184,7 +184,7 @@ class _VisionModel:
 
 class VisionTransformer:
     def __init__(self, batch_size, img_size=(256, 80), num_classes=3, learning_rate=1e-3, weight_decay=1e-4, *, dtype="bf16",
-                 device=None, seed=0, grad_sync=None, clip_norm=1.0, label_smoothing=0.1, num_layers=8):
+                 device=None, seed=0, grad_sync=None, clip_norm=1.0, label_smoothing=0.1, num_layers=8, use_cuda_graph=True):
         if not torch.cuda.is_available():
             raise _lib.TbiError("ultrasound_modeling_b200 needs a CUDA device (sm_100); there is no CPU path")
         self.num_classes, self.batch_size, self.weight_decay = num_classes, batch_size, weight_decay
@@ -202,6 +202,10 @@ class VisionTransformer:
         self.loss = self.compute_loss
         self.visionModel = _VisionModel(self)
         self.grad_sync = grad_sync
+        # CUDA-graph replay of forward / loss+backward (the define-by-run tape issues ~2 600 launches per training step and is
+        # host-bound without it).  Like TBI_ResNest.ResNest: results live in static buffers that the next call overwrites.
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs = {}
         self._hyper = torch.tensor([learning_rate, 1.0, self.clip_norm], dtype=torch.float32, device=self.device)
         self._hyper_host = None
         self._gnorm_sq = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -222,45 +226,83 @@ class VisionTransformer:
     def _x(self, x):
         return torch.as_tensor(np.asarray(x) if not torch.is_tensor(x) else x).to(device=self.device, dtype=self.tdtype).contiguous()
 
+    def _y(self, y):
+        return torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(device=self.device, dtype=torch.float32).contiguous()
+
+    def _graphed(self, tag, fn, inputs):
+        """fn(*device tensors) -> tensors, through a CUDA graph: per (entry point, input shapes, variable-storage generation)
+        two eager calls (they create / freeze the variables), then one capture, then replays over static input buffers."""
+        if not self.use_cuda_graph:
+            return fn(*inputs)
+        key = (tag, tuple(tuple(t.shape) for t in inputs), self.store.generation)
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs = {k: v for k, v in self._graphs.items() if k[2] == self.store.generation}     # stale pointers: drop
+            ent = self._graphs[key] = dict(warm=0, static=[torch.empty_like(t) for t in inputs], graph=None, out=None)
+        for st, t in zip(ent["static"], inputs):
+            st.copy_(t, non_blocking=True)
+        if ent["graph"] is None:
+            if ent["warm"] < 2:
+                ent["warm"] += 1
+                return fn(*ent["static"])
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize(self.device)
+            with torch.cuda.graph(g):
+                out = fn(*ent["static"])
+            ent["graph"], ent["out"] = g, out
+        ent["graph"].replay()
+        return ent["out"]
+
     def _forward_logits(self, x):
         tokens, weights, feats = self.transformer.forward(self._x(x))
         z = self.decoder.forward(tokens, feats, logits=True, record=False)
         return z, weights
 
-    def forward(self, x):
-        """VisionTransformer.forward :220-223 -> (probabilities [N,H,W,num_classes], [attention weights per layer])"""
-        z, weights = self._forward_logits(x)
+    def forward_logits(self, x):
+        """pre-softmax class scores [N,H,W,num_classes] and the attention weights (graph-replayed; the evaluator's entry)"""
+        return self._graphed("logits", self._forward_logits, (self._x(x),))
+
+    def _forward_dev(self, xd):
+        z, weights = self._forward_logits(xd)
         probs, _, _ = ops.softmax_cce(z, torch.zeros_like(z), 0.0, 1.0, need_grad=False)
         return probs, weights
 
+    def forward(self, x):
+        """VisionTransformer.forward :220-223 -> (probabilities [N,H,W,num_classes], [attention weights per layer])"""
+        return self._graphed("forward", self._forward_dev, (self._x(x),))
+
     def compute_loss(self, y_true, y_pred):
         """:225-227 on PROBABILITIES (as the reference calls it); evaluated by the fused kernel on log(p) (softmax(log p) == p)"""
-        y_true = torch.as_tensor(np.asarray(y_true) if not torch.is_tensor(y_true) else y_true).to(device=self.device, dtype=torch.float32).contiguous()
-        y_pred = torch.as_tensor(np.asarray(y_pred) if not torch.is_tensor(y_pred) else y_pred).to(device=self.device, dtype=torch.float32).contiguous()
+        y_true = self._y(y_true)
+        y_pred = self._y(y_pred)
         _, loss, _ = ops.softmax_cce(torch.log(y_pred.clamp_min(1e-30)), y_true, self.label_smoothing, float(self.batch_size), need_grad=False)
         return loss.reshape(())
 
-    def step(self, x, y):
-        """:248-254 -> (loss, probabilities)"""
-        z, _ = self._forward_logits(x)
-        yd = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(device=self.device, dtype=torch.float32).contiguous()
+    def _step_dev(self, xd, yd):
+        z, _ = self._forward_logits(xd)
         probs, loss, _ = ops.softmax_cce(z, yd, self.label_smoothing, float(self.batch_size), need_grad=False)
         return loss.reshape(()), probs
 
+    def step(self, x, y):
+        """:248-254 -> (loss, probabilities)"""
+        return self._graphed("step", self._step_dev, (self._x(x), self._y(y)))
+
     # ------------------------------------------------------------------ training step
-    def backward(self, x, y):
-        """forward + loss + backward (no optimizer): -> (loss, probabilities); gradients() holds d loss / d variable"""
+    def _backward_dev(self, xd, yd):
         s = self.store
         s.start_recording()
-        z, _ = self._forward_logits(x)
+        z, _ = self._forward_logits(xd)
         if s.flat is None:                                      # first step: every variable exists now
             s.freeze()
             s.flat["grads"].zero_()
-        yd = torch.as_tensor(np.asarray(y) if not torch.is_tensor(y) else y).to(device=self.device, dtype=torch.float32).contiguous()
         probs, loss, dz = ops.softmax_cce(z, yd, self.label_smoothing, float(self.batch_size))
         s.gacc(z, dz)
         s.run_backward()
         return loss.reshape(()), probs
+
+    def backward(self, x, y):
+        """forward + loss + backward (no optimizer): -> (loss, probabilities); gradients() holds d loss / d variable"""
+        return self._graphed("backward", self._backward_dev, (self._x(x), self._y(y)))
 
     def train_step(self, x, y):
         """:235-246: gradients of the averaged loss -> clip_by_global_norm(1.0) -> Adam; returns (loss, probabilities).

@@ -3,14 +3,21 @@
 //
 //   dw[tap][ci][co] += sum_pixels x[pixel + off(tap)][ci] * dz[pixel][co]          (3x3 dilation 1, or 1x1)
 //
-// Per 16x8 pixel tile the producer issues ONE halo box of x ((16+2) x (8+2) pixels) and ONE plain box of
-// dz.  Both operands are MN-major (channels contiguous, pixels = K).  The three horizontal taps are packed
-// into the M dimension: an M block is kcA channels, consecutive M blocks start one PIXEL ROW later
-// (descriptor leading-byte-offset = row bytes), so M = 128 covers (dx = -1, 0, +1, [+2 unused]) x kcA input
-// channels in a single MMA.  One accumulator per vertical tap dy -> 3 x N TMEM columns, which stay resident
-// for the whole CTA: a CTA walks a contiguous range of pixel tiles (split-K across CTAs) and reduces its
-// partial dw into the fp32 gradient with red.global.add once, at the end.
-// MMAs per 128 pixels: 3 (dy) x 8 (K steps of 16 pixels) instead of 72 for tap-by-tap accumulation.
+// Per 16x8 pixel tile the producer issues ONE box of x, 16 x (8+2) pixels (halo in x only), and ONE box of dz,
+// (16+2) x 8 pixels (halo in y only).  Both operands are MN-major (channels contiguous, pixels = K).
+// ALL NINE TAPS ARE ONE MMA: the three horizontal taps are packed into the M dimension -- an M block is kcA
+// channels, consecutive M blocks start one PIXEL later (descriptor leading-byte-offset = row bytes), so M = 128
+// covers (dx = -1, 0, +1, [unused]) x kcA input channels -- and the three vertical taps into the N dimension:
+// an N block is kcB channels of dz, consecutive N blocks start one TILE ROW later (leading-byte-offset = 8 pixel
+// rows), i.e. the K index is the pixel q that x is read around and N block n pairs it with dz[q + (n-1) W]:
+//   D[(j, ci), (n, co)] = sum_q x[q + (j-1)][ci] * dz[q + (n-1) W][co] = dw[tap (dy = 1-n, dx = j-1)][ci][co].
+// (A product x[p+off] dz[p] with p outside the image reads TMA zero fill; every in-image pair is counted once, in the
+// tile that holds q.)  The accumulator (3 kcB TMEM columns) stays resident for the whole CTA: a CTA walks a contiguous
+// range of pixel tiles (split-K across CTAs) and reduces its partial dw into the fp32 gradient with red.global.add
+// once, at the end.
+// MMAs per 128 pixels: 8 (K steps of 16 pixels), N = 3 kcB -- instead of 24 with one accumulator per dy (round 1)
+// and 72 for tap-by-tap accumulation.  A tcgen05.mma costs ~49 cycles to dispatch whatever its N
+// (profiles/r1_summary.md), so for these HBM-bound layers the dispatch count, not the math, was the limit.
 #include "tbi_common.cuh"
 #include "tc_common.cuh"
 #include <mutex>
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(WS_THREADS) tapwgrad_small_kernel(const __grid
     const int tile_beg = blockIdx.x * p.tiles_per_cta;
     const int tile_end = min(p.total_tiles, tile_beg + p.tiles_per_cta);
     const int iters = tile_end - tile_beg;
-    const int pitch = WTW + 2 * p.halo;
+    const int pitch = WTW + 2 * p.halo;                            // x: halo columns only; dz: halo rows only
     const uint32_t rowa = 2u * p.kca, rowb = 2u * p.kcb;
 
     if (warp == 4) {
@@ -79,8 +86,8 @@ __global__ void __launch_bounds__(WS_THREADS) tapwgrad_small_kernel(const __grid
             if (leader) {
                 uint8_t* st = smem + (size_t)s * stage_bytes;
                 tc::mbar_expect_tx(&full[s], p.a_tx + p.b_tx);
-                tc::tma_load_5d(st, &p.a, &full[s], g * p.cin_g, x0 - p.halo, 0, y0 - p.halo, n0);
-                tc::tma_load_5d(st + p.a_stage_bytes, &p.b, &full[s], g * p.cout_g, x0, 0, y0, n0);
+                tc::tma_load_5d(st, &p.a, &full[s], g * p.cin_g, x0 - p.halo, 0, y0, n0);
+                tc::tma_load_5d(st + p.a_stage_bytes, &p.b, &full[s], g * p.cout_g, x0, 0, y0 - p.halo, n0);
             }
             if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; }
         }
@@ -88,27 +95,24 @@ __global__ void __launch_bounds__(WS_THREADS) tapwgrad_small_kernel(const __grid
     } else if (warp == 5) {
         // ===================== MMA issuer =====================
         const bool leader = tc::elect_one();
-        const uint32_t idesc = tc::make_idesc_bf16(128, N, 1, 1);                       // both operands MN-major
+        const uint32_t idesc = tc::make_idesc_bf16(128, p.nrow * N, 1, 1);              // both operands MN-major; N = (dy block, co)
         const uint32_t lay_a = p.kca == 64 ? 2u : p.kca == 32 ? 4u : 6u, lay_b = p.kcb == 64 ? 2u : p.kcb == 32 ? 4u : 6u;
         // A: M blocks of kca channels one pixel row apart (LBO = row bytes); K groups of 8 pixels = one tile row (SBO = pitch rows)
         const uint64_t da_base = tc::smem_desc_base(rowa, (uint32_t)pitch * rowa, lay_a);
-        const uint64_t db_base = tc::smem_desc_base(rowb, 8u * rowb, lay_b);
+        // B: N blocks of kcb channels one TILE ROW (8 pixels) apart; K groups of 8 pixels = one tile row as well
+        const uint64_t db_base = tc::smem_desc_base(p.nrow > 1 ? 8u * rowb : rowb, 8u * rowb, lay_b);
         const uint32_t a_lo0 = (uint32_t)da_base, a_hi = (uint32_t)(da_base >> 32), b_lo0 = (uint32_t)db_base, b_hi = (uint32_t)(db_base >> 32);
         const uint32_t ring_lo = (tc::smem_u32(smem) & 0x3FFFFu) >> 4, stage_lo = (uint32_t)stage_bytes >> 4, boff_lo = (uint32_t)p.a_stage_bytes >> 4;
-        const uint32_t a_kstep = (2u * pitch * rowa) >> 4, b_kstep = (16u * rowb) >> 4, a_dy = ((uint32_t)pitch * rowa) >> 4;
+        const uint32_t a_kstep = (2u * pitch * rowa) >> 4, b_kstep = (16u * rowb) >> 4;
         uint32_t s = 0, par = 0, accum = 0;
         for (int it = 0; it < iters; ++it) {
             tc::mbar_wait_bounded(&full[s], par);
             tc::tc_fence_after();
             const uint32_t a0 = a_lo0 + ring_lo + s * stage_lo, b0 = b_lo0 + ring_lo + s * stage_lo + boff_lo;
             if (leader) {
-#pragma unroll 1
-                for (int dy = 0; dy < p.nrow; ++dy) {
-                    const uint32_t ad = a0 + dy * a_dy;
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        tc::umma_bf16_lh(tmem_base + dy * N, ad + ks * a_kstep, a_hi, b0 + ks * b_kstep, b_hi, idesc, (accum | ks) ? 1u : 0u);
-                }
+                for (int ks = 0; ks < 8; ++ks)
+                    tc::umma_bf16_lh(tmem_base, a0 + ks * a_kstep, a_hi, b0 + ks * b_kstep, b_hi, idesc, (accum | ks) ? 1u : 0u);
                 tc::umma_commit(&empty[s]);
             }
             accum = 1;
@@ -123,8 +127,8 @@ __global__ void __launch_bounds__(WS_THREADS) tapwgrad_small_kernel(const __grid
         const bool row_ok = j < p.nrow && ci < p.cin_g;
         tc::mbar_wait_bounded<true>(done, 0);
         tc::tc_fence_after();
-        for (int dy = 0; dy < p.nrow; ++dy) {
-            float* base = p.dw + (size_t)(dy * p.nrow + j) * p.tap_stride + (size_t)ci * p.ci_stride;
+        for (int dy = 0; dy < p.nrow; ++dy) {                      // N block dy holds the tap row (nrow - 1 - dy)
+            float* base = p.dw + (size_t)((p.nrow - 1 - dy) * p.nrow + j) * p.tap_stride + (size_t)ci * p.ci_stride;
 #pragma unroll 1
             for (int c = 0; c < N; c += 16) {
                 uint32_t r[16];
@@ -192,9 +196,9 @@ int tbi_tapwgrad_small(const tbi_tapwgrad* d, cudaStream_t s) {
     p.kca = pow2_ge16(d->cin_g); p.kcb = pow2_ge16(d->cout_g);
     p.halo = d->ntaps == 9 ? 1 : 0; p.nrow = d->ntaps == 9 ? 3 : 1;
     const int bw = WTW + 2 * p.halo, bh = WTH + 2 * p.halo;
-    int rc = ws_act_tmap(&p.a, d->a_src[0], d->n, p.kca, bw, bh); if (rc) return rc;
-    rc = ws_act_tmap(&p.b, d->b_src, d->n, p.kcb, WTW, WTH); if (rc) return rc;
-    p.a_tx = bw * bh * p.kca * 2; p.b_tx = WTW * WTH * p.kcb * 2;
+    int rc = ws_act_tmap(&p.a, d->a_src[0], d->n, p.kca, bw, WTH); if (rc) return rc;
+    rc = ws_act_tmap(&p.b, d->b_src, d->n, p.kcb, WTW, bh); if (rc) return rc;
+    p.a_tx = bw * WTH * p.kca * 2; p.b_tx = WTW * bh * p.kcb * 2;
     // the packed M blocks read up to 128/kca - 1 pixel rows past the halo box: keep that slack inside the stage
     p.a_stage_bytes = (p.a_tx + (128 / p.kca) * p.kca * 2 + 1023) & ~1023;
     p.b_stage_bytes = (p.b_tx + 1023) & ~1023;

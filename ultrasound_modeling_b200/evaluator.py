@@ -25,7 +25,9 @@ class Evaluator:
         self.L = _lib.lib()
 
     def _logits(self, model, x):
-        if hasattr(model, "_forward_logits"):                   # VisionTransformer
+        if hasattr(model, "forward_logits"):                    # VisionTransformer (CUDA-graph replay per batch shape)
+            return model.forward_logits(x)[0]
+        if hasattr(model, "_forward_logits"):
             return model._forward_logits(x)[0]
         if hasattr(model, "engine"):                            # TBI_ResNest.ResNest: probabilities -> log (softmax(log p) == p)
             return torch.log(model.predict(x, dropout_masks=None).clamp_min(1e-30))
