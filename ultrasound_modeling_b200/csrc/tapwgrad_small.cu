@@ -127,19 +127,36 @@ __global__ void __launch_bounds__(WS_THREADS) tapwgrad_small_kernel(const __grid
         const bool row_ok = j < p.nrow && ci < p.cin_g;
         tc::mbar_wait_bounded<true>(done, 0);
         tc::tc_fence_after();
-        for (int dy = 0; dy < p.nrow; ++dy) {                      // N block dy holds the tap row (nrow - 1 - dy)
-            float* base = p.dw + (size_t)((p.nrow - 1 - dy) * p.nrow + j) * p.tap_stride + (size_t)ci * p.ci_stride;
+        // Every CTA adds a full (taps x cin x cout) partial into the same few thousand fp32 words.  Two things keep the L2
+        // atomic units from serialising: each CTA starts at its own 16-column chunk (the CTAs finish together; without the
+        // rotation all of them hit the same addresses in the same order), and with unit cout stride a chunk goes out as four
+        // 16-byte vector reductions instead of sixteen scalar ones.
+        const int cpn = N / 16, chunks = p.nrow * cpn;
+        const bool vec = p.co_stride == 1 && (p.cout_g & 3) == 0 && (p.ci_stride & 3) == 0 && (p.tap_stride & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0);
+        int idx = (int)((blockIdx.x * 7u + blockIdx.y * 3u) % (unsigned)chunks);
 #pragma unroll 1
-            for (int c = 0; c < N; c += 16) {
-                uint32_t r[16];
-                tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + dy * N + c, r);
-                tc::tmem_ld_wait();
-                if (row_ok) {
+        for (int k = 0; k < chunks; ++k, idx = (idx + 1 == chunks ? 0 : idx + 1)) {
+            const int dy = idx / cpn, c = (idx - dy * cpn) * 16;       // N block dy holds the tap row (nrow - 1 - dy)
+            float* base = p.dw + (size_t)((p.nrow - 1 - dy) * p.nrow + j) * p.tap_stride + (size_t)ci * p.ci_stride;
+            uint32_t r[16];
+            tc::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + dy * N + c, r);
+            tc::tmem_ld_wait();
+            if (!row_ok) continue;
+            if (vec) {
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int co = c + q;
-                        if (co < p.cout_g) atomicAdd(base + (size_t)(g * p.cout_g + co) * p.co_stride, __uint_as_float(r[q]));
+                for (int q = 0; q < 16; q += 4) {
+                    if (c + q < p.cout_g) {
+                        float* dst = base + (size_t)(g * p.cout_g + c + q);
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(__uint_as_float(r[q])), "f"(__uint_as_float(r[q + 1])),
+                                     "f"(__uint_as_float(r[q + 2])), "f"(__uint_as_float(r[q + 3])) : "memory");
                     }
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int co = c + q;
+                    if (co < p.cout_g) atomicAdd(base + (size_t)(g * p.cout_g + co) * p.co_stride, __uint_as_float(r[q]));
                 }
             }
         }

@@ -161,20 +161,33 @@ __global__ void __launch_bounds__(WG_THREADS) tapwgrad_tc_kernel(const __grid_co
         wg_wait(tfull, 0);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        // split-K partials of many CTAs land on the same fp32 words: start each CTA at its own 32-column chunk so they do not walk
+        // the addresses in lock step, and with unit cout stride (Conv2D, HWIO) send 16-byte vector reductions
+        const bool vec = p.co_stride == 1 && (p.cout_g & 3) == 0 && (p.ci_stride & 3) == 0 && (p.tap_stride & 3) == 0 &&
+                         ((reinterpret_cast<uintptr_t>(p.dw) & 15) == 0);
+        constexpr int CPT = BN / 32, CHUNKS = T * CPT;
+        int idx = (int)((blockIdx.x * 5u + blockIdx.y * 3u + blockIdx.z) % (unsigned)CHUNKS);
 #pragma unroll 1
-        for (int tt2 = 0; tt2 < T; ++tt2) {
+        for (int k = 0; k < CHUNKS; ++k, idx = (idx + 1 == CHUNKS ? 0 : idx + 1)) {
+            const int tt2 = idx / CPT, c = (idx - tt2 * CPT) * 32;
             float* base = p.dw + (size_t)(tap + tt2) * p.tap_stride + (size_t)ci * p.ci_stride;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
-                uint32_t r[32];
-                tc::tmem_ld32(taddr + tt2 * BN + c, r);
-                tc::tmem_ld_wait();
-                if (row_ok) {
+            uint32_t r[32];
+            tc::tmem_ld32(taddr + tt2 * BN + c, r);
+            tc::tmem_ld_wait();
+            if (!row_ok) continue;
+            if (vec) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int co = co0 + c + j;
-                        if (co < p.cout_g) atomicAdd(base + (size_t)(g * p.cout_g + co) * p.co_stride, __uint_as_float(r[j]));
-                    }
+                for (int j = 0; j < 32; j += 4) {
+                    const int co = co0 + c + j;
+                    if (co < p.cout_g)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(base + (size_t)(g * p.cout_g + co)), "f"(__uint_as_float(r[j])),
+                                     "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3])) : "memory");
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int co = co0 + c + j;
+                    if (co < p.cout_g) atomicAdd(base + (size_t)(g * p.cout_g + co) * p.co_stride, __uint_as_float(r[j]));
                 }
             }
         }

@@ -173,20 +173,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(W2_THREADS, T <= 2 ?
         w2_wait(tfull, 0);
         tc::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        // the split-K CTAs of one output tile finish together: each starts at its own 32-column chunk so that they do not send
+        // their reductions to the same words in the same order
+        constexpr int CHUNKS = T * 4;
+        int idx = (int)((blockIdx.x * 5u + blockIdx.y * 3u + blockIdx.z) % (unsigned)CHUNKS);
 #pragma unroll 1
-        for (int t2 = 0; t2 < T; ++t2) {
+        for (int k = 0; k < CHUNKS; ++k, idx = (idx + 1 == CHUNKS ? 0 : idx + 1)) {
+            const int t2 = idx >> 2, c = (idx & 3) * 32;
             float* base = p.dw + (size_t)(tap + t2) * p.tap_stride + (size_t)cm * p.m_stride;
-#pragma unroll 1
-            for (int c = 0; c < 128; c += 32) {
-                uint32_t r[32];
-                tc::tmem_ld32(taddr + t2 * 128 + c, r);
-                tc::tmem_ld_wait();
-                if (row_ok) {
+            uint32_t r[32];
+            tc::tmem_ld32(taddr + t2 * 128 + c, r);
+            tc::tmem_ld_wait();
+            if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int cn = n_t * 128 + c + j;
-                        if (cn < p.cn) atomicAdd(base + (size_t)cn * p.n_stride, __uint_as_float(r[j]));
-                    }
+                for (int j = 0; j < 32; ++j) {
+                    const int cn = n_t * 128 + c + j;
+                    if (cn < p.cn) atomicAdd(base + (size_t)cn * p.n_stride, __uint_as_float(r[j]));
                 }
             }
         }
