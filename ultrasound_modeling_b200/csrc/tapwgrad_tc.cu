@@ -333,7 +333,10 @@ int tbi_tapwgrad_tc(const tbi_tapwgrad* d, cudaStream_t s) {
         //   waves * (K-steps per CTA + E),  E = the epilogue's T*128*BN reduction atomics expressed in K-steps (~32, measured:
         //   upsample_1 went 104 -> 210 us when an 8-way split left 8 K-steps per CTA in front of that epilogue)
         const long long sms = tbi_sm_count();
-        long long cap = total_tiles < 16 ? total_tiles : 16;
+        // (the cap was 16 while the reduction was scalar and contended; with vector reductions in rotated order a 49-way split of
+        // stage 2's concats_2 -- 3 output tiles -- fills the GPU: 187 -> ~75 us)
+        static const long long cap_env = getenv("TBI_WGRAD_KSPLIT_CAP") ? atoll(getenv("TBI_WGRAD_KSPLIT_CAP")) : 64;
+        long long cap = total_tiles < cap_env ? total_tiles : cap_env;
         long long best = -1; ksplit = 1;
         for (long long ks = 1; ks <= cap; ++ks) {
             const long long ctas = out_tiles * ks, waves = (ctas + sms - 1) / sms;
