@@ -15,7 +15,7 @@ _PKG = Path(__file__).resolve().parent
 _CSRC = _PKG / "csrc"
 LIB_PATH = _PKG / "libtbi_sm100.so"
 HASH_PATH = _PKG / "libtbi_sm100.so.hash"
-SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_halo.cu", "tapwgrad_tc.cu", "tapwgrad_tc2.cu", "tapwgrad_small.cu", "direct_small.cu", "splitatt_fused.cu", "bandwidth.cu", "variant_b.cu", "vit.cu", "data.cu"]
+SOURCES = ["c_api.cu", "tapgemm_simt.cu", "tapgemm_tc.cu", "tapgemm_halo.cu", "tapgemm_xpack.cu", "tapwgrad_tc.cu", "tapwgrad_tc2.cu", "tapwgrad_small.cu", "direct_small.cu", "splitatt_fused.cu", "bandwidth.cu", "variant_b.cu", "vit.cu", "data.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

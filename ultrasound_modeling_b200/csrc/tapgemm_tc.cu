@@ -278,6 +278,7 @@ static int launch_tc(const TcGemmParams& p, dim3 grid, size_t smem, cudaStream_t
 int tbi_tapgemm_tc(const tbi_tapgemm* d, cudaStream_t s) {
     const char* why = "";
     if (!tbi_tapgemm_tc_supported(d, &why)) return tbi_set_error(TBI_ERR_UNSUPPORTED, "tapgemm_tc: %s", why);
+    if (tbi_tapgemm_xpack_supported(d)) return tbi_tapgemm_xpack(d, s);     // 3x3, few channels: dx taps packed into N
     if (tbi_tapgemm_halo_supported(d)) return tbi_tapgemm_halo(d, s);       // large spatial extents: persistent halo schedule
     TcGemmParams p; memset(&p, 0, sizeof(p));
     const int kc = pick_kc(d);

@@ -112,6 +112,8 @@ int tbi_tapwgrad_small(const tbi_tapwgrad* d, cudaStream_t s);
 int tbi_splitatt_fwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* v, cudaStream_t s);     // 1 launched, 0 not applicable
 int tbi_splitatt_bwd_fused(const tbi_splitatt* p, const tbi_view* u, const tbi_view* dv, const tbi_view* du, float* scratch, cudaStream_t s);
 int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s);
+bool tbi_tapgemm_xpack_supported(const tbi_tapgemm* d);         // 3x3 stride-1, few channels: horizontal taps packed into N (tapgemm_xpack.cu)
+int tbi_tapgemm_xpack(const tbi_tapgemm* d, cudaStream_t s);
 int tbi_tapgemm_direct(const tbi_tapgemm* d, cudaStream_t s);   // few-input-channel direct conv (stem)
 int tbi_tapwgrad_direct(const tbi_tapwgrad* d, cudaStream_t s);
 bool tbi_tapgemm_direct_supported(const tbi_tapgemm* d);
