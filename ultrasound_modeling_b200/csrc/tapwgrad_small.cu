@@ -39,6 +39,7 @@ struct alignas(64) WsParams {
     int stages, a_stage_bytes, b_stage_bytes, a_tx, b_tx;
     float* dw;
     long long tap_stride, ci_stride, co_stride;
+    float* dbias;                 // bias gradient (column sums of dz) accumulated by the otherwise idle epilogue warps, or nullptr
 };
 
 template <int NB>   // N (= kcb) / 16
@@ -56,7 +57,8 @@ __global__ void __launch_bounds__(WS_THREADS) tapwgrad_small_kernel(const __grid
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 4 && lane == 0) {
         tc::prefetch_tmap(&p.a); tc::prefetch_tmap(&p.b);
-        for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        // a stage is free once its MMAs have completed AND (bias gradient fused) the four epilogue warps have summed its dz tile
+        for (int s = 0; s < p.stages; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], p.dbias ? 5 : 1); }
         tc::mbar_init(done, 1);
         tc::fence_barrier_init();
     }
@@ -121,6 +123,43 @@ __global__ void __launch_bounds__(WS_THREADS) tapwgrad_small_kernel(const __grid
         if (leader) tc::umma_commit(done);
         __syncwarp();
     } else if (iters > 0) {
+        if (p.dbias) {
+            // ---- bias gradient while the tiles stream by: dbias[co] += sum over the tile's 16 x 8 pixels of dz[pixel][co] ----
+            // (the separate column-sum kernel re-read every dz tensor from HBM: 26 launches, 420 us per step, 0.83 of the HBM
+            // peak, i.e. only fusion removes it).  The dz box is [18 or 16 rows][8 pixels][kcb channels], TMA-swizzled with
+            // Swizzle<B,4,3> on the byte offset within the 1 KB-aligned stage (B = 3 / 2 / 1 for 128 / 64 / 32-byte pixel rows).
+            // Thread t sums the 16-byte chunk (8 channels) t % nch of the pixels t / nch + k * (128 / nch).
+            const int t = warp * 32 + lane;
+            const int nch = p.kcb >> 3, c = t % nch, p0 = t / nch, pstep = 128 / nch;
+            const uint32_t bmask = (uint32_t)(p.kcb == 64 ? 7 : p.kcb == 32 ? 3 : 1);
+            float bs[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bs[j] = 0.f;
+            uint32_t s = 0, par = 0;
+            for (int it = 0; it < iters; ++it) {
+                tc::mbar_wait_bounded<true>(&full[s], par);
+                const uint8_t* bt = smem + (size_t)s * stage_bytes + p.a_stage_bytes;
+                for (int k = 0; k < nch; ++k) {
+                    const int px = p0 + k * pstep;                                    // pixel of the 16 x 8 centre, row-major
+                    const uint32_t o = (uint32_t)(px + 8 * p.halo) * rowb + (uint32_t)c * 16u;
+                    const uint4 v = *reinterpret_cast<const uint4*>(bt + (o ^ (((o >> 7) & bmask) << 4)));
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); bs[2 * j] += f.x; bs[2 * j + 1] += f.y; }
+                }
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&empty[s]);
+                if (++s == (uint32_t)p.stages) { s = 0; par ^= 1u; }
+            }
+            // lanes with equal t % nch hold the same channels: butterfly over the higher lane bits, then one atomic per warp
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float v = bs[j];
+                for (int o = 16; o >= nch; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const int co = c * 8 + j;
+                if (lane < nch && co < p.cout_g) atomicAdd(p.dbias + g * p.cout_g + co, v);
+            }
+        }
         // ===================== epilogue: TMEM lane = (dx block j, ci) ; columns = co ; one accumulator per dy =====================
         const int m = warp * 32 + lane;
         const int j = m / p.kca, ci = m % p.kca;
@@ -223,6 +262,7 @@ int tbi_tapwgrad_small(const tbi_tapwgrad* d, cudaStream_t s) {
     int stages = (100 * 1024) / stage_bytes; if (stages > 8) stages = 8; if (stages < 2) stages = 2;
     p.stages = stages;
     p.dw = d->dw; p.tap_stride = d->tap_stride; p.ci_stride = d->ci_stride; p.co_stride = d->co_stride;
+    p.dbias = d->dbias;                                    // column sums of dz ride along (the epilogue warps are idle in the main loop)
     int ctas = 2 * tbi_sm_count() / (d->groups > 0 ? d->groups : 1); if (ctas < 1) ctas = 1;
     if (ctas > p.total_tiles) ctas = p.total_tiles;
     p.tiles_per_cta = (p.total_tiles + ctas - 1) / ctas;
@@ -234,7 +274,5 @@ int tbi_tapwgrad_small(const tbi_tapwgrad* d, cudaStream_t s) {
         case 2:  rc = launch_ws<2>(p, grid, smem, s); break;
         default: rc = launch_ws<4>(p, grid, smem, s); break;
     }
-    if (rc) return rc;
-    if (d->dbias) return tbi_colsum(d->dtype, (int64_t)d->n * d->b_src.h * d->b_src.w, &d->b_src, d->dbias, (void*)s);
-    return TBI_OK;
+    return rc;
 }
