@@ -382,12 +382,14 @@ class Engine:
             self.keep.append(torch.ones(n, h, w, u["out"], dtype=torch.uint8, device=dev) if u["drop"] else None)
         self.logits = torch.empty(n, H, W, self.num_class, dtype=torch.float32, device=dev)
         self.probs = torch.empty(n, H, W, self.num_class, dtype=torch.float32, device=dev)
-        # bf16: the head gradient is stored with 16 channels per pixel (3 real + zeros) so that its pixel records are
-        # 16-byte aligned for TMA; the loss kernel writes the real channels only, the padding stays zero
-        self.dl_c = 16 if self.dt == BF16 else self.num_class
-        self.dlogits = torch.zeros(n, H, W, self.dl_c, dtype=td, device=dev)
         # bf16: the head's backward runs on the GATHERED gradient G[n,H/2,W/2, 16 taps x num_class (padded to 64 channels)]
         self.head_gather = self.dt == BF16 and 16 * self.num_class <= 64
+        # bf16 head gradient: 4 channels per pixel (8-byte records: 3 real + a zero) when only the gather and the bias column sum
+        # read it -- 33 MB instead of the 134 MB of 16-channel records at 64 x 256 x 256, which the loss kernel wrote and the
+        # gather re-read sector by sector; 16 channels (16-byte aligned pixel records for TMA) when the transposed-conv kernels
+        # read it directly.  The loss kernel writes the real channels only, the padding stays zero.
+        self.dl_c = (4 if self.head_gather else 16) if self.dt == BF16 else self.num_class
+        self.dlogits = torch.zeros(n, H, W, self.dl_c, dtype=td, device=dev)
         if self.head_gather:
             self.head_g = torch.zeros(n, H // 2, W // 2, 64, dtype=td, device=dev)
             self.head_wg = torch.zeros(self.head.cin * 64, dtype=td, device=dev)
