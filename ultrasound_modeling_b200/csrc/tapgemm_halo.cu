@@ -48,6 +48,11 @@ struct alignas(64) HaloParams {
     int flat;                      // resident + one halo per chunk + (ntaps, ksteps) has an unrolled issue loop
     int rank4;                     // stride-1 sources: 4-D tensor map (C, W, H, N) instead of the 5-D parity view
     int pair, m_pairs;             // PAIR mode (cta_group::2): iterations are (slab, pair of M tiles); m_pairs = ceil(m_tiles / 2)
+    // Side inputs of the epilogue (act' reference, residual, skip-gradient accumulator): the producer thread asks L2 for the
+    // tile's box of each with ONE cp.async.bulk.prefetch.tensor when it loads the tile's first halo, i.e. a ring depth ahead of
+    // the epilogue, whose one-row-per-thread loads then hit L2 instead of waiting a DRAM round trip per 32-column chunk.
+    CUtensorMap side[3];
+    int nside, side_split[3];      // side_split[k]: map k covers the channels >= split_c (out2 / residual2) instead of the main ones
     unsigned long long* trace;     // debug timeline buffer or nullptr (a kernel parameter: testing it costs no memory access)
     tbi_epilogue epi;
 };
@@ -383,6 +388,12 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                 if (mt >= p.m_tiles) mt = p.m_tiles - 1;                 // odd tile count: load something valid, the epilogue drops it
                 decode_mtile(p, mt, t.x0, t.y0, t.n0);
             } else if (p.resident) { t = slab_t; decode_mtile(p, i, t.x0, t.y0, t.n0); } else t = decode_tile(p, i, BN);
+            if (p.nside && leader) {
+                const int co0 = t.cg * p.cout_g + t.nc0;
+                const int in_split = (p.epi.split_c > 0 && co0 >= p.epi.split_c) ? 1 : 0;
+                for (int k = 0; k < p.nside; ++k)
+                    if (p.side_split[k] == in_split) tc::tma_prefetch_4d(&p.side[k], in_split ? co0 - p.epi.split_c : co0, t.x0, t.y0, t.n0);
+            }
             for (int c = 0; c < p.nchunks; ++c) {
                 const int ch = c * p.kc;
                 int src = 0, cch = ch + (p.cgroups > 1 ? t.cg * p.cin_g : 0);
@@ -743,6 +754,14 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     int bn = 128;
     while (bn > 16 && bn / 2 >= d->cout_g) bn >>= 1;
     if (p.narrow) bn = 16;                                   // the element-wise epilogue exists for 16-column tiles only
+    {
+        // A weights-resident CTA is tied to ONE N tile.  With a ragged last tile (the head's data gradient: 160 = 128 + 32
+        // columns over one 64-channel K chunk, all epilogue) the CTAs of the full tile carry 4x the work of the others, and block
+        // ids are dealt to SMs round-robin, so with two slabs the heavy CTAs all land on the even SMs.  Equal 32-column slabs
+        // instead (5 x 59 CTAs; the 16 KB halo is then read five times, from L2): 387 -> 310 us, step 7.68 -> 7.62 ms.
+        static const bool ragged32 = getenv("TBI_HALO_NO_RAGGED_BN32") == nullptr;
+        if (ragged32 && !p.narrow && bn >= 64 && d->cout_g % bn != 0 && d->cout_g % 32 == 0 && d->groups == 1 && p.nphase == 1 && kc == 64 && d->cin_g == 64) bn = 32;
+    }
     p.n_tiles = (d->cout_g + bn - 1) / bn;
     p.total_tiles = p.m_tiles * p.cgroups * p.nphase * p.n_tiles;
     p.nslabs = p.n_tiles * p.cgroups * p.nphase;
@@ -781,6 +800,30 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         const int ks = kc / 16, nt = d->ntaps;
         const bool have = (nt == 1 && (ks == 1 || ks == 2 || ks == 4)) || (nt == 4 && (ks == 2 || ks == 4)) || (nt == 9 && (ks == 1 || ks == 2 || ks == 4));
         p.flat = (p.resident && p.ngroups == 1 && have && !no_flat) ? 1 : 0;
+    }
+    {
+        static const bool no_pf = getenv("TBI_HALO_NO_SIDE_PF") != nullptr;
+        const tbi_epilogue& e = d->epi;
+        p.nside = 0;
+        if (!no_pf && !p.narrow && !p.f32wide && p.nphase == 1 && p.out_stride == 1 && e.out_off_x == 0 && e.out_off_y == 0) {
+            auto add = [&](const tbi_view& v, int split) -> int {
+                if (!v.ptr || ((v.cstride * 2) & 15) || ((v.coff * 2) & 15) || (((uintptr_t)v.ptr) & 15)) return TBI_OK;
+                int cols = v.c < bn ? v.c : bn;
+                cols &= ~7;
+                if (cols <= 0) return TBI_OK;
+                const uint64_t px = (uint64_t)v.cstride * 2;
+                uint64_t d4[4] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)d->n};
+                uint64_t s4[3] = {px, px * v.w, px * v.w * v.h};
+                uint32_t b4[4] = {(uint32_t)cols, (uint32_t)TW, (uint32_t)TH, 1u};
+                p.side_split[p.nside] = split;
+                const int r = tbi_make_tmap_bf16(&p.side[p.nside], (char*)v.ptr + (size_t)v.coff * 2, 4, d4, s4, b4, 0);
+                if (r == TBI_OK) ++p.nside;
+                return r;
+            };
+            if (e.dact != TBI_ACT_NONE) { rc = add(e.dact_ref, 0); if (rc) return rc; }
+            rc = add(e.residual, 0); if (rc) return rc;
+            if (e.split_c > 0) { rc = add(e.residual2, 1); if (rc) return rc; }
+        }
     }
     auto lg2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; };
     p.sh_x = lg2(p.tiles_x); p.sh_y = lg2(p.tiles_y);
