@@ -159,22 +159,43 @@ def test_cuda_graph_replay_equals_eager(cuda_device):
         net.load_variables(o.state_dict())
     x2 = V.B.synthetic_input(2, 64, 32, 10); y2 = V.synthetic_labels(2, 64, 32)
     x4 = V.B.synthetic_input(4, 64, 32, 10, seed=77); y4 = V.synthetic_labels(4, 64, 32, seed=78)
+    # (1) at FIXED variables: backward() through replay == eager, tensor by tensor.  Not bit-equal: fp32 sums (split-K partials,
+    # atomics) are taken in a different order from one net / call to the next; the key bias gradient is exactly 0 in exact
+    # arithmetic (softmax shift invariance), i.e. pure rounding noise, and is skipped.
+    for (x, y) in [(x2, y2), (x4, y4)]:
+        for _ in range(4):                                   # two eager warm-ups, the capture, one replay
+            (la, _), (lb, _) = nets[0].backward(x, y), nets[1].backward(x, y)
+        ga, gb = nets[0].gradients(), nets[1].gradients()
+        assert abs(float(la) - float(lb)) < 1e-5 * abs(float(la))
+        worst = max((rel(gb[k], ga[k]), k) for k in ga if not k.endswith("attn/key/bias"))
+        assert worst[0] < 5e-3, worst
+    # step() / forward() through replay at the same (identical) variables
+    for _ in range(4):
+        (la, pa), (lb, pb) = nets[0].step(x2, y2), nets[1].step(x2, y2)
+        fa, fb = nets[0].forward(x4), nets[1].forward(x4)
+    assert abs(float(la) - float(lb)) < 1e-5 * abs(float(la)) and rel(pb, pa) < 1e-4 and rel(fb[0], fa[0]) < 1e-4
+    assert len(fb[1]) == 2 and rel(fb[1][0], fa[1][0]) < 1e-4
+    # (2) six optimizer steps across a batch-size change and back.  Two EAGER nets already part ways here (measured on B200,
+    # scratch/vit_div.py: loss 1e-7 apart for the first steps, then up to 7e-4 by step 10; ~20 % of the variables more than
+    # 2e-5 apart, 1.3e-3 at most): summation-order differences of ~1e-4 in a few cancellation-heavy gradients are turned into
+    # full-size steps by global-norm clipping + Adam.  The bounds below are that chaos with margin; a replay that used stale
+    # inputs or stale variable storage is off by O(1) (the x2 and x4 losses differ by 2x).
     losses = [[], []]
     for (x, y) in [(x2, y2)] * 4 + [(x4, y4)] * 4 + [(x2, y2)] * 2:
         for i, net in enumerate(nets):
             loss, probs = net.train_step(x, y)
             losses[i].append(float(loss))
     assert len(nets[1]._graphs) >= 2 and all(e["graph"] is not None for e in nets[1]._graphs.values())
-    assert max(abs(a - b) / abs(a) for a, b in zip(*losses)) < 1e-4, losses
+    assert max(abs(a - b) / abs(a) for a, b in zip(*losses[:2])) < 5e-3, losses
+    assert max(abs(a - b) / abs(a) for a, b in zip(losses[0][:3], losses[1][:3])) < 1e-5, losses
     va, vb = nets[0].variables(), nets[1].variables()
-    # fp32 atomics reorder sums between runs; Adam turns rounding-level differences into steps of at most lr
     diffs = torch.cat([(va[k] - vb[k]).abs().reshape(-1) for k in va])
-    assert float((diffs > 1e-3 * 2e-2).double().mean()) < 1e-3 and float(diffs.max()) < 1e-2
-    for _ in range(4):
+    assert float(diffs.mean()) < 2e-4 and float(diffs.max()) < 1e-2
+    # the replayed step / forward graphs read the UPDATED variables (same storage): still the eager net's answer up to the divergence above
+    for _ in range(2):
         (la, pa), (lb, pb) = nets[0].step(x2, y2), nets[1].step(x2, y2)
         fa, fb = nets[0].forward(x4), nets[1].forward(x4)
-    assert abs(float(la) - float(lb)) < 1e-3 * abs(float(la)) and rel(pb, pa) < 2e-3 and rel(fb[0], fa[0]) < 2e-3
-    assert len(fb[1]) == 2 and rel(fb[1][0], fa[1][0]) < 2e-3
+    assert abs(float(la) - float(lb)) < 5e-3 * abs(float(la)) and rel(pb, pa) < 5e-2 and rel(fb[0], fa[0]) < 5e-2
     # a learning-rate change reaches the replayed step (the Adam tail reads a device buffer)
     before = nets[1].variables()["decoder/head/bias"].clone()
     nets[1].optimizer.learning_rate = 0.0

@@ -48,6 +48,11 @@ struct alignas(64) HaloParams {
     int flat;                      // resident + one halo per chunk + (ntaps, ksteps) has an unrolled issue loop
     int rank4;                     // stride-1 sources: 4-D tensor map (C, W, H, N) instead of the 5-D parity view
     int pair, m_pairs;             // PAIR mode (cta_group::2): iterations are (slab, pair of M tiles); m_pairs = ceil(m_tiles / 2)
+    // iteration space of a CTA: it_first (from blockIdx), then += it_stride while < it_count.  Host-computed and read from the
+    // constant bank: as kernel-computed values they were live across every role and SPILLED -- the reload sat in the loop
+    // control of the epilogue, producer and MMA loops, and with ~210 KB of the SM's 228 KB in shared memory a local-memory
+    // load is an L2 round trip (ncu: 14 % of the head data gradient's stall samples on the instruction behind that LDL).
+    int it_stride, it_count;
     // Side inputs of the epilogue (act' reference, residual, skip-gradient accumulator): the producer thread asks L2 for the
     // tile's box of each with ONE cp.async.bulk.prefetch.tensor when it loads the tile's first halo, i.e. a ring depth ahead of
     // the epilogue, whose one-row-per-thread loads then hit L2 instead of waiting a DRAM round trip per 32-column chunk.
@@ -58,9 +63,16 @@ struct alignas(64) HaloParams {
 };
 
 // optional timeline trace (debug): block 0 writes clock64 stamps, [role][tile][event]; enabled by tbi_debug_set_halo_trace()
+// Compiled in only with -DTBI_HALO_TRACE (scratch/ timeline scripts): the stamps cost registers in every role.
+#ifdef TBI_HALO_TRACE
 __device__ __forceinline__ void trace(unsigned long long* tr, int role, int tile, int ev) {
     if (tr && blockIdx.x == 0 && tile < 64) tr[(role * 64 + tile) * 8 + ev] = clock64();
 }
+#define TBI_TRACE_PTR(p) ((p).trace)
+#else
+__device__ __forceinline__ void trace(unsigned long long*, int, int, int) {}
+#define TBI_TRACE_PTR(p) ((unsigned long long*)nullptr)
+#endif
 
 static unsigned long long* g_halo_trace_host = nullptr;
 
@@ -69,6 +81,20 @@ static unsigned long long* g_halo_trace_host = nullptr;
 __host__ __device__ constexpr int halo_nbuf(int bn) { return bn <= 32 ? 4 : 2; }
 
 struct TileCoord { int x0, y0, n0, nc0, cg, ph; };
+
+// Per-CTA constants of the roles (TMEM base address, the resident slab's (N tile, group, phase)) live in four shared-memory
+// words and are re-read with ld.volatile.shared where they are used: as ordinary values they were live across the whole
+// epilogue loop, ptxas spilled them, and a local-memory reload in these kernels is an L2 round trip (see it_stride above) --
+// a shared-memory load is ~30 cycles and needs no register between uses.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+#define SLOT_TMEM(ts) lds_u32(ts)
+#define SLOT_NC0(ts)  ((int)lds_u32((ts) + 4))
+#define SLOT_CG(ts)   ((int)lds_u32((ts) + 8))
+#define SLOT_PH(ts)   ((int)lds_u32((ts) + 12))
 
 __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile, int BN) {
     TileCoord t;
@@ -91,8 +117,8 @@ __device__ __forceinline__ void decode_mtile(const HaloParams& p, int mt, int& x
     }
 }
 // lane 0 does the divisions, the warp gets the result by shuffle
-__device__ __forceinline__ TileCoord decode_tile_warp(const HaloParams& p, int tile, int BN, int lane, const TileCoord& slab_t, int mt) {
-    if (p.resident) { TileCoord t = slab_t; decode_mtile(p, mt, t.x0, t.y0, t.n0); return t; }
+__device__ __forceinline__ TileCoord decode_tile_warp(const HaloParams& p, int tile, int BN, int lane, uint32_t ts, int mt) {
+    if (p.resident) { TileCoord t; t.nc0 = SLOT_NC0(ts); t.cg = SLOT_CG(ts); t.ph = SLOT_PH(ts); decode_mtile(p, mt, t.x0, t.y0, t.n0); return t; }
     TileCoord t{};
     if (lane == 0) t = decode_tile(p, tile, BN);
     t.x0 = __shfl_sync(0xffffffffu, t.x0, 0); t.y0 = __shfl_sync(0xffffffffu, t.y0, 0); t.n0 = __shfl_sync(0xffffffffu, t.n0, 0);
@@ -103,7 +129,7 @@ __device__ __forceinline__ TileCoord decode_tile_warp(const HaloParams& p, int t
 struct Rings {
     uint8_t* a_ring; uint8_t* b_ring;
     uint64_t *a_full, *a_empty, *b_full, *b_empty, *t_full, *t_empty, *b_res;
-    int slab, it_first, it_stride, it_count;
+    int slab, it_first;
 };
 
 
@@ -113,7 +139,7 @@ struct Rings {
 // instructions per MMA; for N=32 tiles -- 16 cycles of math per MMA -- the single issuing thread was the bottleneck:
 // ~210 cycles per MMA measured against ~49 for a free-running issue loop, profiles/r1_summary.md.)
 template <int NTAPS, int KSTEPS>
-__device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, const Rings& R, uint32_t tmem_base, uint32_t acc_cols, bool leader,
+__device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, const Rings& R, uint32_t ts, uint32_t acc_cols, bool leader,
                                                        uint32_t idesc, uint32_t a_base, uint32_t a_stage_lo, uint32_t a_hi,
                                                        uint32_t b_base, uint32_t b_stage_lo, uint32_t b_hi, uint32_t row_lo, int ph, uint32_t nbuf) {
     uint32_t a_off[NTAPS];
@@ -121,19 +147,19 @@ __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, cons
     for (int t = 0; t < NTAPS; ++t) a_off[t] = ((uint32_t)p.t_row[ph][t] & 0x3FFu) * row_lo;
     uint32_t sa = 0, a_par = 0, acc_it = 0;
     const uint32_t lgb = nbuf == 4 ? 2u : 1u;
-    for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+    for (int i = R.it_first; i < p.it_count; i += p.it_stride, ++acc_it) {
         const uint32_t buf = acc_it & (nbuf - 1u);
-        trace(p.trace, 1, acc_it, 0);
+        trace(TBI_TRACE_PTR(p), 1, acc_it, 0);
         tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> lgb) & 1u) ^ 1u);
         tc::tc_fence_after();
-        trace(p.trace, 1, acc_it, 1);
-        const uint32_t tmem_d = tmem_base + buf * acc_cols;
+        trace(TBI_TRACE_PTR(p), 1, acc_it, 1);
+        const uint32_t tmem_d = SLOT_TMEM(ts) + buf * acc_cols;
         uint32_t b_lo = b_base;
 #pragma unroll 1
         for (int c = 0; c < p.nchunks; ++c) {
             tc::mbar_wait_bounded(&R.a_full[sa], a_par);
             tc::tc_fence_after();
-            trace(p.trace, 1, acc_it, 2);
+            trace(TBI_TRACE_PTR(p), 1, acc_it, 2);
             const uint32_t a_lo = a_base + sa * a_stage_lo;
             if (leader) {
 #pragma unroll
@@ -147,7 +173,7 @@ __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, cons
             if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
         }
         if (leader) tc::umma_commit(&R.t_full[buf]);
-        trace(p.trace, 1, acc_it, 3);
+        trace(TBI_TRACE_PTR(p), 1, acc_it, 3);
     }
 }
 
@@ -159,14 +185,14 @@ __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, cons
 // half of the weight stage), issued by the leader CTA only; commits are multicast so both CTAs' producers and epilogues see
 // them, and the accumulator-free barrier collects the epilogue warps of both CTAs.
 template <int BN, bool PAIR, int NTAPS, int KSTEPS>
-__device__ __forceinline__ void streamed_mma_loop(const HaloParams& p, const Rings& R, uint32_t tmem_base, bool leader, uint32_t idesc,
+__device__ __forceinline__ void streamed_mma_loop(const HaloParams& p, const Rings& R, uint32_t ts, bool leader, uint32_t idesc,
                                                   uint32_t a_base, uint32_t a_stage_lo, uint32_t a_hi, uint32_t b_base, uint32_t b_stage_lo,
                                                   uint32_t b_hi, uint32_t row_lo) {
     uint32_t toff[NTAPS];
     uint32_t first_mask = 0, last_mask = 0;
     int cur_ph = -1;
     uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0, acc_it = 0;
-    for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+    for (int i = R.it_first; i < p.it_count; i += p.it_stride, ++acc_it) {
         const int ph = (p.nphase > 1 ? decode_tile(p, PAIR ? i % p.nslabs : i, BN).ph : 0);
         if (ph != cur_ph) {
             first_mask = last_mask = 0;
@@ -180,12 +206,12 @@ __device__ __forceinline__ void streamed_mma_loop(const HaloParams& p, const Rin
             cur_ph = ph;
         }
         const uint32_t buf = acc_it & 1u;
-        trace(p.trace, 1, acc_it, 0);
+        trace(TBI_TRACE_PTR(p), 1, acc_it, 0);
         if (PAIR) { if (!tc::mbar_try_wait_cluster(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u)) { const long long t0 = clock64(); while (!tc::mbar_try_wait_cluster(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u)) { if (clock64() - t0 > 6000000000LL) { printf("tbi tcgen05 (pair): accumulator barrier timeout (block %d)\n", blockIdx.x); __trap(); } } } }
         else tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> 1) & 1u) ^ 1u);
         tc::tc_fence_after();
-        trace(p.trace, 1, acc_it, 1);
-        const uint32_t tmem_d = tmem_base + buf * BN;
+        trace(TBI_TRACE_PTR(p), 1, acc_it, 1);
+        const uint32_t tmem_d = SLOT_TMEM(ts) + buf * BN;
         uint32_t a_lo = 0;
         long long wait_a = 0, wait_b = 0, tw = 0;          // debug timeline only (p.trace): cycles this tile spent waiting for operands
 #pragma unroll 1
@@ -193,15 +219,15 @@ __device__ __forceinline__ void streamed_mma_loop(const HaloParams& p, const Rin
 #pragma unroll
             for (int t = 0; t < NTAPS; ++t) {
                 if ((first_mask >> t) & 1u) {
-                    if (p.trace) tw = clock64();
+                    if (TBI_TRACE_PTR(p)) tw = clock64();
                     tc::mbar_wait_bounded(&R.a_full[sa], a_par);
-                    if (p.trace) wait_a += clock64() - tw;
-                    trace(p.trace, 1, acc_it, 2);
+                    if (TBI_TRACE_PTR(p)) wait_a += clock64() - tw;
+                    trace(TBI_TRACE_PTR(p), 1, acc_it, 2);
                     a_lo = a_base + sa * a_stage_lo;
                 }
-                if (p.trace) tw = clock64();
+                if (TBI_TRACE_PTR(p)) tw = clock64();
                 tc::mbar_wait_bounded(&R.b_full[sb], b_par);
-                if (p.trace) wait_b += clock64() - tw;
+                if (TBI_TRACE_PTR(p)) wait_b += clock64() - tw;
                 tc::tc_fence_after();
                 const uint32_t al = a_lo + toff[t], bl = b_base + sb * b_stage_lo;
                 if (leader) {
@@ -220,13 +246,13 @@ __device__ __forceinline__ void streamed_mma_loop(const HaloParams& p, const Rin
             }
         }
         if (leader) { if (PAIR) tc::umma_commit_pair(&R.t_full[buf]); else tc::umma_commit(&R.t_full[buf]); }
-        trace(p.trace, 1, acc_it, 3);
-        if (p.trace && blockIdx.x == 0 && acc_it < 64) { p.trace[(64 + acc_it) * 8 + 4] = (unsigned long long)wait_a; p.trace[(64 + acc_it) * 8 + 5] = (unsigned long long)wait_b; }
+        trace(TBI_TRACE_PTR(p), 1, acc_it, 3);
+        if (TBI_TRACE_PTR(p) && blockIdx.x == 0 && acc_it < 64) { p.trace[(64 + acc_it) * 8 + 4] = (unsigned long long)wait_a; p.trace[(64 + acc_it) * 8 + 5] = (unsigned long long)wait_b; }
     }
 }
 
 template <int BN, bool PAIR, int ACT, int DACT>
-__device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, const float* sbias, uint32_t tmem_base, int warp, int lane) {
+__device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& R, const float* sbias, uint32_t ts, int warp, int lane) {
     // Two groups of four warps (one warp per TMEM lane quadrant).  Group g owns accumulator buffer g, i.e. every
     // second tile, so the epilogues of consecutive tiles overlap (the per-tile chain wait -> tcgen05.ld -> loads ->
     // math -> stores is latency-bound for small K).
@@ -237,14 +263,12 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     const int m = q * 32 + lane;
     const int xx = m & (TW - 1), yy = m >> 3;
     uint32_t acc_it = 0;
-    TileCoord slab_t{};
-    if (p.resident) slab_t = decode_tile(p, R.slab, BN);
-    unsigned long long* tr = (warp == 0 && lane == 0) ? p.trace : nullptr;
+    unsigned long long* tr = (warp == 0 && lane == 0) ? TBI_TRACE_PTR(p) : nullptr;
     const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
     // PAIR: the accumulator-free barrier the MMA thread waits on lives in the leader CTA
     uint32_t te_addr[2] = {0u, 0u};
     if (PAIR) { te_addr[0] = tc::map_to_cta(tc::smem_u32(&R.t_empty[0]), 0); te_addr[1] = tc::map_to_cta(tc::smem_u32(&R.t_empty[1]), 0); }
-    for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+    for (int i = R.it_first; i < p.it_count; i += p.it_stride, ++acc_it) {
         if ((int)(acc_it & 1u) != grp) continue;
         const uint32_t buf = acc_it & (NBUF - 1u);
         TileCoord t;
@@ -254,21 +278,17 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
             const int mt = 2 * (i / p.nslabs) + (int)rank;   // this CTA's pixel tile of the pair
             tile_ok = mt < p.m_tiles;                        // odd tile count: the last pair's second CTA repeats a tile and drops it
             decode_mtile(p, tile_ok ? mt : 0, t.x0, t.y0, t.n0);
-        } else t = decode_tile_warp(p, i, BN, lane, slab_t, i);
+        } else t = decode_tile_warp(p, i, BN, lane, ts, i);
         trace(tr, 2, acc_it, 0);
         const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
         const bool valid = tile_ok && gx < p.gw && gy < p.gh;
         const int oy = gy * p.out_stride + (p.nphase > 1 ? p.ph_off_y[t.ph] : p.epi.out_off_y);
         const int ox = gx * p.out_stride + (p.nphase > 1 ? p.ph_off_x[t.ph] : p.epi.out_off_x);
-        RowCtx rc{};
-        if (valid && !p.narrow && !p.f32wide) {
-            rc = make_row_ctx(p.epi, n, oy, ox);
-            if (rc.bias) rc.bias = sbias;
-        }
+        const LeanRowCtx rc = make_lean_row_ctx(p.epi, n, oy, ox, p.epi.bias ? sbias : nullptr);
         tc::mbar_wait_bounded<true>(&R.t_full[buf], (acc_it >> LGB) & 1u);
         tc::tc_fence_after();
         trace(tr, 2, acc_it, 1);
-        const uint32_t taddr = tmem_base + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
+        const uint32_t taddr = SLOT_TMEM(ts) + buf * ACC_COLS + ((uint32_t)(q * 32) << 16);
         if constexpr (BN >= 32) {
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
@@ -341,11 +361,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
     // tile iteration: streaming = round-robin over all tiles; resident = this CTA's slab x a strided set of M tiles
     R.slab = p.resident ? (int)(blockIdx.x % p.nslabs) : 0;
     R.it_first = p.resident ? (int)(blockIdx.x / p.nslabs) : (int)blockIdx.x;
-    R.it_stride = p.resident ? (int)(gridDim.x / p.nslabs) : (int)gridDim.x;
-    R.it_count = p.resident ? p.m_tiles : p.total_tiles;
     const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
     if (PAIR) {                    // a cluster of two CTAs walks (slab, tile pair) iterations; CTA `rank` owns tile 2*pair + rank
-        R.it_first = (int)(blockIdx.x >> 1); R.it_stride = (int)(gridDim.x >> 1); R.it_count = p.m_pairs * p.nslabs;
+        R.it_first = (int)(blockIdx.x >> 1);
     }
 
     // the scheduler prefers higher warp ids: the two single-issuer warps get the highest ids so the epilogue math cannot starve them
@@ -361,26 +379,31 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         tc::fence_barrier_init();
     }
     if (warp == W_MMA) { if (PAIR) tc::tmem_alloc_pair<TMEM_COLS>(tslot); else tc::tmem_alloc<TMEM_COLS>(tslot); }
+    if (threadIdx.x == 0) {
+        TileCoord st{};
+        if (p.resident) st = decode_tile(p, R.slab, BN);
+        tslot[1] = (uint32_t)st.nc0; tslot[2] = (uint32_t)st.cg; tslot[3] = (uint32_t)st.ph;
+    }
     tc::tc_fence_before();
     __syncthreads();
     if (PAIR) tc::cluster_sync_all();                       // the peer's barriers exist before anything is signalled across the pair
     tc::tc_fence_after();
-    const uint32_t tmem_base = *tslot;
+    const uint32_t ts = tc::smem_u32(tslot);                // [0] TMEM base (written by tcgen05.alloc), [1..3] the resident slab's nc0 / cg / ph
 
     if (warp == W_TMA) {
         // ===================== TMA producer: the whole warp walks the loop, one elected lane issues =====================
         const bool leader = tc::elect_one();
         uint32_t a_it = 0, sa = 0, a_par = 1, sb = 0, b_par = 1;       // ring stage + parity (empty barriers start "free")
         TileCoord slab_t{};
-        if (p.resident) slab_t = decode_tile(p, R.slab, BN);
-        if (p.resident && R.it_first < R.it_count && leader) {            // the whole weight slab, once
+        if (p.resident) { slab_t.nc0 = SLOT_NC0(ts); slab_t.cg = SLOT_CG(ts); slab_t.ph = SLOT_PH(ts); }
+        if (p.resident && R.it_first < p.it_count && leader) {            // the whole weight slab, once
             tc::mbar_expect_tx(R.b_res, (uint32_t)(p.nchunks * p.ntaps) * p.b_tx);
             for (int c = 0; c < p.nchunks; ++c)
                 for (int tap = 0; tap < p.ntaps; ++tap)
                     tc::tma_load_2d(R.b_ring + (size_t)(c * p.ntaps + tap) * p.b_stage_bytes, &p.b, R.b_res,
                                     (int)p.t_kidx[slab_t.ph][tap] * p.cin_g + c * p.kc, slab_t.ph * p.cout_total + slab_t.cg * p.cout_g + slab_t.nc0);
         }
-        for (int i = R.it_first; i < R.it_count; i += R.it_stride) {
+        for (int i = R.it_first; i < p.it_count; i += p.it_stride) {
             TileCoord t;
             if (PAIR) {
                 t = decode_tile(p, i % p.nslabs, BN);
@@ -400,9 +423,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                 if (p.cgroups == 1 && cch >= p.c0) { src = 1; cch -= p.c0; }
                 int tap = 0;
                 for (int grp = 0; grp < p.ngroups; ++grp) {
-                    trace(p.trace, 0, a_it, 0);
+                    trace(TBI_TRACE_PTR(p), 0, a_it, 0);
                     tc::mbar_wait_bounded(&R.a_empty[sa], a_par);
-                    trace(p.trace, 0, a_it, 1);
+                    trace(TBI_TRACE_PTR(p), 0, a_it, 1);
                     if (leader && PAIR) {
                         // both CTAs' halos complete on the LEADER's barrier (it expects the pair's bytes)
                         if (rank == 0) tc::mbar_expect_tx(&R.a_full[sa], 2u * (uint32_t)p.a_tx);
@@ -455,7 +478,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         const uint32_t row_lo = (uint32_t)p.row_bytes >> 4;
         const int ksteps = p.kc / 16;
         uint32_t a_it = 0, b_it = 0, acc_it = 0;
-        const int slab_ph = p.resident ? decode_tile(p, R.slab, BN).ph : 0;
+        const int slab_ph = p.resident ? SLOT_PH(ts) : 0;
         // per-phase tap table packed into registers: 12 bits per tap = row offset (10) | first-of-group (1) | last-of-group (1),
         // five taps per 64-bit word, consumed by a running shift -> no memory load sits in front of an MMA
         unsigned long long tw0 = 0, tw1 = 0, tw2 = 0, tw3 = 0; int cur_ph = -1;
@@ -474,9 +497,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         bool flat_done = false;
         if (p.resident && p.ngroups == 1 && p.flat) {
             // ---- weights resident, one halo per chunk: unrolled issue stream ----
-            if (R.it_first < R.it_count) tc::mbar_wait_bounded(R.b_res, 0);
+            if (R.it_first < p.it_count) tc::mbar_wait_bounded(R.b_res, 0);
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
-#define TBI_FLAT(NT, KS) resident_flat_mma_loop<NT, KS>(p, R, tmem_base, ACC_COLS, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo, slab_ph, NBUF)
+#define TBI_FLAT(NT, KS) resident_flat_mma_loop<NT, KS>(p, R, ts, ACC_COLS, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo, slab_ph, NBUF)
             switch (p.ntaps * 8 + ksteps) {
                 case 1 * 8 + 1: TBI_FLAT(1, 1); break;
                 case 1 * 8 + 2: TBI_FLAT(1, 2); break;
@@ -493,7 +516,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         if (!flat_done && !p.resident && BN >= 64 && ksteps == 4) {
             // ---- weights streamed, 64-channel stages: unrolled issue stream per tap count (NBUF == 2 for BN >= 64) ----
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
-#define TBI_STREAM(NT) streamed_mma_loop<BN, PAIR, NT, 4>(p, R, tmem_base, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo)
+#define TBI_STREAM(NT) streamed_mma_loop<BN, PAIR, NT, 4>(p, R, ts, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo)
             if constexpr (BN >= 64) {
                 switch (p.ntaps) {
                     case 1:  TBI_STREAM(1); flat_done = true; break;
@@ -508,16 +531,16 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         if (flat_done) {
         } else if (p.resident) {
             // ---- weights resident: nothing but halo waits, descriptor adds and MMAs in the steady state ----
-            if (R.it_first < R.it_count) { load_taps(slab_ph); tc::mbar_wait_bounded(R.b_res, 0); }
+            if (R.it_first < p.it_count) { load_taps(slab_ph); tc::mbar_wait_bounded(R.b_res, 0); }
             uint32_t sa = 0, a_par = 0;
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
-            for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+            for (int i = R.it_first; i < p.it_count; i += p.it_stride, ++acc_it) {
                 const uint32_t buf = acc_it & (NBUF - 1u);
-                trace(p.trace, 1, acc_it, 0);
+                trace(TBI_TRACE_PTR(p), 1, acc_it, 0);
                 tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> LGB) & 1u) ^ 1u);
                 tc::tc_fence_after();
-                trace(p.trace, 1, acc_it, 1);
-                const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+                trace(TBI_TRACE_PTR(p), 1, acc_it, 1);
+                const uint32_t tmem_d = SLOT_TMEM(ts) + buf * ACC_COLS;
                 uint32_t accum = 0, b_lo = b_base, a_lo = 0;
 #pragma unroll 1
                 for (int c = 0; c < p.nchunks; ++c) {
@@ -530,7 +553,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                         if (e & 0x400u) {
                             tc::mbar_wait_bounded(&R.a_full[sa], a_par);
                             tc::tc_fence_after();
-                            trace(p.trace, 1, acc_it, 2);
+                            trace(TBI_TRACE_PTR(p), 1, acc_it, 2);
                             a_lo = a_base + sa * a_stage_lo;
                         }
                         const uint32_t al = a_lo + (e & 0x3FFu) * row_lo;
@@ -546,21 +569,21 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                     }
                 }
                 if (leader) tc::umma_commit(&R.t_full[buf]);
-                trace(p.trace, 1, acc_it, 3);
+                trace(TBI_TRACE_PTR(p), 1, acc_it, 3);
             }
         } else {
             // ---- weights streamed: one B stage per (chunk, tap); wrap-around stage counters, nothing but waits + MMAs ----
             uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0;
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
-            for (int i = R.it_first; i < R.it_count; i += R.it_stride, ++acc_it) {
+            for (int i = R.it_first; i < p.it_count; i += p.it_stride, ++acc_it) {
                 const int ph = (p.nphase > 1 ? decode_tile(p, i, BN).ph : 0);
                 if (ph != cur_ph) load_taps(ph);
                 const uint32_t buf = acc_it & (NBUF - 1u);
-                trace(p.trace, 1, acc_it, 0);
+                trace(TBI_TRACE_PTR(p), 1, acc_it, 0);
                 tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> LGB) & 1u) ^ 1u);
                 tc::tc_fence_after();
-                trace(p.trace, 1, acc_it, 1);
-                const uint32_t tmem_d = tmem_base + buf * ACC_COLS;
+                trace(TBI_TRACE_PTR(p), 1, acc_it, 1);
+                const uint32_t tmem_d = SLOT_TMEM(ts) + buf * ACC_COLS;
                 uint32_t accum = 0, a_lo = 0;
 #pragma unroll 1
                 for (int c = 0; c < p.nchunks; ++c) {
@@ -572,7 +595,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                         cur >>= 12;
                         if (e & 0x400u) {
                             tc::mbar_wait_bounded(&R.a_full[sa], a_par);
-                            trace(p.trace, 1, acc_it, 2);
+                            trace(TBI_TRACE_PTR(p), 1, acc_it, 2);
                             a_lo = a_base + sa * a_stage_lo;
                         }
                         tc::mbar_wait_bounded(&R.b_full[sb], b_par);
@@ -592,18 +615,18 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                     }
                 }
                 if (leader) tc::umma_commit(&R.t_full[buf]);
-                trace(p.trace, 1, acc_it, 3);
+                trace(TBI_TRACE_PTR(p), 1, acc_it, 3);
             }
         }
         __syncwarp();
     } else if (warp < HT_EPI_WARPS) {
         // ===================== epilogue (warp w owns TMEM lanes [32*(w%4), +32)) =====================
-        TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_role<BN, PAIR, A_, D_>(p, R, sbias, tmem_base, warp, lane)));
+        TBI_EPI_DISPATCH(p.epi.act, p.epi.dact, (epilogue_role<BN, PAIR, A_, D_>(p, R, sbias, ts, warp, lane)));
     }
     tc::tc_fence_before();
     __syncthreads();
     if (PAIR) tc::cluster_sync_all();                       // the peer may still signal this CTA's barriers / read its operands
-    if (warp == W_MMA) { if (PAIR) tc::tmem_dealloc_pair<TMEM_COLS>(tmem_base); else tc::tmem_dealloc<TMEM_COLS>(tmem_base); }
+    if (warp == W_MMA) { if (PAIR) tc::tmem_dealloc_pair<TMEM_COLS>(SLOT_TMEM(ts)); else tc::tmem_dealloc<TMEM_COLS>(SLOT_TMEM(ts)); }
 }
 
 inline uint32_t r1024(uint32_t x) { return (x + 1023u) & ~1023u; }
@@ -855,6 +878,8 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
             grid = (int)(2 * pairs);
         }
     }
+    p.it_stride = p.pair ? grid / 2 : p.resident ? grid / p.nslabs : grid;
+    p.it_count = p.pair ? p.m_pairs * p.nslabs : p.resident ? p.m_tiles : p.total_tiles;
     const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512 +
                         ((size_t)p.cout_total * 4 + 64) + (size_t)(2 * (p.a_stages + p.b_stages) + 8) * 8;
     if (p.pair) return launch_halo<128, true>(p, grid, smem, s);

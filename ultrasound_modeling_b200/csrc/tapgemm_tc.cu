@@ -255,6 +255,9 @@ bool tbi_tapgemm_tc_supported(const tbi_tapgemm* d, const char** why) {
         if (!aligned_view(e.out) || !aligned_view(e.residual) || !aligned_view(e.dact_ref) || !aligned_view(e.out2) || !aligned_view(e.residual2))
             NO("epilogue view not 16-byte aligned");
         if (e.split_c % 8 != 0) NO("split_c");
+        auto same_grid = [&](const tbi_view& v) { return !v.ptr || (v.h == e.out.h && v.w == e.out.w); };
+        if (!same_grid(e.residual) || !same_grid(e.out2) || !same_grid(e.residual2) || (e.dact != TBI_ACT_NONE && !same_grid(e.dact_ref)))
+            NO("epilogue tensors on a different pixel grid than the output");
     }
     if (e.bias && ((uintptr_t)e.bias & 15) && !narrow) NO("bias alignment");
     if (((uintptr_t)d->w & 15)) NO("weight alignment");

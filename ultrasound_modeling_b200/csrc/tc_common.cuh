@@ -35,23 +35,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) { }
 }
-// bounded wait.  Fast path = one try_wait, inlined; the polling loop (with the watchdog that turns a wrong descriptor /
-// byte count into a trap the host sees instead of a hung GPU) is out of line so hot loops stay small.
-template <bool RELAXED>
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
-#pragma unroll 1
-        for (int i = 0; i < 4096; ++i) {
-            if (RELAXED) __nanosleep(20);          // epilogue warps: leave the issue slots to the TMA / MMA warps
-            if (mbar_try_wait(bar, parity)) return;
-        }
-        if (clock64() - t0 > 6000000000LL) { printf("tbi tcgen05: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
-    }
-}
+// bounded wait, fully inlined.  (It used to call an out-of-line polling function that printed a diagnostic before trapping: a
+// real call with the CUDA ABI's caller-saved registers in front of every barrier wait of every role loop -- ptxas answered
+// with spills around the call sites, and in these kernels (>= 200 KB of the SM's 228 KB is shared memory, L1 is a few KB and
+// streamed through) a local-memory reload is an L2 round trip.)  The watchdog turns a wrong descriptor / byte count into a
+// trap the host sees as a launch failure instead of a hung GPU: mbarrier.try_wait suspends the thread for a
+// hardware-chosen interval per attempt, so 2^22 failed attempts are far beyond any legitimate wait of a sub-millisecond kernel.
 template <bool RELAXED = false>
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-    if (!mbar_try_wait(bar, parity)) mbar_wait_slow<RELAXED>(bar, parity);
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+#pragma unroll 1
+    while (!mbar_try_wait(bar, parity)) {
+        if (RELAXED) __nanosleep(20);              // epilogue warps: leave the issue slots to the TMA / MMA warps
+        if (++spins > (1u << 22)) __trap();
+    }
 }
 
 // one lane of a converged warp (warp-uniform control flow around it keeps addresses/descriptors in uniform registers)

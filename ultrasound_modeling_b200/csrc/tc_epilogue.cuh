@@ -66,6 +66,14 @@ struct RowCtx {
     const uint8_t* keep; const uint8_t* dkeep;
     const float* bias;
     int split_c;
+    __device__ __forceinline__ __nv_bfloat16* p_out() const { return out; }
+    __device__ __forceinline__ __nv_bfloat16* p_out2() const { return out2; }
+    __device__ __forceinline__ const __nv_bfloat16* p_res() const { return res; }
+    __device__ __forceinline__ const __nv_bfloat16* p_res2() const { return res2; }
+    __device__ __forceinline__ const __nv_bfloat16* p_ref() const { return ref; }
+    __device__ __forceinline__ const uint8_t* p_keep() const { return keep; }
+    __device__ __forceinline__ const uint8_t* p_dkeep() const { return dkeep; }
+    __device__ __forceinline__ int split() const { return split_c; }
 };
 
 __device__ __forceinline__ size_t pix_off(const tbi_view& v, int n, int y, int x) {
@@ -87,48 +95,72 @@ __device__ __forceinline__ RowCtx make_row_ctx(const tbi_epilogue& e, int n, int
     return r;
 }
 
+// The same context in TWO registers: every tensor of the epilogue shares the output's pixel grid (checked on the host,
+// tbi_tapgemm_tc_supported), so one linear pixel index plus the epilogue descriptor -- a kernel parameter, i.e. constant-bank
+// operands -- gives each row pointer with one IMAD.WIDE where it is used.  The eight live 64-bit pointers of RowCtx were what
+// pushed the persistent kernels' epilogue loops over their 96-register budget.
+struct LeanRowCtx {
+    const tbi_epilogue* e;
+    int lin;
+    const float* bias;
+    typedef __nv_bfloat16 T;
+    __device__ __forceinline__ T* p_out() const { return (T*)e->out.ptr + ((size_t)lin * e->out.cstride + e->out.coff); }
+    __device__ __forceinline__ T* p_out2() const { return e->split_c > 0 ? (T*)e->out2.ptr + ((size_t)lin * e->out2.cstride + e->out2.coff) : nullptr; }
+    __device__ __forceinline__ const T* p_res() const { return e->residual.ptr ? (const T*)e->residual.ptr + ((size_t)lin * e->residual.cstride + e->residual.coff) : nullptr; }
+    __device__ __forceinline__ const T* p_res2() const { return e->residual2.ptr ? (const T*)e->residual2.ptr + ((size_t)lin * e->residual2.cstride + e->residual2.coff) : nullptr; }
+    __device__ __forceinline__ const T* p_ref() const { return e->dact != TBI_ACT_NONE ? (const T*)e->dact_ref.ptr + ((size_t)lin * e->dact_ref.cstride + e->dact_ref.coff) : nullptr; }
+    __device__ __forceinline__ const uint8_t* p_keep() const { return e->drop_keep ? e->drop_keep + (size_t)lin * e->out.c : nullptr; }
+    __device__ __forceinline__ const uint8_t* p_dkeep() const { return e->dact_keep ? e->dact_keep + (size_t)lin * e->dact_ref.c : nullptr; }
+    __device__ __forceinline__ int split() const { return e->split_c; }
+};
+__device__ __forceinline__ LeanRowCtx make_lean_row_ctx(const tbi_epilogue& e, int n, int oy, int ox, const float* bias) {
+    LeanRowCtx r;
+    r.e = &e; r.lin = (n * e.out.h + oy) * e.out.w + ox; r.bias = bias;
+    return r;
+}
+
 // Side inputs of one 8-channel group (slow path: ragged channel counts, chunks straddling the split point).
 struct Side8 { uint4 res, ref; uint2 k; };      // k = forward dropout multiplier OR the act' dropout multiplier (never both)
 
-template <int DACT>
-__device__ __forceinline__ void load_side8(const RowCtx& r, int co, Side8& s) {
-    if (r.split_c > 0 && co >= r.split_c) {
-        if (r.res2) s.res = *reinterpret_cast<const uint4*>(r.res2 + (co - r.split_c));
+template <int DACT, typename Ctx>
+__device__ __forceinline__ void load_side8(const Ctx& r, int co, Side8& s) {
+    if (r.split() > 0 && co >= r.split()) {
+        if (r.p_res2()) s.res = *reinterpret_cast<const uint4*>(r.p_res2() + (co - r.split()));
         return;
     }
-    if (r.res) s.res = *reinterpret_cast<const uint4*>(r.res + co);
+    if (r.p_res()) s.res = *reinterpret_cast<const uint4*>(r.p_res() + co);
     if (DACT != TBI_ACT_NONE) {
-        s.ref = *reinterpret_cast<const uint4*>(r.ref + co);
-        if (r.dkeep) s.k = *reinterpret_cast<const uint2*>(r.dkeep + co);
-    } else if (r.keep) {
-        s.k = *reinterpret_cast<const uint2*>(r.keep + co);
+        s.ref = *reinterpret_cast<const uint4*>(r.p_ref() + co);
+        if (r.p_dkeep()) s.k = *reinterpret_cast<const uint2*>(r.p_dkeep() + co);
+    } else if (r.p_keep()) {
+        s.k = *reinterpret_cast<const uint2*>(r.p_keep() + co);
     }
 }
 
 // same math as epilogue_store<bf16> (tbi_common.cuh) on 8 consecutive channels starting at co
-template <int ACT, int DACT>
-__device__ __forceinline__ void finish_store8(const RowCtx& r, int co, float (&v)[8], const Side8& s) {
-    if (r.split_c > 0 && co >= r.split_c) {
-        if (r.res2) {
+template <int ACT, int DACT, typename Ctx>
+__device__ __forceinline__ void finish_store8(const Ctx& r, int co, float (&v)[8], const Side8& s) {
+    if (r.split() > 0 && co >= r.split()) {
+        if (r.p_res2()) {
             float t[8]; unpack8(s.res, t);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] += t[i];
         }
-        *reinterpret_cast<uint4*>(r.out2 + (co - r.split_c)) = pack8(v);
+        *reinterpret_cast<uint4*>(r.p_out2() + (co - r.split())) = pack8(v);
         return;
     }
     if (r.bias) {
         const float4 b0 = *reinterpret_cast<const float4*>(r.bias + co), b1 = *reinterpret_cast<const float4*>(r.bias + co + 4);
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
     }
-    if (DACT == TBI_ACT_NONE && r.keep) {
+    if (DACT == TBI_ACT_NONE && r.p_keep()) {
         const unsigned char* kb = reinterpret_cast<const unsigned char*>(&s.k);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= (float)kb[i];
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = act_fast<ACT>(v[i]);
-    if (r.res) {
+    if (r.p_res()) {
         float t[8]; unpack8(s.res, t);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] += t[i];
@@ -137,13 +169,13 @@ __device__ __forceinline__ void finish_store8(const RowCtx& r, int co, float (&v
         float t[8]; unpack8(s.ref, t);
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] *= dact_fast<DACT>(t[i]);
-        if (r.dkeep) {
+        if (r.p_dkeep()) {
             const unsigned char* kb = reinterpret_cast<const unsigned char*>(&s.k);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] *= (float)kb[i];
         }
     }
-    *reinterpret_cast<uint4*>(r.out + co) = pack8(v);
+    *reinterpret_cast<uint4*>(r.p_out() + co) = pack8(v);
 }
 
 // Fast path: NCOLS in-range channels on one side of the split.  Loads and stores go through pointers the compiler must
@@ -210,25 +242,29 @@ __device__ __forceinline__ void epilogue_fast(__nv_bfloat16* out, const __nv_bfl
 }
 
 // NCOLS accumulator columns (already in registers) -> fused epilogue for channels [col0, col0+NCOLS) of the group
-template <int ACT, int DACT, int NCOLS>
-__device__ __forceinline__ void epilogue_cols(const RowCtx& rc, const uint32_t (&r)[NCOLS], int col0, int cout_g, int cbase) {
+template <int ACT, int DACT, int NCOLS, typename Ctx>
+__device__ __forceinline__ void epilogue_cols(const Ctx& rc, const uint32_t (&r)[NCOLS], int col0, int cout_g, int cbase) {
     const int co0 = cbase + col0;
     const bool whole = col0 + NCOLS <= cout_g;
-    if (whole && rc.split_c > 0 && co0 >= rc.split_c) {                       // the pass-through half of a split output
-        const int c2 = co0 - rc.split_c;
-        if (rc.res2) epilogue_fast<TBI_ACT_NONE, TBI_ACT_NONE, true, false, NCOLS>(rc.out2 + c2, rc.res2 + c2, nullptr, nullptr, nullptr, r);
-        else         epilogue_fast<TBI_ACT_NONE, TBI_ACT_NONE, false, false, NCOLS>(rc.out2 + c2, nullptr, nullptr, nullptr, nullptr, r);
+    const int split_c = rc.split();
+    if (whole && split_c > 0 && co0 >= split_c) {                             // the pass-through half of a split output
+        const int c2 = co0 - split_c;
+        const __nv_bfloat16* res2 = rc.p_res2();
+        if (res2) epilogue_fast<TBI_ACT_NONE, TBI_ACT_NONE, true, false, NCOLS>(rc.p_out2() + c2, res2 + c2, nullptr, nullptr, nullptr, r);
+        else      epilogue_fast<TBI_ACT_NONE, TBI_ACT_NONE, false, false, NCOLS>(rc.p_out2() + c2, nullptr, nullptr, nullptr, nullptr, r);
         return;
     }
-    if (whole && (rc.split_c <= 0 || co0 + NCOLS <= rc.split_c) && !(DACT != TBI_ACT_NONE && rc.bias)) {
-        const uint8_t* k = DACT != TBI_ACT_NONE ? rc.dkeep : rc.keep;
+    if (whole && (split_c <= 0 || co0 + NCOLS <= split_c) && !(DACT != TBI_ACT_NONE && rc.bias)) {
+        const uint8_t* k = DACT != TBI_ACT_NONE ? rc.p_dkeep() : rc.p_keep();
         const float* bias = rc.bias ? rc.bias + co0 : nullptr;
-        if (rc.res) {
-            if (k) epilogue_fast<ACT, DACT, true, true, NCOLS>(rc.out + co0, rc.res + co0, rc.ref + co0, k + co0, bias, r);
-            else   epilogue_fast<ACT, DACT, true, false, NCOLS>(rc.out + co0, rc.res + co0, rc.ref + co0, nullptr, bias, r);
+        const __nv_bfloat16* res = rc.p_res();
+        const __nv_bfloat16* ref = DACT != TBI_ACT_NONE ? rc.p_ref() + co0 : nullptr;
+        if (res) {
+            if (k) epilogue_fast<ACT, DACT, true, true, NCOLS>(rc.p_out() + co0, res + co0, ref, k + co0, bias, r);
+            else   epilogue_fast<ACT, DACT, true, false, NCOLS>(rc.p_out() + co0, res + co0, ref, nullptr, bias, r);
         } else {
-            if (k) epilogue_fast<ACT, DACT, false, true, NCOLS>(rc.out + co0, nullptr, rc.ref + co0, k + co0, bias, r);
-            else   epilogue_fast<ACT, DACT, false, false, NCOLS>(rc.out + co0, nullptr, rc.ref + co0, nullptr, bias, r);
+            if (k) epilogue_fast<ACT, DACT, false, true, NCOLS>(rc.p_out() + co0, nullptr, ref, k + co0, bias, r);
+            else   epilogue_fast<ACT, DACT, false, false, NCOLS>(rc.p_out() + co0, nullptr, ref, nullptr, bias, r);
         }
         return;
     }
