@@ -53,11 +53,20 @@ struct alignas(64) HaloParams {
     // control of the epilogue, producer and MMA loops, and with ~210 KB of the SM's 228 KB in shared memory a local-memory
     // load is an L2 round trip (ncu: 14 % of the head data gradient's stall samples on the instruction behind that LDL).
     int it_stride, it_count;
+    // ALL-SLABS mode (nsl > 1): a weights-resident CTA holds EVERY N tile's weights and walks pixel tiles only; each halo is
+    // loaded once and multiplied against the nsl slabs in turn (accumulator buffers round-robin, one epilogue pass per slab).
+    // For a one-chunk GEMM that is all epilogue (the head's data gradient: K = 64, N = 160) the operand crosses HBM once --
+    // with one slab per CTA the five CTAs sharing a pixel tile drift apart and each re-reads it (ncu: 736 MB read for 402 MB).
+    int nsl;
     // Side inputs of the epilogue (act' reference, residual, skip-gradient accumulator): the producer thread asks L2 for the
     // tile's box of each with ONE cp.async.bulk.prefetch.tensor when it loads the tile's first halo, i.e. a ring depth ahead of
     // the epilogue, whose one-row-per-thread loads then hit L2 instead of waiting a DRAM round trip per 32-column chunk.
     CUtensorMap side[3];
     int nside, side_split[3];      // side_split[k]: map k covers the channels >= split_c (out2 / residual2) instead of the main ones
+    // The producer runs a whole halo ring (up to 8 tiles with resident weights) ahead of the epilogue; boxes requested that early
+    // were evicted again before the epilogue read them (ncu, head data gradient: the act' reference crossed HBM twice).  The
+    // request for tile i is therefore issued when the halo of tile i + pf_lag is loaded, pf_lag = ring depth - 2.
+    int pf_lag;
     unsigned long long* trace;     // debug timeline buffer or nullptr (a kernel parameter: testing it costs no memory access)
     tbi_epilogue epi;
 };
@@ -177,6 +186,41 @@ __device__ __forceinline__ void resident_flat_mma_loop(const HaloParams& p, cons
     }
 }
 
+// ALL-SLABS variant of the loop above (one K chunk): per pixel tile one halo wait, then nsl accumulators in a row.
+template <int NTAPS, int KSTEPS>
+__device__ __forceinline__ void allslab_flat_mma_loop(const HaloParams& p, const Rings& R, uint32_t ts, uint32_t acc_cols, bool leader,
+                                                      uint32_t idesc, uint32_t a_base, uint32_t a_stage_lo, uint32_t a_hi,
+                                                      uint32_t b_base, uint32_t b_stage_lo, uint32_t b_hi, uint32_t row_lo, uint32_t nbuf) {
+    uint32_t a_off[NTAPS];
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) a_off[t] = ((uint32_t)p.t_row[0][t] & 0x3FFu) * row_lo;
+    uint32_t sa = 0, a_par = 0, acc_it = 0;
+    const uint32_t lgb = nbuf == 4 ? 2u : 1u;
+    for (int i = R.it_first; i < p.it_count; i += p.it_stride) {
+        tc::mbar_wait_bounded(&R.a_full[sa], a_par);
+        const uint32_t a_lo = a_base + sa * a_stage_lo;
+        uint32_t b_lo = b_base;
+#pragma unroll 1
+        for (int sl = 0; sl < p.nsl; ++sl, ++acc_it) {
+            const uint32_t buf = acc_it & (nbuf - 1u);
+            tc::mbar_wait_bounded(&R.t_empty[buf], ((acc_it >> lgb) & 1u) ^ 1u);
+            tc::tc_fence_after();
+            const uint32_t tmem_d = SLOT_TMEM(ts) + buf * acc_cols;
+            if (leader) {
+#pragma unroll
+                for (int t = 0; t < NTAPS; ++t)
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k)
+                        tc::umma_bf16_lh(tmem_d, a_lo + a_off[t] + 2 * k, a_hi, b_lo + t * b_stage_lo + 2 * k, b_hi, idesc, (t | k) ? 1u : 0u);
+                if (sl + 1 == p.nsl) tc::umma_commit(&R.a_empty[sa]);
+                tc::umma_commit(&R.t_full[buf]);
+            }
+            b_lo += NTAPS * b_stage_lo;
+        }
+        if (++sa == (uint32_t)p.a_stages) { sa = 0; a_par ^= 1u; }
+    }
+}
+
 // Streamed weights (one B stage per (chunk, tap)) with the tap count and the K steps per stage known at compile time: tap row
 // offsets and group boundaries sit in registers, the K steps of a stage are back-to-back MMAs with immediate address
 // increments (the generic loop below spends ~30 dependent instructions per MMA: table decode + loop-carried address
@@ -268,7 +312,8 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     // PAIR: the accumulator-free barrier the MMA thread waits on lives in the leader CTA
     uint32_t te_addr[2] = {0u, 0u};
     if (PAIR) { te_addr[0] = tc::map_to_cta(tc::smem_u32(&R.t_empty[0]), 0); te_addr[1] = tc::map_to_cta(tc::smem_u32(&R.t_empty[1]), 0); }
-    for (int i = R.it_first; i < p.it_count; i += p.it_stride, ++acc_it) {
+    for (int i = R.it_first; i < p.it_count; i += p.it_stride)
+    for (int sl = 0; sl < p.nsl; ++sl, ++acc_it) {
         if ((int)(acc_it & 1u) != grp) continue;
         const uint32_t buf = acc_it & (NBUF - 1u);
         TileCoord t;
@@ -279,6 +324,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
             tile_ok = mt < p.m_tiles;                        // odd tile count: the last pair's second CTA repeats a tile and drops it
             decode_mtile(p, tile_ok ? mt : 0, t.x0, t.y0, t.n0);
         } else t = decode_tile_warp(p, i, BN, lane, ts, i);
+        if (p.nsl > 1) t.nc0 = sl * BN;
         trace(tr, 2, acc_it, 0);
         const int gx = t.x0 + xx, gy = t.y0 + yy, n = t.n0;
         const bool valid = tile_ok && gx < p.gw && gy < p.gh;
@@ -303,15 +349,20 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
                     trace(tr, 2, acc_it, 3);
                 }
                 if (valid && p.f32wide) {
-                    // fp32 row of this pixel, columns [nc0 + c, +32) clipped to cout_g (a multiple of 4)
+                    // fp32 row of this pixel, columns [nc0 + c, +32) clipped to cout_g (a multiple of 8 here: 32-byte stores, whole sectors)
                     float* o = (float*)p.epi.out.ptr + pix_off(p.epi.out, n, oy, ox) + t.nc0 + c;
                     const float* bsm = p.epi.bias ? sbias + t.nc0 + c : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
+                    for (int j = 0; j < 32; j += 8) {
                         if (t.nc0 + c + j < p.cout_g) {
-                            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                            if (bsm) { v.x += bsm[j]; v.y += bsm[j + 1]; v.z += bsm[j + 2]; v.w += bsm[j + 3]; }
-                            *reinterpret_cast<float4*>(o + j) = v;
+                            float v[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(r[j + k]) + (bsm ? bsm[j + k] : 0.f);
+                            if (t.nc0 + c + j + 8 <= p.cout_g)
+                                st_global_32B(o + j, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                                              make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+                            else
+                                *reinterpret_cast<float4*>(o + j) = make_float4(v[0], v[1], v[2], v[3]);
                         }
                     }
                 } else if (valid) epilogue_cols<ACT, DACT, 32>(rc, r, t.nc0 + c, p.cout_g, t.cg * p.cout_g);
@@ -396,13 +447,33 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         uint32_t a_it = 0, sa = 0, a_par = 1, sb = 0, b_par = 1;       // ring stage + parity (empty barriers start "free")
         TileCoord slab_t{};
         if (p.resident) { slab_t.nc0 = SLOT_NC0(ts); slab_t.cg = SLOT_CG(ts); slab_t.ph = SLOT_PH(ts); }
-        if (p.resident && R.it_first < p.it_count && leader) {            // the whole weight slab, once
-            tc::mbar_expect_tx(R.b_res, (uint32_t)(p.nchunks * p.ntaps) * p.b_tx);
-            for (int c = 0; c < p.nchunks; ++c)
-                for (int tap = 0; tap < p.ntaps; ++tap)
-                    tc::tma_load_2d(R.b_ring + (size_t)(c * p.ntaps + tap) * p.b_stage_bytes, &p.b, R.b_res,
-                                    (int)p.t_kidx[slab_t.ph][tap] * p.cin_g + c * p.kc, slab_t.ph * p.cout_total + slab_t.cg * p.cout_g + slab_t.nc0);
+        if (p.resident && R.it_first < p.it_count && leader) {            // the whole weight slab (all-slabs mode: every slab), once
+            tc::mbar_expect_tx(R.b_res, (uint32_t)(p.nsl * p.nchunks * p.ntaps) * p.b_tx);
+            for (int sl = 0; sl < p.nsl; ++sl)
+                for (int c = 0; c < p.nchunks; ++c)
+                    for (int tap = 0; tap < p.ntaps; ++tap)
+                        tc::tma_load_2d(R.b_ring + (size_t)((sl * p.nchunks + c) * p.ntaps + tap) * p.b_stage_bytes, &p.b, R.b_res,
+                                        (int)p.t_kidx[slab_t.ph][tap] * p.cin_g + c * p.kc,
+                                        slab_t.ph * p.cout_total + slab_t.cg * p.cout_g + slab_t.nc0 + sl * BN);
         }
+        auto side_prefetch = [&](int it) {
+            TileCoord t;
+            if (PAIR) {
+                t = decode_tile(p, it % p.nslabs, BN);
+                int mt = 2 * (it / p.nslabs) + (int)rank;
+                if (mt >= p.m_tiles) return;
+                decode_mtile(p, mt, t.x0, t.y0, t.n0);
+            } else if (p.resident) { t = slab_t; decode_mtile(p, it, t.x0, t.y0, t.n0); } else t = decode_tile(p, it, BN);
+            if (p.nsl > 1) {
+                // all-slabs: one box per side tensor spans the columns of every slab
+                for (int k = 0; k < p.nside; ++k) tc::tma_prefetch_4d(&p.side[k], 0, t.x0, t.y0, t.n0);
+            } else {
+                const int co0 = t.cg * p.cout_g + t.nc0;
+                const int in_split = (p.epi.split_c > 0 && co0 >= p.epi.split_c) ? 1 : 0;
+                for (int k = 0; k < p.nside; ++k)
+                    if (p.side_split[k] == in_split) tc::tma_prefetch_4d(&p.side[k], in_split ? co0 - p.epi.split_c : co0, t.x0, t.y0, t.n0);
+            }
+        };
         for (int i = R.it_first; i < p.it_count; i += p.it_stride) {
             TileCoord t;
             if (PAIR) {
@@ -412,10 +483,9 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                 decode_mtile(p, mt, t.x0, t.y0, t.n0);
             } else if (p.resident) { t = slab_t; decode_mtile(p, i, t.x0, t.y0, t.n0); } else t = decode_tile(p, i, BN);
             if (p.nside && leader) {
-                const int co0 = t.cg * p.cout_g + t.nc0;
-                const int in_split = (p.epi.split_c > 0 && co0 >= p.epi.split_c) ? 1 : 0;
-                for (int k = 0; k < p.nside; ++k)
-                    if (p.side_split[k] == in_split) tc::tma_prefetch_4d(&p.side[k], in_split ? co0 - p.epi.split_c : co0, t.x0, t.y0, t.n0);
+                // the tile whose side boxes are requested now: pf_lag iterations behind the halo loads (see HaloParams::pf_lag)
+                const int ip = i - p.pf_lag * p.it_stride;
+                if (ip >= R.it_first) side_prefetch(ip);
             }
             for (int c = 0; c < p.nchunks; ++c) {
                 const int ch = c * p.kc;
@@ -463,6 +533,10 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
                 }
             }
         }
+        if (p.nside && leader && p.pf_lag > 0 && R.it_first < p.it_count) {       // the last pf_lag tiles' boxes
+            const int cnt = (p.it_count - 1 - R.it_first) / p.it_stride + 1;    // iterations of this CTA
+            for (int k = cnt > p.pf_lag ? cnt - p.pf_lag : 0; k < cnt; ++k) side_prefetch(R.it_first + k * p.it_stride);
+        }
         __syncwarp();
     } else if (warp == W_MMA && (!PAIR || rank == 0)) {
         // ===================== MMA issuer: warp-uniform loop (descriptors live in uniform registers), elected lane issues =====================
@@ -495,7 +569,19 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
             cur_ph = ph;
         };
         bool flat_done = false;
-        if (p.resident && p.ngroups == 1 && p.flat) {
+        if (p.resident && p.ngroups == 1 && p.flat && p.nsl > 1) {
+            // ---- every slab resident, one K chunk, one tap: halo once, nsl accumulators ----
+            if (R.it_first < p.it_count) tc::mbar_wait_bounded(R.b_res, 0);
+            const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
+#define TBI_ALLSLAB(KS) allslab_flat_mma_loop<1, KS>(p, R, ts, ACC_COLS, leader, idesc, a_base, a_stage_lo, a_hi, b_base, b_stage_lo, b_hi, row_lo, NBUF)
+            switch (ksteps) {
+                case 1:  TBI_ALLSLAB(1); break;
+                case 2:  TBI_ALLSLAB(2); break;
+                default: TBI_ALLSLAB(4); break;
+            }
+#undef TBI_ALLSLAB
+            flat_done = true;
+        } else if (p.resident && p.ngroups == 1 && p.flat) {
             // ---- weights resident, one halo per chunk: unrolled issue stream ----
             if (R.it_first < p.it_count) tc::mbar_wait_bounded(R.b_res, 0);
             const uint32_t a_base = a_lo0 + a_ring_lo, b_base = b_lo0 + b_ring_lo;
@@ -824,6 +910,15 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         const bool have = (nt == 1 && (ks == 1 || ks == 2 || ks == 4)) || (nt == 4 && (ks == 2 || ks == 4)) || (nt == 9 && (ks == 1 || ks == 2 || ks == 4));
         p.flat = (p.resident && p.ngroups == 1 && have && !no_flat) ? 1 : 0;
     }
+    p.nsl = 1;
+    {
+        static const bool no_allslabs = getenv("TBI_HALO_NO_ALLSLABS") != nullptr;
+        if (!no_allslabs && p.resident && p.flat && p.n_tiles > 1 && p.n_tiles <= 8 && p.cgroups == 1 && p.nphase == 1 && p.nchunks == 1 &&
+            d->ntaps == 1 && bn <= 32 && (long long)p.n_tiles * slab_bytes + 2 * p.a_stage_bytes <= budget) {
+            p.nsl = p.n_tiles;
+            p.nslabs = 1;                                    // the CTA's slab arithmetic sees one slab starting at column 0
+        }
+    }
     {
         static const bool no_pf = getenv("TBI_HALO_NO_SIDE_PF") != nullptr;
         const tbi_epilogue& e = d->epi;
@@ -831,7 +926,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
         if (!no_pf && !p.narrow && !p.f32wide && p.nphase == 1 && p.out_stride == 1 && e.out_off_x == 0 && e.out_off_y == 0) {
             auto add = [&](const tbi_view& v, int split) -> int {
                 if (!v.ptr || ((v.cstride * 2) & 15) || ((v.coff * 2) & 15) || (((uintptr_t)v.ptr) & 15)) return TBI_OK;
-                int cols = v.c < bn ? v.c : bn;
+                int cols = v.c < bn * p.nsl ? v.c : bn * p.nsl;
                 cols &= ~7;
                 if (cols <= 0) return TBI_OK;
                 const uint64_t px = (uint64_t)v.cstride * 2;
@@ -854,8 +949,8 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     int grid;
     if (p.resident) {
         // weights stay in smem for the CTA's lifetime; everything else is a deep ring of halo tiles
-        p.b_stages = p.nchunks * d->ntaps;
-        int as = (int)((budget - slab_bytes) / p.a_stage_bytes);
+        p.b_stages = p.nsl * p.nchunks * d->ntaps;
+        int as = (int)((budget - p.nsl * slab_bytes) / p.a_stage_bytes);
         if (as > 8) as = 8;
         p.a_stages = as;
         int per_slab = max_ctas / p.nslabs;
@@ -877,6 +972,12 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
             if (pairs > its) pairs = its;
             grid = (int)(2 * pairs);
         }
+    }
+    {
+        static const int lag_env = getenv("TBI_HALO_PF_LAG") ? atoi(getenv("TBI_HALO_PF_LAG")) : -1;
+        const int tiles_ahead = p.a_stages / (p.nchunks * p.ngroups);       // halo stages per tile = chunks x tap groups
+        p.pf_lag = lag_env >= 0 ? lag_env : (tiles_ahead > 2 ? tiles_ahead - 2 : 0);
+        if (p.pf_lag > tiles_ahead - 1) p.pf_lag = tiles_ahead > 1 ? tiles_ahead - 1 : 0;
     }
     p.it_stride = p.pair ? grid / 2 : p.resident ? grid / p.nslabs : grid;
     p.it_count = p.pair ? p.m_pairs * p.nslabs : p.resident ? p.m_tiles : p.total_tiles;

@@ -72,24 +72,11 @@ __device__ __forceinline__ void xp_epilogue(const XpParams& p, const float* sbia
     int tix = i % p.tiles_x, tiy = (i / p.tiles_x) % p.tiles_y, n0 = i / (p.tiles_x * p.tiles_y);
     const uint32_t buf = (uint32_t)grp;
     const tbi_epilogue& e = p.epi;
-    const size_t o_c = (size_t)e.out.cstride, r_c = (size_t)e.residual.cstride, f_c = (size_t)e.dact_ref.cstride;
     for (uint32_t k = 0; i < p.m_tiles; i += step, ++k) {
         const int gx = tix * XOUT - 1 + xx, gy = tiy * XTH + yy;
         const bool valid = xx >= 1 && xx <= XOUT && gx < p.gw && gy < p.gh;
-        RowCtx rc{};
-        if (valid) {
-            if (p.simple_ctx) {
-                // out / residual / act' reference all have the conv's own geometry (no offsets, no split, no dropout)
-                const size_t pix = ((size_t)n0 * p.gh + gy) * p.gw + gx;
-                rc.out = (__nv_bfloat16*)e.out.ptr + pix * o_c + e.out.coff;
-                rc.res = e.residual.ptr ? (const __nv_bfloat16*)e.residual.ptr + pix * r_c + e.residual.coff : nullptr;
-                rc.ref = e.dact != TBI_ACT_NONE ? (const __nv_bfloat16*)e.dact_ref.ptr + pix * f_c + e.dact_ref.coff : nullptr;
-                rc.bias = e.bias;
-            } else {
-                rc = make_row_ctx(p.epi, n0, gy + p.epi.out_off_y, gx + p.epi.out_off_x);
-            }
-            if (rc.bias) rc.bias = sbias;
-        }
+        // two-register row context (tc_epilogue.cuh): every epilogue tensor shares the output's pixel grid
+        const LeanRowCtx rc = make_lean_row_ctx(e, n0, gy + e.out_off_y, gx + e.out_off_x, e.bias ? sbias : nullptr);
         tix += s_x; if (tix >= p.tiles_x) { tix -= p.tiles_x; ++tiy; }
         tiy += s_y; if (tiy >= p.tiles_y) { tiy -= p.tiles_y; ++n0; }
         n0 += s_n;
