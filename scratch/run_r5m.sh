@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py > gpurun_out/b_r5m.json 2> gpurun_out/b_r5m.err; echo "bench rc=$?"
+python -c "
+import json; d=json.loads(open('gpurun_out/b_r5m.json').read().strip().splitlines()[-1]); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['ms_per_call'], d['roofline']['frac'], d['clocks'])"

@@ -404,8 +404,11 @@ __global__ void __launch_bounds__(NT, 1024 / NT) splitatt_fwd_cluster_kernel(tbi
 }
 
 // scratch layout (as tbi_split_attention_bwd): dz [n][K][R][c] | dgap [n][K][c] | dbn [n][K][c2] | xhat [n][K][c2]
+#ifndef SA_BWD_MINB
+#define SA_BWD_MINB 2
+#endif
 template <int R, int NT>
-__global__ void __launch_bounds__(NT, 2) splitatt_bwd_cluster_kernel(tbi_splitatt p, tbi_view u, tbi_view dv, tbi_view du, float* scratch,
+__global__ void __launch_bounds__(NT, NT == 256 ? SA_BWD_MINB : 2) splitatt_bwd_cluster_kernel(tbi_splitatt p, tbi_view u, tbi_view dv, tbi_view du, float* scratch,
                                                                                       int cache, FcPlan fc) {
     extern __shared__ __align__(16) float sm[];
     cg::cluster_group cl = cg::this_cluster();

@@ -65,7 +65,7 @@ struct alignas(64) HaloParams {
     int nside, side_split[3];      // side_split[k]: map k covers the channels >= split_c (out2 / residual2) instead of the main ones
     // The producer runs a whole halo ring (up to 8 tiles with resident weights) ahead of the epilogue; boxes requested that early
     // were evicted again before the epilogue read them (ncu, head data gradient: the act' reference crossed HBM twice).  The
-    // request for tile i is therefore issued when the halo of tile i + pf_lag is loaded, pf_lag = ring depth - 2.
+    // request for tile i is therefore issued when the halo of tile i + pf_lag is loaded, pf_lag = ring depth in tiles - 1.
     int pf_lag;
     unsigned long long* trace;     // debug timeline buffer or nullptr (a kernel parameter: testing it costs no memory access)
     tbi_epilogue epi;
@@ -310,8 +310,9 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
     unsigned long long* tr = (warp == 0 && lane == 0) ? TBI_TRACE_PTR(p) : nullptr;
     const uint32_t rank = PAIR ? tc::cluster_ctarank() : 0u;
     // PAIR: the accumulator-free barrier the MMA thread waits on lives in the leader CTA
-    uint32_t te_addr[2] = {0u, 0u};
-    if (PAIR) { te_addr[0] = tc::map_to_cta(tc::smem_u32(&R.t_empty[0]), 0); te_addr[1] = tc::map_to_cta(tc::smem_u32(&R.t_empty[1]), 0); }
+    // (one base address + 8 * buffer: a two-element array indexed by the buffer number lived in LOCAL memory, i.e. an L2 round trip
+    // in front of every accumulator release)
+    const uint32_t te_addr0 = PAIR ? tc::map_to_cta(tc::smem_u32(&R.t_empty[0]), 0) : 0u;
     for (int i = R.it_first; i < p.it_count; i += p.it_stride)
     for (int sl = 0; sl < p.nsl; ++sl, ++acc_it) {
         if ((int)(acc_it & 1u) != grp) continue;
@@ -345,7 +346,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
                     trace(tr, 2, acc_it, 2);
                     tc::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(te_addr[buf & 1u]); else tc::mbar_arrive(&R.t_empty[buf]); }
+                    if (lane == 0) { if (PAIR) tc::mbar_arrive_cluster(te_addr0 + 8u * (buf & 1u)); else tc::mbar_arrive(&R.t_empty[buf]); }
                     trace(tr, 2, acc_it, 3);
                 }
                 if (valid && p.f32wide) {
@@ -376,6 +377,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&R.t_empty[buf]);
             if (valid && p.narrow) {
+#pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (t.nc0 + j < p.cout_g) epilogue_store<__nv_bfloat16>(p.epi, n, oy, ox, t.cg * p.cout_g + t.nc0 + j, __uint_as_float(r[j]));
             } else if (valid) {
@@ -976,7 +978,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     {
         static const int lag_env = getenv("TBI_HALO_PF_LAG") ? atoi(getenv("TBI_HALO_PF_LAG")) : -1;
         const int tiles_ahead = p.a_stages / (p.nchunks * p.ngroups);       // halo stages per tile = chunks x tap groups
-        p.pf_lag = lag_env >= 0 ? lag_env : (tiles_ahead > 2 ? tiles_ahead - 2 : 0);
+        p.pf_lag = lag_env >= 0 ? lag_env : (tiles_ahead > 1 ? tiles_ahead - 1 : 0);      // one tile of lead (swept 0..4: 6.99 / 6.98 / 6.95 / 6.95 / 6.91 ms per step)
         if (p.pf_lag > tiles_ahead - 1) p.pf_lag = tiles_ahead > 1 ? tiles_ahead - 1 : 0;
     }
     p.it_stride = p.pair ? grid / 2 : p.resident ? grid / p.nslabs : grid;
