@@ -279,7 +279,7 @@ def run_ours(args):
         # ---- dominant kernel, timed live: the persistent halo tap-GEMM (tapgemm_halo_kernel<128>, ~19 % of the step) on its
         # longest launch of the step, upsample_4's transposed conv forward (one 4-phase launch).  Algorithmic flops per launch
         # = 2 * N*h*w * 16 taps * Cin * Cout; `traffic` = dram read+write bytes of that launch from the ncu
-        # --set full capture summarised in profiles/r1_ncu_upsample4_fwd.md (same shape; scaled by batch if --batch differs).
+        # --set full capture summarised in profiles/r2_ncu_upsample4_fwd.md (same shape, N = 64 only).
         st = torch.cuda.current_stream().cuda_stream
         name = "upsample_4"
         calls = [(fn, a) for fn, a in e.prog_fwd if fn.__name__ == "tbi_conv2d_transpose_s2_fwd"]
@@ -302,11 +302,13 @@ def run_ours(args):
         peak_sus = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])   # sustained figure: for the whole step
         step_flops = 3.0 * O.forward_flops_per_image(args.size, args.size, 1, 3, 3, args.radix, args.kpaths) * B
         # dram__bytes_read.sum + dram__bytes_write.sum of exactly this launch (N=64, 256x256, bf16) in the committed capture
-        # profiles/r2_ncu_upsample4_fwd.md (169.2 MB read + 230.2 MB written; algorithmic 436 MB); null for any other shape
-        traffic = 399.46e6 if (args.dtype == "bf16" and B == 64 and args.size == 256) else None
+        # profiles/r2_ncu_upsample4_fwd.md, end-of-round re-capture (169.2 MB read + 223.2 MB written; algorithmic 436 MB: the tail
+        # of the output is still in L2 when the kernel ends); null for any other shape
+        traffic = 392.37e6 if (args.dtype == "bf16" and B == 64 and args.size == 256) else None
         roof = {"bound": "tensor", "kernel": f"tapgemm_halo_kernel<128, pair>: {name} Conv2DTranspose k4 s2 fwd [{B},{h},{w},{cin}]->[{B},{2*h},{2*w},{cout}] (one 4-phase launch, cta_group::2)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_source": "profiles/r2_ncu_upsample4_fwd.md (ncu --set full capture of this launch)",
-                "peak_source": pk_kind + " (burst bf16, kernel timed alone with L2 flushed between launches)",
+                "peak_source": pk_kind + " (burst bf16 = what cuBLAS reached on this pool, kernel timed alone with L2 flushed between launches; a frac near or above 1 means this kernel runs at the library GEMM's measured rate, not at the hardware limit)",
+                "frac_of_nominal_dense_bf16": ach / 2250.0,
                 "ms_per_call": kms, "flops_per_call": flops_call, "step_tflops": step_flops * world * args.steps / (ms / 1e3) / 1e12 / world,
                 "step_frac_of_peak_sustained": step_flops * args.steps / (ms / 1e3) / 1e12 / peak_sus}
         cpu_val, cores, sample = cpu_oracle_rate(args.radix, args.kpaths, args.size, seconds=args.cpu_seconds)
