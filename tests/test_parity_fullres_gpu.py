@@ -420,3 +420,29 @@ def test_wgrad_cta_pairs_vs_fp64(ops, case):
     e_dw, e_db = rel(dw, gw), rel(db, dz.double().cpu().sum((0, 1, 2)))
     report(test="wgrad_cta_pairs", case=str(case), wgrad=e_dw, dbias=e_db)
     assert e_dw < 2e-3 and e_db < 2e-3, (e_dw, e_db)
+
+
+@pytest.mark.parametrize("n,h,w,c0,c1", [(16, 128, 64, 128, 32),      # the head's data gradient, 1 024 pixel tiles: 3-4 per persistent CTA
+                                         (3, 48, 40, 128, 32),       # partial tiles in x and y
+                                         (2, 32, 32, 64, 32)])       # 96 = 3 x 32 columns, split inside the slab list
+def test_split_output_all_slabs_vs_fp64(ops, n, h, w, c0, c1):
+    """A one-chunk (K = 64) 1x1 data gradient whose output is the virtual concat of two tensors with a ragged column count (the
+    head: 160 = 128 + 32, TBI_ResNest.py:124 backward): the halo kernel's ALL-SLABS resident mode (every 32-column weight slab in
+    one CTA, one halo per pixel tile, one accumulator per slab), with ReLU' from a stored forward output on the first tensor and
+    a plain write on the second, and the side-input boxes prefetched one tile ahead.  Against fp64 on the same bf16 inputs, at
+    a size where every persistent CTA walks several pixel tiles (ring wrap, TMEM buffer reuse, prefetch flush at the end)."""
+    x, x2 = rnd(n, h, w, c0, seed=31), rnd(n, h, w, c1, seed=32)
+    wt = torch.randn(1, 1, c0 + c1, 64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(33)) / 8.0
+    dz = rnd(n, h, w, 64, seed=34)
+    (dx, dx2), dw, db = ops.conv2d_grads(x, wt, dz, x2=x2, impl=ops._lib.IMPL_TCGEN05, dact=ops._lib.ACT_RELU, dact_ref=x,
+                                         wgrad_impl=ops._lib.IMPL_AUTO)
+    torch.cuda.synchronize()
+    g = dz.double().cpu() @ wt.to(BF).double().cpu()[0, 0].T                     # [n,h,w,c0+c1]
+    want1 = g[..., :c0] * (x.double().cpu() > 0)
+    want2 = g[..., c0:]
+    e1, e2 = rel(dx, want1), rel(dx2, want2)
+    xc = torch.cat([x, x2], 3).double().cpu()
+    gw = torch.einsum("nhwi,nhwo->io", xc, dz.double().cpu())
+    e3 = rel(dw[0, 0], gw)
+    report(test="all_slabs_split_dgrad", n=n, h=h, w=w, c=(c0, c1), dx=e1, dx2=e2, dw=e3)
+    assert e1 < 1e-2 and e2 < 1e-2 and e3 < 1e-3, (e1, e2, e3)

@@ -104,6 +104,13 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
 #define SLOT_NC0(ts)  ((int)lds_u32((ts) + 4))
 #define SLOT_CG(ts)   ((int)lds_u32((ts) + 8))
 #define SLOT_PH(ts)   ((int)lds_u32((ts) + 12))
+// PAIR mode: (N tile, group, phase) of every slab, packed nc0 | cg << 16 | ph << 24, in the 32 words behind the four above --
+// the five divisions of decode_tile() per iteration in every role (and the registers they held) become one shared-memory load
+constexpr int PAIR_MAX_SLABS = 32;
+__device__ __forceinline__ void slab_from_table(uint32_t ts, int slab, TileCoord& t) {
+    const uint32_t v = lds_u32(ts + 16u + 4u * (uint32_t)slab);
+    t.nc0 = (int)(v & 0xFFFFu); t.cg = (int)((v >> 16) & 0xFFu); t.ph = (int)(v >> 24);
+}
 
 __device__ __forceinline__ TileCoord decode_tile(const HaloParams& p, int tile, int BN) {
     TileCoord t;
@@ -237,7 +244,7 @@ __device__ __forceinline__ void streamed_mma_loop(const HaloParams& p, const Rin
     int cur_ph = -1;
     uint32_t sa = 0, a_par = 0, sb = 0, b_par = 0, acc_it = 0;
     for (int i = R.it_first; i < p.it_count; i += p.it_stride, ++acc_it) {
-        const int ph = (p.nphase > 1 ? decode_tile(p, PAIR ? i % p.nslabs : i, BN).ph : 0);
+        const int ph = p.nphase > 1 ? (PAIR ? (int)(lds_u32(ts + 16u + 4u * (uint32_t)(i % p.nslabs)) >> 24) : decode_tile(p, i, BN).ph) : 0;
         if (ph != cur_ph) {
             first_mask = last_mask = 0;
 #pragma unroll
@@ -320,7 +327,7 @@ __device__ __forceinline__ void epilogue_role(const HaloParams& p, const Rings& 
         TileCoord t;
         bool tile_ok = true;
         if (PAIR) {
-            t = decode_tile(p, i % p.nslabs, BN);            // slab part: (N tile, group, phase)
+            slab_from_table(ts, i % p.nslabs, t);            // slab part: (N tile, group, phase)
             const int mt = 2 * (i / p.nslabs) + (int)rank;   // this CTA's pixel tile of the pair
             tile_ok = mt < p.m_tiles;                        // odd tile count: the last pair's second CTA repeats a tile and drops it
             decode_mtile(p, tile_ok ? mt : 0, t.x0, t.y0, t.n0);
@@ -408,7 +415,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
     uint32_t* tslot = reinterpret_cast<uint32_t*>(R.b_res + 1);
     // the folded bias of every output channel, staged once: the epilogue reads it with shared-memory latency and the loads do not
     // sit behind the (possibly aliasing) global stores of the previous channel group
-    float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tslot + 4) + 15) & ~static_cast<uintptr_t>(15));
+    float* sbias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tslot + 4 + (PAIR ? PAIR_MAX_SLABS : 0)) + 15) & ~static_cast<uintptr_t>(15));
     if (p.epi.bias && !p.narrow)
         for (int i = threadIdx.x; i < p.cout_total; i += HT_THREADS) sbias[i] = p.epi.bias[i];
     // tile iteration: streaming = round-robin over all tiles; resident = this CTA's slab x a strided set of M tiles
@@ -437,6 +444,10 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         if (p.resident) st = decode_tile(p, R.slab, BN);
         tslot[1] = (uint32_t)st.nc0; tslot[2] = (uint32_t)st.cg; tslot[3] = (uint32_t)st.ph;
     }
+    if (PAIR && (int)threadIdx.x < p.nslabs) {
+        const TileCoord st = decode_tile(p, (int)threadIdx.x, BN);
+        tslot[4 + threadIdx.x] = (uint32_t)st.nc0 | ((uint32_t)st.cg << 16) | ((uint32_t)st.ph << 24);
+    }
     tc::tc_fence_before();
     __syncthreads();
     if (PAIR) tc::cluster_sync_all();                       // the peer's barriers exist before anything is signalled across the pair
@@ -461,7 +472,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         auto side_prefetch = [&](int it) {
             TileCoord t;
             if (PAIR) {
-                t = decode_tile(p, it % p.nslabs, BN);
+                slab_from_table(ts, it % p.nslabs, t);
                 int mt = 2 * (it / p.nslabs) + (int)rank;
                 if (mt >= p.m_tiles) return;
                 decode_mtile(p, mt, t.x0, t.y0, t.n0);
@@ -479,7 +490,7 @@ __global__ void __launch_bounds__(HT_THREADS, 2) tapgemm_halo_kernel(const __gri
         for (int i = R.it_first; i < p.it_count; i += p.it_stride) {
             TileCoord t;
             if (PAIR) {
-                t = decode_tile(p, i % p.nslabs, BN);
+                slab_from_table(ts, i % p.nslabs, t);
                 int mt = 2 * (i / p.nslabs) + (int)rank;
                 if (mt >= p.m_tiles) mt = p.m_tiles - 1;                 // odd tile count: load something valid, the epilogue drops it
                 decode_mtile(p, mt, t.x0, t.y0, t.n0);
@@ -885,7 +896,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     const bool would_be_resident = !no_resident0 && slab_bytes_full <= 72 * 1024 && p.nslabs <= 2 * tbi_sm_count() &&
                                    slab_bytes_full + 2 * (long long)r1024((uint32_t)(bw * bh * kc * 2)) <= 104 * 1024 && (d->cin_g / kc) * d->ntaps <= 192;
     p.pair = (!no_pair && !would_be_resident && bn == 128 && !p.narrow && kc == 64 && d->cout_g % 128 == 0 &&
-              (d->ntaps == 1 || d->ntaps == 4 || d->ntaps == 9 || d->ntaps == 16) &&
+              (d->ntaps == 1 || d->ntaps == 4 || d->ntaps == 9 || d->ntaps == 16) && p.nslabs <= PAIR_MAX_SLABS && d->cout_g < 65536 && d->groups < 256 &&
               (long long)p.m_pairs * p.nslabs >= (g_pair_min > 0 ? (long long)g_pair_min : (long long)tbi_sm_count())) ? 1 : 0;
     const int b_rows = p.pair ? bn / 2 : bn;                 // PAIR: each CTA streams half of the N tile's weight rows
     {
@@ -983,7 +994,7 @@ int tbi_tapgemm_halo(const tbi_tapgemm* d, cudaStream_t s) {
     }
     p.it_stride = p.pair ? grid / 2 : p.resident ? grid / p.nslabs : grid;
     p.it_count = p.pair ? p.m_pairs * p.nslabs : p.resident ? p.m_tiles : p.total_tiles;
-    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512 +
+    const size_t smem = (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes + 1024 + 512 + (p.pair ? 4 * PAIR_MAX_SLABS : 0) +
                         ((size_t)p.cout_total * 4 + 64) + (size_t)(2 * (p.a_stages + p.b_stages) + 8) * 8;
     if (p.pair) return launch_halo<128, true>(p, grid, smem, s);
     switch (bn) {

@@ -156,6 +156,7 @@ __global__ void __launch_bounds__(NUM_THREADS) tapgemm_tc_kernel(const __grid_co
             tc::tmem_ld16(taddr, r);
             tc::tmem_ld_wait();
             if (valid && p.narrow) {
+#pragma unroll
                 for (int j = 0; j < 16; ++j)
                     if (nc0 + j < p.cout_g) epilogue_store<__nv_bfloat16>(p.epi, n, oy, ox, g * p.cout_g + nc0 + j, __uint_as_float(r[j]));
             } else if (valid) {
