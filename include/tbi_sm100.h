@@ -273,6 +273,13 @@ int tbi_softmax_loss_fwd_bwd(int dlogits_dtype, int n, int h, int w, int nc, con
                              float* probs, float* loss_map, int32_t* correct, void* dlogits, int dlogits_cstride,
                              void* stream);
 /* dlogits_cstride >= nc: elements per pixel record of dlogits (channels >= nc are left untouched).     */
+/* The same with the logits FORMED inside the kernel from the head's per-input-pixel tap products (f_tran as a plain GEMM,
+ * TBI_ResNest.py:124): ytaps fp32 [n, h/2, w/2, >= 16*nc] with column (ky*4+kx)*nc + c, bias fp32 [nc] or NULL;
+ * logits[n,oy,ox,c] = bias[c] + sum of the 2 x 2 taps with 2i-1+ky = oy, 2j-1+kx = ox -- what tbi_convt_scatter_y would write,
+ * bit for bit -- so the [n,h,w,nc] logits tensor is never materialised.  (h, w) = OUTPUT grid.                          */
+int tbi_softmax_loss_fwd_bwd_taps(int dlogits_dtype, int n, int h, int w, int nc, const tbi_view* ytaps, const float* bias,
+                                  const float* y, float* probs, float* loss_map, int32_t* correct, void* dlogits,
+                                  int dlogits_cstride, void* stream);
 
 /* dz = dy * act'(y_ref) [* keep]     (standalone activation backward where it cannot be fused)   */
 int tbi_act_bwd(int dtype, int64_t npix, int act, const tbi_view* dy, const tbi_view* y_ref,

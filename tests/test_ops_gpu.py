@@ -267,6 +267,33 @@ def test_softmax_loss(ops, nc):
     assert int(correct.item()) == int((probs.argmax(-1) == y.argmax(-1)).sum())
 
 
+@pytest.mark.parametrize("shape", [(5, 8, 8), (3, 20, 36), (2, 64, 96)])
+def test_softmax_loss_from_head_taps(ops, shape):
+    """tbi_softmax_loss_fwd_bwd_taps: the logits formed inside the loss kernel from the head's per-input-pixel tap products
+    (f_tran as a GEMM, TBI_ResNest.py:124) must be what the 4-tap scatter writes -- so probabilities, loss map, accuracy count and
+    dlogits equal scatter + tbi_softmax_loss_fwd_bwd BIT FOR BIT -- and the logits must equal the transposed conv of the oracle."""
+    torch.manual_seed(16)
+    n, h, w = shape                                            # OUTPUT grid; the head's input grid is h/2 x w/2
+    nc, cin = 3, 32
+    x = torch.randn(n, h // 2, w // 2, cin, dtype=torch.float64)
+    wt = torch.randn(4, 4, nc, cin, dtype=torch.float64) * 0.2          # HWOI
+    b = torch.randn(nc, dtype=torch.float64) * 0.1
+    ytaps = torch.einsum("nhwi,abci->nhwabc", x, wt).reshape(n, h // 2, w // 2, 16 * nc).float().cuda().contiguous()
+    y = F.one_hot(torch.randint(0, nc, (n, h, w)), nc).float().cuda()
+    L = ops._lib.lib()
+    bd = b.float().cuda()
+    logits = torch.empty(n, h, w, nc, dtype=torch.float32, device="cuda")
+    ops.check(L.tbi_convt_scatter_y(ops.F32, n, h // 2, w // 2, 4, nc, ops._vp(ops.view(ytaps)), bd.data_ptr(),
+                                    ops._vp(ops.view(logits)), ops._st()), "scatter")
+    want = O.conv2d_transpose_s2_same(x, wt, b)
+    assert rel(logits, want) < 1e-5
+    ref = ops.softmax_loss(logits, y)
+    got = ops.softmax_loss_from_taps(ytaps, bd, y)
+    torch.cuda.synchronize()
+    for a_, b_ in zip(got, ref):
+        assert torch.equal(a_, b_)
+
+
 def test_adam_matches_oracle(ops):
     torch.manual_seed(7)
     n = 1003

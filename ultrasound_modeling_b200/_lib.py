@@ -180,6 +180,7 @@ SIGNATURES = {
     "tbi_splitatt_gap": (_I, [C.POINTER(SplitAtt), _PV, _VP]),
     "tbi_splitatt_combine": (_I, [C.POINTER(SplitAtt), _PV, _PV, _VP]),
     "tbi_softmax_loss_fwd_bwd": (_I, [_I, _I, _I, _I, _I, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
+    "tbi_softmax_loss_fwd_bwd_taps": (_I, [_I, _I, _I, _I, _I, _PV, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP]),
     "tbi_act_bwd": (_I, [_I, _I64, _I, _PV, _PV, _VP, _PV, _VP]),
     "tbi_accumulate": (_I, [_I, _I64, _PV, _PV, _VP]),
     "tbi_colsum": (_I, [_I, _I64, _PV, _VP, _VP]),

@@ -622,10 +622,14 @@ __global__ void splitatt_param_grad_kernel(tbi_splitatt p, const float* scratch,
 // memory in a fixed order (deterministic).  A warp is 32 consecutive pixels of one image: 384-byte contiguous accesses.
 // (One thread per pixel looping over the whole batch left only 65 536 threads for 285 MB of traffic: 118 us.)
 constexpr int SL_J = 8;
-template <int NC, typename TD>
+// FROM_Y: the logits are not read but FORMED here from the head's per-input-pixel tap products Y[n, H/2, W/2, 16 taps x NC]
+// (fp32; tbi_convt_scatter_y's sum, same order: bias, then the 2 x 2 contributing (ky, kx) -- bit-identical logits), so the
+// [N,H,W,NC] logits tensor is never written or re-read and the scatter launch disappears.  W = width of the OUTPUT grid.
+template <int NC, typename TD, bool FROM_Y>
 __global__ void __launch_bounds__(32 * SL_J) softmax_loss_kernel(int N, int hw, const float* __restrict__ logits, const float* __restrict__ y,
                                                                 float* __restrict__ probs, float* __restrict__ loss_map, int32_t* correct,
-                                                                TD* __restrict__ dlogits, int dl_cs) {
+                                                                TD* __restrict__ dlogits, int dl_cs,
+                                                                const float* __restrict__ ytap, int y_cs, const float* __restrict__ bias, int W) {
     __shared__ float red[SL_J][32][3];
     const int lane = threadIdx.x & 31, j = threadIdx.x >> 5;
     const int p = blockIdx.x * 32 + lane;
@@ -658,7 +662,26 @@ __global__ void __launch_bounds__(32 * SL_J) softmax_loss_kernel(int N, int hw, 
             float z[NC], yy[NC];
             float m = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < NC; ++c) { z[c] = logits[o + c]; yy[c] = y[o + c]; m = fmaxf(m, z[c]); }
+            if (FROM_Y) {
+                const int H = hw / W, oy = p / W, ox = p - oy * W, h2 = H >> 1, w2 = W >> 1;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) z[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+                for (int a = 0; a < 2; ++a) {
+                    const int ky = ((oy + 1) & 1) + 2 * a, iy = (oy + 1 - ky) >> 1;
+                    if (iy < 0 || iy >= h2) continue;
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int kx = ((ox + 1) & 1) + 2 * e, ix = (ox + 1 - kx) >> 1;
+                        if (ix < 0 || ix >= w2) continue;
+                        const float* src = ytap + (((size_t)n * h2 + iy) * w2 + ix) * y_cs + (ky * 4 + kx) * NC;
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) z[c] += src[c];
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { if (!FROM_Y) z[c] = logits[o + c]; yy[c] = y[o + c]; m = fmaxf(m, z[c]); }
             float sm = 0.f;
 #pragma unroll
             for (int c = 0; c < NC; ++c) { z[c] = expf(z[c] - m); sm += z[c]; }
@@ -1253,13 +1276,36 @@ extern "C" int tbi_softmax_loss_fwd_bwd(int dlogits_dtype, int n, int h, int w, 
     const int hw = h * w;
     const unsigned g = (hw + 31) / 32;
     if (dlogits_dtype == TBI_F32) {
-        if (nc == 3) softmax_loss_kernel<3, float><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
-        else         softmax_loss_kernel<4, float><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs);
+        if (nc == 3) softmax_loss_kernel<3, float, false><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs, nullptr, 0, nullptr, w);
+        else         softmax_loss_kernel<4, float, false><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (float*)dlogits, dl_cs, nullptr, 0, nullptr, w);
     } else if (dlogits_dtype == TBI_BF16) {
-        if (nc == 3) softmax_loss_kernel<3, __nv_bfloat16><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
-        else         softmax_loss_kernel<4, __nv_bfloat16><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs);
+        if (nc == 3) softmax_loss_kernel<3, __nv_bfloat16, false><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs, nullptr, 0, nullptr, w);
+        else         softmax_loss_kernel<4, __nv_bfloat16, false><<<g, 32 * SL_J, 0, s>>>(n, hw, logits, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs, nullptr, 0, nullptr, w);
     } else return tbi_set_error(TBI_ERR_UNSUPPORTED, "softmax_loss: dlogits dtype");
     TBI_CUDA_LAUNCH_CHECK("softmax_loss");
+    return TBI_OK;
+}
+
+extern "C" int tbi_softmax_loss_fwd_bwd_taps(int dlogits_dtype, int n, int h, int w, int nc, const tbi_view* ytaps, const float* bias,
+                                             const float* y, float* probs, float* loss_map, int32_t* correct, void* dlogits,
+                                             int dlogits_cstride, void* stream) {
+    const int dl_cs = dlogits_cstride > 0 ? dlogits_cstride : nc;
+    TBI_CHECK(dl_cs >= nc, TBI_ERR_BAD_SHAPE, "softmax_loss_taps: dlogits_cstride %d < num_class %d", dl_cs, nc);
+    TBI_CHECK(nc >= 3 && nc <= 4, TBI_ERR_UNSUPPORTED, "softmax_loss_taps: num_class %d", nc);
+    TBI_CHECK((h % 2) == 0 && (w % 2) == 0 && ytaps && ytaps->ptr && ytaps->h == h / 2 && ytaps->w == w / 2 && ytaps->c >= 16 * nc && ytaps->coff == 0,
+              TBI_ERR_BAD_SHAPE, "softmax_loss_taps: Y must be fp32 [n, h/2, w/2, >= 16*nc] for an [n, h, w] output grid");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int hw = h * w;
+    const unsigned g = (hw + 31) / 32;
+    const float* yt = (const float*)ytaps->ptr;
+    if (dlogits_dtype == TBI_F32) {
+        if (nc == 3) softmax_loss_kernel<3, float, true><<<g, 32 * SL_J, 0, s>>>(n, hw, nullptr, y, probs, loss_map, correct, (float*)dlogits, dl_cs, yt, ytaps->cstride, bias, w);
+        else         softmax_loss_kernel<4, float, true><<<g, 32 * SL_J, 0, s>>>(n, hw, nullptr, y, probs, loss_map, correct, (float*)dlogits, dl_cs, yt, ytaps->cstride, bias, w);
+    } else if (dlogits_dtype == TBI_BF16) {
+        if (nc == 3) softmax_loss_kernel<3, __nv_bfloat16, true><<<g, 32 * SL_J, 0, s>>>(n, hw, nullptr, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs, yt, ytaps->cstride, bias, w);
+        else         softmax_loss_kernel<4, __nv_bfloat16, true><<<g, 32 * SL_J, 0, s>>>(n, hw, nullptr, y, probs, loss_map, correct, (__nv_bfloat16*)dlogits, dl_cs, yt, ytaps->cstride, bias, w);
+    } else return tbi_set_error(TBI_ERR_UNSUPPORTED, "softmax_loss_taps: dlogits dtype");
+    TBI_CUDA_LAUNCH_CHECK("softmax_loss_taps");
     return TBI_OK;
 }
 

@@ -582,13 +582,22 @@ class Engine:
             gf.cin_g = self.head.cin; gf.cout_g = self.head_yc; gf.src[0] = view(self.up[4]); gf.src[1] = view(self.pool[0]); gf.in_stride = 1; gf.ntaps = 1
             gf.w = _ptr(self.head_wf); gf.epi = epi(out=view(self.head_y), out_f32=int(self.head_y.dtype == torch.float32))
             self.prog_fwd.append((L.tbi_tapgemm_run, (C.byref(gf),)))
-            self.prog_fwd.append((L.tbi_convt_scatter_y, (F32 if self.head_y.dtype == torch.float32 else BF16, n, H // 2, W // 2, 4, self.num_class, bref(view(self.head_y)),
-                                                          _ptr(self.packed[self.head.name]["fbias"]), bref(view(self.logits)))))
+            # fp32 tap products: the loss kernel forms the logits itself (tbi_softmax_loss_fwd_bwd_taps) -- the 4-tap scatter launch
+            # and the [N,H,W,3] fp32 logits round trip disappear (80 + 68 us -> one kernel; TBI_HEAD_FUSED_LOSS=0 keeps the scatter)
+            self.head_fused_loss = self.head_y.dtype == torch.float32 and os.environ.get("TBI_HEAD_FUSED_LOSS", "1") != "0"
+            if not self.head_fused_loss:
+                self.prog_fwd.append((L.tbi_convt_scatter_y, (F32 if self.head_y.dtype == torch.float32 else BF16, n, H // 2, W // 2, 4, self.num_class, bref(view(self.head_y)),
+                                                              _ptr(self.packed[self.head.name]["fbias"]), bref(view(self.logits)))))
         else:
+            self.head_fused_loss = False
             conv_fwd(self.head, H // 2, W // 2, view(self.up[4]), view(self.pool[0]), epi(out=view(self.logits), out_f32=1))
         # ---------------- loss ----------------
-        self.prog_loss.append((L.tbi_softmax_loss_fwd_bwd, (dt, n, H, W, self.num_class, _ptr(self.logits), _ptr(self.y_in), _ptr(self.probs),
-                                                            _ptr(self.loss_map), _ptr(self.correct), _ptr(self.dlogits), self.dl_c)))
+        if self.head_fused_loss:
+            self.prog_loss.append((L.tbi_softmax_loss_fwd_bwd_taps, (dt, n, H, W, self.num_class, bref(view(self.head_y)), _ptr(self.packed[self.head.name]["fbias"]),
+                                                                     _ptr(self.y_in), _ptr(self.probs), _ptr(self.loss_map), _ptr(self.correct), _ptr(self.dlogits), self.dl_c)))
+        else:
+            self.prog_loss.append((L.tbi_softmax_loss_fwd_bwd, (dt, n, H, W, self.num_class, _ptr(self.logits), _ptr(self.y_in), _ptr(self.probs),
+                                                                _ptr(self.loss_map), _ptr(self.correct), _ptr(self.dlogits), self.dl_c)))
         # ---------------- backward ----------------
         # head: d(up4) gets ReLU' of up4 (no dropout on upsample_4); d(pool[0]) plain write
         head_epi = epi(out=view(self.dup[4]), dact=ACT_RELU, dact_ref=view(self.up[4]), split_c=self.ups[4]["out"], out2=view(self.dpool[0]))

@@ -292,6 +292,21 @@ def softmax_loss(logits, y, dlogits_dtype=torch.float32):
     return probs, loss, correct, dlog
 
 
+def softmax_loss_from_taps(ytaps, bias, y, dlogits_dtype=torch.float32):
+    """the same with the logits formed in the kernel from the head's tap products ytaps fp32 [n, h/2, w/2, 16*nc]
+    (column (ky*4+kx)*nc + c) + bias: tbi_softmax_loss_fwd_bwd_taps; y = labels [n, h, w, nc]"""
+    L = _lib.lib()
+    n, h, w, nc = y.shape
+    dev = y.device
+    probs = torch.empty(n, h, w, nc, dtype=torch.float32, device=dev)
+    loss = torch.empty(h, w, dtype=torch.float32, device=dev)
+    correct = torch.zeros(1, dtype=torch.int32, device=dev)
+    dlog = torch.empty(n, h, w, nc, dtype=dlogits_dtype, device=dev)
+    check(L.tbi_softmax_loss_fwd_bwd_taps(F32 if dlogits_dtype == torch.float32 else BF16, n, h, w, nc, _vp(view(ytaps)), _p(bias), _p(y), _p(probs),
+                                          _p(loss), _p(correct), _p(dlog), nc, _st()), "softmax_loss_taps")
+    return probs, loss, correct, dlog
+
+
 def adam_step(p, g, m, v, step_count, lr, b1=0.9, b2=0.999, eps=1e-7, grad_scale=1.0):
     L = _lib.lib()
     check(L.tbi_adam_multi(p.numel(), _p(p), _p(g), _p(m), _p(v), _p(step_count), lr, b1, b2, eps, grad_scale, _st()), "adam")
