@@ -74,10 +74,10 @@ def test_plan_buckets_at_named_boundaries():
     assert plan_buckets_at(marks, 1000, (700, 100)) == [(5, 700, 1000), (12, 100, 700), (20, 0, 100)]
     assert plan_buckets_at(marks, 1000, (800,)) == [(5, 800, 1000), (20, 0, 800)]           # a cut between marks waits for the next mark
     assert plan_buckets_at(marks, 1000, ()) == [(20, 0, 1000)]
-    # the engine's cuts: decoder | two deepest encoder stages | rest, tiling the flat buffer
+    # the engine's cut: [decoder + the two deepest encoder stages] | rest, tiling the flat buffer (swept on 2 GPUs, engine.py)
     e = Engine(256, 256, 1, 3, 3, 2, 1, layout_only=True)
-    hi, lo = e.bucket_cuts
-    assert 0 < lo < hi < e.P.total and (e.P.total - hi) * 4 > 80 << 20 and lo * 4 < 4 << 20
+    cut, = e.bucket_cuts
+    assert 0 < cut < e.P.total and (e.P.total - cut) * 4 > 95 << 20 and cut * 4 < 8 << 20
 
 
 def _free_port():

@@ -201,10 +201,15 @@ class Engine:
             self.ups.append(dict(layer=up, drop=drop, cin=cin, out=out))
             cin = out + SKIP_C[4 - i]
         self.head = add(ConvLayer("f_tran", "convt", 4, cin, self.num_class, keras=[("f_tran", 0, self.num_class)]))
-        # all-reduce bucket boundaries for data parallelism (parallel.GradSync), as flat offsets: [upsample_0 .. head] (~85 MiB,
-        # final once upsample_0's weight gradient is done, a little over half way through the backward), [conv3_2, conv4_1]
-        # (~17 MiB), and the rest (~3 MiB) at the end of the backward
-        self.bucket_cuts = (self.P.specs["upsample_0/w"].offset, self.P.specs["conv3_2/c1/w"].offset)
+        # all-reduce bucket boundary for data parallelism (parallel.GradSync), as a flat offset: [conv3_2 .. head] (~100 MiB: the
+        # decoder and the two deepest encoder stages, final ~70 % of the way through the backward) and the rest (~5 MiB) at the
+        # end.  Measured on 2 x B200 (step 6.94 ms on one GPU): this single cut 7.16 ms; cut at conv4_1 7.18; at conv3_1 7.22; no
+        # cut (one all-reduce after the backward, fully exposed) 7.21; the earlier three buckets [upsample_0 | conv3_2 | rest] 7.28
+        # -- every boundary also joins the weight-gradient side stream into the main stream, and the NCCL kernel costs the
+        # persistent compute kernels about as much time as it overlaps, so fewer boundaries win.
+        self.bucket_cuts = (self.P.specs["conv3_2/c1/w"].offset,)
+        if os.environ.get("TBI_BUCKET_CUTS"):                   # sweep knob: comma-separated variable names (first variable of each later bucket)
+            self.bucket_cuts = tuple(self.P.specs[nm].offset for nm in os.environ["TBI_BUCKET_CUTS"].split(","))
 
     def _alloc_params(self, seed):
         dev = self.device

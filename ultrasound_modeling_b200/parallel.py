@@ -182,10 +182,10 @@ class GradSync:
         if self._plan_key != key:
             cuts = getattr(engine, "bucket_cuts", None)
             if cuts and os.environ.get("TBI_BUCKET_MB") is None:
-                # boundaries where the backward's TIMELINE makes them free (Engine.bucket_cuts): the decoder's transposed convs
-                # hold ~80 % of the gradient bytes and are final after ~55 % of the backward, the two deepest encoder stages
-                # most of the rest; what is left for the end of the backward (the wide, slow, nearly parameter-free
-                # full-resolution layers) is a few MB, so the exposed tail all-reduce is short
+                # boundaries chosen on the backward's TIMELINE (Engine.bucket_cuts, measured there): the decoder's transposed convs
+                # and the two deepest encoder stages hold ~95 % of the gradient bytes and are final ~70 % of the way through the
+                # backward; what is left for the end (the wide, slow, nearly parameter-free full-resolution layers) is a few
+                # MB, so the exposed tail all-reduce is short
                 self._plan = plan_buckets_at(engine.bwd_marks, engine.P.total, cuts)
             else:
                 self._plan = plan_buckets(engine.bwd_marks, engine.P.total, self.bucket_elems)
