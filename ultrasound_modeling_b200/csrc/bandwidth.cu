@@ -160,9 +160,15 @@ __global__ void __launch_bounds__(256) convt_gather4_bf16_kernel(int n, int h, i
                 for (int c = 0; c < COUT; ++c) rec[tap * COUT + c] = vv[c];
             }
         }
-        uint4* dst = reinterpret_cast<uint4*>((__nv_bfloat16*)g.ptr + view_off(g, b, y, x, 0));
+        // four 32-byte stores (the record is 128-byte aligned): whole sectors, where eight 16-byte stores wrote every sector in two halves
+        char* dst = reinterpret_cast<char*>((__nv_bfloat16*)g.ptr + view_off(g, b, y, x, 0));
+        const uint4* r4 = reinterpret_cast<const uint4*>(rec);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = reinterpret_cast<const uint4*>(rec)[q];
+        for (int q = 0; q < 4; ++q) {
+            const uint4 a = r4[2 * q], c = r4[2 * q + 1];
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + 32 * q), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+                         "r"(c.x), "r"(c.y), "r"(c.z), "r"(c.w) : "memory");
+        }
     }
 }
 
@@ -1062,7 +1068,7 @@ extern "C" int tbi_convt_gather_dz(int dtype, int n, int h, int w, int ksize, in
     const unsigned gr = grid_for((long long)n * h * w * ksize * ksize, 256);
     const int pad = ksize == 4 ? 1 : 0;
     if (dtype == TBI_BF16 && ksize == 4 && cout <= 4 && dz->c >= 4 && dz->cstride % 4 == 0 && dz->coff % 4 == 0 && ((uintptr_t)dz->ptr & 7) == 0 &&
-        g->c == 64 && g->cstride == 64 && g->coff == 0 && ((uintptr_t)g->ptr & 15) == 0) {
+        g->c == 64 && g->cstride == 64 && g->coff == 0 && ((uintptr_t)g->ptr & 31) == 0) {
         const unsigned gg = grid_for((long long)n * h * w, 256);
         switch (cout) {
             case 1: convt_gather4_bf16_kernel<1><<<gg, 256, 0, s>>>(n, h, w, *dz, *g); break;
