@@ -11,6 +11,15 @@
 //   * CTAs are persistent (grid = resident CTAs, static round-robin over tiles, N-tile fastest so
 //     neighbouring CTAs hit the same halo in L2); two TMEM accumulator buffers let the epilogue of tile
 //     i run under the TMA/MMA main loop of tile i+1; separate A (halo) and B (weights) smem rings.
+//   * schedules on top of that (chosen per launch on the host, tbi_tapgemm_halo): STREAMED weights (one B stage per chunk and tap),
+//     PAIR (cta_group::2: a cluster of two CTAs computes a 256 x 128 tile, each CTA streams half of every weight stage),
+//     RESIDENT (a CTA keeps one N tile's whole weight slab in shared memory and walks pixel tiles), ALL-SLABS (a resident CTA
+//     keeps EVERY N tile's slab and runs one accumulator per slab against each halo: one-chunk, all-epilogue GEMMs);
+//   * the epilogue's side inputs (act' reference, residual, skip-gradient accumulator) are requested by the PRODUCER thread as L2
+//     prefetch boxes (cp.async.bulk.prefetch.tensor) one tile ahead of the epilogue that reads them row by row;
+//   * nothing in the role loops may touch local memory: with ~208 KB of shared memory per SM the L1 is a few KB and a spill
+//     reload is an L2 round trip on the MMA -> epilogue -> MMA chain (profiles/r2_ncu_local_memory.md) -- iteration constants
+//     come from the kernel parameters, per-CTA constants are re-read from shared memory, the row context is two registers.
 // Warp roles (320 threads): warps 0..7 epilogue (two per TMEM lane quadrant), warp 8 TMA producer, warp 9 MMA issuer + TMEM owner
 // (highest ids = highest scheduler priority for the two single-issuer warps).
 #include "tbi_common.cuh"
